@@ -1,0 +1,199 @@
+/*
+ * adder_b200.h — C ABI of the B200-native framed→ADΔER per-pixel transcode path.
+ *
+ * This is the drop-in boundary for ONE hot path of ac-freeman/adder-codec-rs:
+ *   Framed::consume            adder-codec-rs/src/transcoder/source/framed.rs:127-157
+ *   Video::integrate_matrix    adder-codec-rs/src/transcoder/source/video.rs:651-778
+ *   integrate_for_px           adder-codec-rs/src/transcoder/source/video.rs:1317-1380
+ *   PixelArena::*              adder-codec-rs/src/transcoder/event_pixel_tree.rs:68-532
+ *   u8::get_frame_value        adder-codec-rs/src/framer/scale_intensity.rs:58-104
+ *
+ * The reference has no FFI of its own (it is all Rust); the entry points below
+ * are what a Rust `extern "C"` block inside `Video<W>` would bind when
+ * `event_pixel_trees: Array3<PixelArena>` (video.rs:325) is replaced by an opaque device handle.
+ * INTEGRATION.md shows that binding.  Every function cites the reference item it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; nothing unwinds across the boundary; every call returns an
+ *    `adder_status` (0 = ok).  `adder_b200_last_error()` gives a thread-local message.
+ *  - a handle is NOT thread-safe (mirrors `&mut self` on Source::consume, video.rs:1421).
+ *  - the library owns all device state and one CUDA stream per handle.  There is no CPU fallback:
+ *    without a usable CUDA device `adder_b200_video_create` fails with ADDER_ERR_NO_DEVICE.
+ */
+#ifndef ADDER_B200_H
+#define ADDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADDER_B200_ABI_VERSION 1
+
+/* ---- constants: adder-codec-core/src/lib.rs:181-193 ------------------------------------------ */
+#define ADDER_D_MAX 127u              /* D_MAX */
+#define ADDER_D_ZERO_INTEGRATION 128u /* D_ZERO_INTEGRATION */
+#define ADDER_D_NO_EVENT 253u         /* D_NO_EVENT */
+#define ADDER_D_EMPTY 255u            /* D_EMPTY */
+#define ADDER_C_NONE 0xFFu            /* Coord.c == None (single-channel plane), lib.rs:263-274 */
+
+/* ---- Event: adder-codec-core/src/lib.rs:371-377 ----------------------------------------------
+ * The Rust `Event` is `repr(packed)` with an `Option<u8>` inside, which is not a stable ABI, so
+ * the boundary uses this defined 12-byte little-endian record and the Rust shim maps it to
+ * `Event { coord: Coord { x, y, c }, d, t }` (c == ADDER_C_NONE  <=>  None).                    */
+typedef struct adder_event {
+  uint16_t x;
+  uint16_t y;
+  uint8_t c; /* channel, or ADDER_C_NONE when the plane has one channel */
+  uint8_t d;
+  uint16_t reserved; /* always 0 */
+  uint32_t t;
+} adder_event_t;
+
+typedef enum adder_status {
+  ADDER_OK = 0,
+  ADDER_ERR_BAD_PARAMS = 1,   /* SourceError::BadParams, video.rs:55-122 */
+  ADDER_ERR_NO_DEVICE = 2,    /* no CUDA device / driver: the product path has no CPU fallback */
+  ADDER_ERR_CUDA = 3,         /* a CUDA runtime call failed; see adder_b200_last_error() */
+  ADDER_ERR_CAPACITY = 4,     /* caller's event buffer too small; *n_events holds the need */
+  ADDER_ERR_ARENA_DEPTH = 5,  /* a pixel's node stack outgrew the allocated depth
+                                 (reference: panic "Infinite loop detected", event_pixel_tree.rs:387) */
+  ADDER_ERR_UNSUPPORTED = 6,  /* e.g. Mode::Continuous on the GPU path (only FramePerfect is in scope) */
+  ADDER_ERR_INTERNAL = 7,     /* a state invariant the kernel relies on was violated */
+  ADDER_ERR_NOMEM = 8
+} adder_status;
+
+/* Mode: adder-codec-core/src/lib.rs:196-205 */
+typedef enum adder_pixel_tree_mode { ADDER_MODE_FRAME_PERFECT = 0, ADDER_MODE_CONTINUOUS = 1 } adder_pixel_tree_mode;
+/* PixelMultiMode: lib.rs:207-213 (default Collapse) */
+typedef enum adder_pixel_multi_mode { ADDER_MULTI_NORMAL = 0, ADDER_MULTI_COLLAPSE = 1 } adder_pixel_multi_mode;
+/* TimeMode: lib.rs:72-83 (default AbsoluteT); numeric values = the header's enum index */
+typedef enum adder_time_mode { ADDER_TIME_DELTA_T = 0, ADDER_TIME_ABSOLUTE_T = 1, ADDER_TIME_MIXED = 2 } adder_time_mode;
+/* FramedViewMode: video.rs:140-158 */
+typedef enum adder_view_mode { ADDER_VIEW_INTENSITY = 0, ADDER_VIEW_D = 1, ADDER_VIEW_DELTA_T = 2, ADDER_VIEW_SAE = 3 } adder_view_mode;
+
+/* CrfParameters: adder-codec-core/src/codec/rate_controller.rs:40-53 */
+typedef struct adder_crf_parameters {
+  uint8_t c_thresh_baseline;
+  uint8_t c_thresh_max;
+  uint8_t c_increase_velocity;
+  uint8_t reserved;
+  uint16_t feature_c_radius;
+  uint16_t reserved2;
+} adder_crf_parameters_t;
+
+/* Opaque: stands for Video<W>.state + Video<W>.event_pixel_trees (video.rs:322-345). */
+typedef struct adder_b200_video adder_b200_video;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int adder_b200_abi_version(void);
+const char* adder_b200_last_error(void);
+/* Number of CUDA devices visible, or a negative adder_status. */
+int adder_b200_device_count(void);
+/* CRF table lookup: Crf::new, rate_controller.rs:55-70 (table :5-18). crf in 0..=9. */
+int adder_b200_crf_parameters(uint8_t crf, uint16_t plane_w, uint16_t plane_h, adder_crf_parameters_t* out);
+
+/* ---- construction: Video::new, video.rs:350-438 ----------------------------------------------
+ * All W*H*C pixels start as PixelArena::new(1.0, coord) (event_pixel_tree.rs:69-87): one fresh
+ * node, c_thresh 10, c_increase_counter 1, TimeMode::AbsoluteT.  Defaults as VideoState::default
+ * (video.rs:226-243): chunk_rows 1, in_interval_count 1, ref_time 255, delta_t_max 7650,
+ * multi-mode Collapse, CRF parameters of quality 3, view mode Intensity.
+ * `max_depth` = node-stack depth to allocate per pixel (0 = derive from delta_t_max/ref_time when
+ * first needed; at most 31, the reference's own iteration guard).                              */
+int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, int pixel_tree_mode,
+                            int device, uint32_t max_depth, adder_b200_video** out);
+void adder_b200_video_destroy(adder_b200_video* v);
+
+/* ---- builder / setters ------------------------------------------------------ */
+/* Video::chunk_rows, video.rs:473-481 */
+int adder_b200_video_chunk_rows(adder_b200_video* v, uint32_t chunk_rows);
+/* Video::time_parameters, video.rs:493-537.  time_mode < 0 means None (keep).  Like the reference,
+ * out-of-range values keep the old ones and still return ADDER_OK; *applied (may be NULL) says
+ * which happened.  The delta_t_max % ref_time check is the CALLER's (framed.rs:100-109, :223-229). */
+int adder_b200_video_time_parameters(adder_b200_video* v, uint32_t tps, uint32_t ref_time,
+                                     uint32_t delta_t_max, int time_mode, int* applied);
+/* Side effects of Video::write_out on the transcode state, video.rs:546-636:
+ * pixel_multi_mode (<0 = None -> Collapse) and per-pixel time_mode (<0 = None -> keep). */
+int adder_b200_video_write_out(adder_b200_video* v, int time_mode, int pixel_multi_mode);
+/* Video::update_crf, video.rs:1241-1251: parameters from the table, every px c_thresh=baseline, counter=0 */
+int adder_b200_video_update_crf(adder_b200_video* v, uint8_t crf);
+/* Video::update_quality_manual, video.rs:1264-1287 */
+int adder_b200_video_update_quality_manual(adder_b200_video* v, uint8_t c_thresh_baseline, uint8_t c_thresh_max,
+                                           uint32_t delta_t_max_multiplier, uint8_t c_increase_velocity,
+                                           float feature_c_radius);
+/* Video::update_delta_t_max, video.rs:819-822 */
+int adder_b200_video_update_delta_t_max(adder_b200_video* v, uint32_t delta_t_max);
+/* Video::c_thresh_pos / update_adder_thresh_pos (deprecated), video.rs:445-455, :842-851 */
+int adder_b200_video_c_thresh_pos(adder_b200_video* v, uint8_t c);
+/* The per-pixel write done by handle_roi (video.rs:865-881) and the feature radius reset
+ * (video.rs:1089-1104): c_thresh := value for x0..=x1, y0..=y1, all channels. */
+int adder_b200_video_set_c_thresh_rect(adder_b200_video* v, uint16_t x0, uint16_t y0, uint16_t x1, uint16_t y1,
+                                       uint8_t value);
+/* Video.instantaneous_view_mode, video.rs:331 */
+int adder_b200_video_set_view_mode(adder_b200_video* v, int view_mode);
+/* VideoState.in_interval_count, video.rs:203 (adder-viz zeroes it on restart, adder.rs:155-166) */
+int adder_b200_video_set_in_interval_count(adder_b200_video* v, uint32_t n);
+
+/* ---- getters ---------------------------------------------------------------------------------- */
+typedef struct adder_b200_video_info {
+  uint16_t width, height;
+  uint8_t channels;
+  uint8_t pixel_tree_mode, pixel_multi_mode, time_mode, view_mode;
+  uint8_t reserved[3];
+  uint32_t chunk_rows, n_chunks;
+  uint32_t in_interval_count, tps, ref_time, delta_t_max;
+  adder_crf_parameters_t crf;
+  uint32_t max_depth;        /* allocated node-stack depth */
+  uint32_t device;
+  uint64_t state_bytes;      /* device bytes held for per-pixel state */
+  uint64_t events_capacity;  /* device event-buffer capacity, records */
+} adder_b200_video_info_t;
+int adder_b200_video_get_info(const adder_b200_video* v, adder_b200_video_info_t* out);
+
+/* ---- the hot path: Video::integrate_matrix, video.rs:651-778 ---------------------------------
+ * Host-buffer form (what Framed::consume calls, framed.rs:131-134).
+ *   frame            H rows of W*C bytes, `row_pitch` bytes apart (row_pitch 0 = W*C)   [host]
+ *   time_spanned     ticks the frame spans (Framed passes ref_time as f32)
+ *   events_out       capacity `events_cap` records; receives this frame's events in the
+ *                    reference's order: chunk by chunk, raster (y,x,c) inside a chunk, each
+ *                    pixel's events contiguous in push order                              [host]
+ *   chunk_counts     n_chunks = ceil(H/chunk_rows) entries: events per chunk, i.e. the lengths of
+ *                    the reference's Vec<Vec<Event>> (driver.rs:566 needs exactly n_chunks) [host, may be NULL]
+ *   n_events         total events of the frame (set even on ADDER_ERR_CAPACITY)
+ * On ADDER_ERR_CAPACITY nothing is lost: the events stay on the device and
+ * adder_b200_video_fetch_events() re-reads them into a larger buffer.
+ * Effects kept from the reference: in_interval_count += 1 (video.rs:662); set_initial_d when
+ * in_interval_count == 0 (video.rs:656-658, :780-801); running_intensities updated (:713-730). */
+int adder_b200_video_integrate_matrix(adder_b200_video* v, const uint8_t* frame, size_t row_pitch,
+                                      float time_spanned, adder_event_t* events_out, size_t events_cap,
+                                      uint32_t* chunk_counts, uint64_t* n_events);
+/* Re-read the last frame's events (after ADDER_ERR_CAPACITY). */
+int adder_b200_video_fetch_events(adder_b200_video* v, adder_event_t* events_out, size_t events_cap,
+                                  uint32_t* chunk_counts, uint64_t* n_events);
+/* VideoState.running_intensities / Video.display_frame_features (video.rs:212, :328, :742):
+ * (H,W,C) u8, copied to `out` [host]. */
+int adder_b200_video_running_intensities(adder_b200_video* v, uint8_t* out);
+
+/* Device-resident form of the same step: frames already in HBM, events left in HBM.
+ *   d_frames         n_frames frames, each H*W*C bytes densely packed, `frame_stride` bytes apart [device]
+ *   d_events         device buffer; frame f's events start at d_events + f*events_stride       [device]
+ *   d_chunk_offsets  (n_chunks+1) u32 per frame: exclusive event offset of every chunk, last = total;
+ *                    frame f's row at d_chunk_offsets + f*(n_chunks+1)                     [device, may be NULL]
+ * Runs asynchronously on the handle's stream; call adder_b200_video_sync() to wait and collect status
+ * (capacity / depth overflows are reported there).  n_frames consecutive frames are processed in
+ * one submission, exactly as n_frames calls of integrate_matrix would. */
+int adder_b200_video_integrate_frames_device(adder_b200_video* v, const uint8_t* d_frames, size_t frame_stride,
+                                             uint32_t n_frames, float time_spanned, adder_event_t* d_events,
+                                             size_t events_stride, uint32_t* d_chunk_offsets);
+int adder_b200_video_sync(adder_b200_video* v);
+/* The CUDA stream (cudaStream_t) work is queued on, for event timing by the caller. */
+void* adder_b200_video_stream(adder_b200_video* v);
+/* Number of kernels this handle has launched so far. */
+uint64_t adder_b200_video_launch_count(const adder_b200_video* v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADDER_B200_H */
