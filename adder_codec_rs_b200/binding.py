@@ -1,0 +1,391 @@
+"""ctypes binding of libadder_b200.so (C ABI: include/adder_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libadder_b200.so")
+_CSRC = os.path.join(_HERE, "csrc")
+
+# adder_event_t (12 bytes, little-endian)
+EVENT_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("c", "u1"), ("d", "u1"), ("reserved", "<u2"), ("t", "<u4")])
+assert EVENT_DTYPE.itemsize == 12
+
+MODE_FRAME_PERFECT, MODE_CONTINUOUS = 0, 1
+MULTI_NORMAL, MULTI_COLLAPSE = 0, 1
+TIME_DELTA_T, TIME_ABSOLUTE_T, TIME_MIXED = 0, 1, 2
+VIEW_INTENSITY, VIEW_D, VIEW_DELTA_T, VIEW_SAE = 0, 1, 2, 3
+
+OK, ERR_BAD_PARAMS, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_ARENA_DEPTH, ERR_UNSUPPORTED, ERR_INTERNAL, ERR_NOMEM = range(9)
+_NAMES = ["OK", "BAD_PARAMS", "NO_DEVICE", "CUDA", "CAPACITY", "ARENA_DEPTH", "UNSUPPORTED", "INTERNAL", "NOMEM"]
+
+# every symbol include/adder_b200.h declares (tests check the built library exports all of them)
+SYMBOLS = [
+    "adder_b200_abi_version", "adder_b200_last_error", "adder_b200_device_count", "adder_b200_crf_parameters",
+    "adder_b200_video_create", "adder_b200_video_destroy", "adder_b200_video_chunk_rows",
+    "adder_b200_video_time_parameters", "adder_b200_video_write_out", "adder_b200_video_update_crf",
+    "adder_b200_video_update_quality_manual", "adder_b200_video_set_crf_parameters", "adder_b200_video_update_delta_t_max", "adder_b200_video_c_thresh_pos",
+    "adder_b200_video_set_c_thresh_rect", "adder_b200_video_set_view_mode", "adder_b200_video_set_in_interval_count",
+    "adder_b200_video_get_info", "adder_b200_video_integrate_matrix", "adder_b200_video_fetch_events",
+    "adder_b200_video_running_intensities", "adder_b200_video_integrate_frames_device", "adder_b200_video_sync",
+    "adder_b200_video_stream", "adder_b200_video_launch_count", "adder_b200_video_events_emitted",
+    "adder_b200_video_integrate_frames_host", "adder_b200_video_reset_state", "adder_b200_video_read_px",
+    "adder_b200_host_alloc", "adder_b200_host_free", "adder_b200_device_alloc", "adder_b200_device_free",
+    "adder_b200_copy_to_device", "adder_b200_copy_to_host", "adder_b200_video_timer_start",
+    "adder_b200_video_timer_stop", "adder_b200_synth_frames",
+]
+
+
+class AdderError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"adder_b200: {_NAMES[code] if 0 <= code < len(_NAMES) else code}: {msg}")
+        self.code = code
+
+
+class CrfParameters(C.Structure):
+    _fields_ = [("c_thresh_baseline", C.c_uint8), ("c_thresh_max", C.c_uint8), ("c_increase_velocity", C.c_uint8),
+                ("reserved", C.c_uint8), ("feature_c_radius", C.c_uint16), ("reserved2", C.c_uint16)]
+
+
+class VideoInfo(C.Structure):
+    _fields_ = [("width", C.c_uint16), ("height", C.c_uint16), ("channels", C.c_uint8), ("pixel_tree_mode", C.c_uint8),
+                ("pixel_multi_mode", C.c_uint8), ("time_mode", C.c_uint8), ("view_mode", C.c_uint8),
+                ("reserved", C.c_uint8 * 3), ("chunk_rows", C.c_uint32), ("n_chunks", C.c_uint32),
+                ("in_interval_count", C.c_uint32), ("tps", C.c_uint32), ("ref_time", C.c_uint32),
+                ("delta_t_max", C.c_uint32), ("crf", CrfParameters), ("max_depth", C.c_uint32), ("device", C.c_uint32),
+                ("state_bytes", C.c_uint64), ("events_capacity", C.c_uint64)]
+
+
+class PxNode(C.Structure):
+    _fields_ = [("integration", C.c_float), ("delta_t", C.c_float), ("best_delta_t", C.c_float), ("d", C.c_uint8),
+                ("best_d", C.c_uint8), ("has_best", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+class PxState(C.Structure):
+    _fields_ = [("last_fired_t", C.c_float), ("running_t", C.c_float), ("base_val", C.c_uint8), ("c_thresh", C.c_uint8),
+                ("c_increase_counter", C.c_uint8), ("length", C.c_uint8), ("dtm_reached", C.c_uint8),
+                ("popped_dtm", C.c_uint8), ("time_mode", C.c_uint8), ("reserved", C.c_uint8), ("nodes", PxNode * 31)]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libadder_b200.so for sm_100a with the committed recipe (csrc/Makefile)."""
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", ".h")) or f == "Makefile"]
+    deps.append(os.path.join(os.path.dirname(_HERE), "include", "adder_b200.h"))
+    stale = not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps)
+    if force or stale:
+        r = subprocess.run(["make", "-C", _CSRC] + (["-B"] if force else []), capture_output=True, text=True)
+        if verbose or r.returncode:
+            print(r.stdout, r.stderr)
+        if r.returncode:
+            raise RuntimeError("building libadder_b200.so failed")
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library.  Fails loudly when it is missing: there is no other implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise ImportError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the product has no CPU or PyTorch fallback)")
+    L = C.CDLL(_SO)
+    vp, u8, u16, u32, u64, f32, i32, sz = (C.c_void_p, C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64, C.c_float,
+                                           C.c_int, C.c_size_t)
+    P = C.POINTER
+    sig = {
+        "adder_b200_abi_version": (i32, []),
+        "adder_b200_last_error": (C.c_char_p, []),
+        "adder_b200_device_count": (i32, []),
+        "adder_b200_crf_parameters": (i32, [u8, u16, u16, P(CrfParameters)]),
+        "adder_b200_video_create": (i32, [u16, u16, u8, i32, i32, u32, P(vp)]),
+        "adder_b200_video_destroy": (None, [vp]),
+        "adder_b200_video_chunk_rows": (i32, [vp, u32]),
+        "adder_b200_video_time_parameters": (i32, [vp, u32, u32, u32, i32, P(i32)]),
+        "adder_b200_video_write_out": (i32, [vp, i32, i32]),
+        "adder_b200_video_update_crf": (i32, [vp, u8]),
+        "adder_b200_video_update_quality_manual": (i32, [vp, u8, u8, u32, u8, f32]),
+        "adder_b200_video_set_crf_parameters": (i32, [vp, P(CrfParameters)]),
+        "adder_b200_video_update_delta_t_max": (i32, [vp, u32]),
+        "adder_b200_video_c_thresh_pos": (i32, [vp, u8]),
+        "adder_b200_video_set_c_thresh_rect": (i32, [vp, u16, u16, u16, u16, u8]),
+        "adder_b200_video_set_view_mode": (i32, [vp, i32]),
+        "adder_b200_video_set_in_interval_count": (i32, [vp, u32]),
+        "adder_b200_video_get_info": (i32, [vp, P(VideoInfo)]),
+        "adder_b200_video_integrate_matrix": (i32, [vp, vp, sz, f32, vp, sz, vp, P(u64)]),
+        "adder_b200_video_fetch_events": (i32, [vp, vp, sz, vp, P(u64)]),
+        "adder_b200_video_running_intensities": (i32, [vp, vp]),
+        "adder_b200_video_integrate_frames_device": (i32, [vp, vp, sz, u32, f32, vp, sz, vp]),
+        "adder_b200_video_sync": (i32, [vp]),
+        "adder_b200_video_stream": (vp, [vp]),
+        "adder_b200_video_launch_count": (u64, [vp]),
+        "adder_b200_video_events_emitted": (i32, [vp, P(u64)]),
+        "adder_b200_video_integrate_frames_host": (i32, [vp, vp, sz, u32, f32, vp, sz, vp, vp, P(u64), P(u32)]),
+        "adder_b200_video_reset_state": (i32, [vp]),
+        "adder_b200_video_read_px": (i32, [vp, sz, P(PxState)]),
+        "adder_b200_host_alloc": (i32, [sz, P(vp)]),
+        "adder_b200_host_free": (i32, [vp]),
+        "adder_b200_device_alloc": (i32, [vp, sz, P(vp)]),
+        "adder_b200_device_free": (i32, [vp, vp]),
+        "adder_b200_copy_to_device": (i32, [vp, vp, vp, sz]),
+        "adder_b200_copy_to_host": (i32, [vp, vp, vp, sz]),
+        "adder_b200_video_timer_start": (i32, [vp]),
+        "adder_b200_video_timer_stop": (i32, [vp, P(f32)]),
+        "adder_b200_synth_frames": (i32, [vp, vp, sz, u32, u32, i32, u64]),
+    }
+    assert set(sig) == set(SYMBOLS)
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise AdderError(rc, lib().adder_b200_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    n = lib().adder_b200_device_count()
+    return max(n, 0)
+
+
+def crf_parameters(crf, w, h) -> CrfParameters:
+    out = CrfParameters()
+    _check(lib().adder_b200_crf_parameters(crf, w, h, C.byref(out)))
+    return out
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.L = lib()
+        self.p = C.c_void_p()
+        _check(self.L.adder_b200_host_alloc(nbytes, C.byref(self.p)))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            self.L.adder_b200_host_free(self.p)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """A numpy array over page-locked host memory (adder_b200_host_alloc); freed with the array."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    owner = _Pinned(max(n, 1))
+    buf = (C.c_uint8 * max(n, 1)).from_address(owner.p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+    return _PinnedArray(arr, owner)
+
+
+class _PinnedArray(np.ndarray):
+    def __new__(cls, arr, owner):
+        obj = arr.view(cls)
+        obj._owner = owner
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
+class DeviceBuffer:
+    """Device memory owned through the C ABI (no torch needed)."""
+
+    def __init__(self, video: "Video", nbytes: int):
+        self.video = video
+        self.nbytes = nbytes
+        self.p = C.c_void_p()
+        _check(video.L.adder_b200_device_alloc(video.v, nbytes, C.byref(self.p)))
+
+    @property
+    def ptr(self):
+        return self.p.value
+
+    def to_host(self, dtype=np.uint8, nbytes=None, offset=0) -> np.ndarray:
+        nbytes = self.nbytes - offset if nbytes is None else nbytes
+        out = np.empty(nbytes, dtype=np.uint8)
+        if nbytes:
+            _check(self.video.L.adder_b200_copy_to_host(self.video.v, out.ctypes.data, self.p.value + offset, nbytes))
+        return out.view(dtype)
+
+    def from_host(self, arr: np.ndarray, offset=0):
+        arr = np.ascontiguousarray(arr)
+        _check(self.video.L.adder_b200_copy_to_device(self.video.v, self.p.value + offset, arr.ctypes.data, arr.nbytes))
+
+    def free(self):
+        if self.p:
+            self.video.L.adder_b200_device_free(self.video.v, self.p)
+            self.p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Video:
+    """Mirrors the transcode-state part of the reference's Video<W> (video.rs:322-345): same method
+    names and argument meaning as the builder/setters of video.rs and the oracle's Video."""
+
+    def __init__(self, width, height, channels, pixel_tree_mode=MODE_FRAME_PERFECT, device=0, max_depth=0):
+        self.L = lib()
+        self.w, self.h, self.c = width, height, channels
+        self.v = C.c_void_p()
+        _check(self.L.adder_b200_video_create(width, height, channels, pixel_tree_mode, device, max_depth, C.byref(self.v)))
+
+    def close(self):
+        if getattr(self, "v", None):
+            self.L.adder_b200_video_destroy(self.v)
+            self.v = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- builder / setters ----
+    def chunk_rows(self, n):
+        _check(self.L.adder_b200_video_chunk_rows(self.v, n))
+        return self
+
+    def time_parameters(self, tps, ref_time, delta_t_max, time_mode=None) -> bool:
+        applied = C.c_int()
+        _check(self.L.adder_b200_video_time_parameters(self.v, tps, ref_time, delta_t_max, -1 if time_mode is None else time_mode, C.byref(applied)))
+        return bool(applied.value)
+
+    def write_out(self, time_mode=None, pixel_multi_mode=None):
+        _check(self.L.adder_b200_video_write_out(self.v, -1 if time_mode is None else time_mode, -1 if pixel_multi_mode is None else pixel_multi_mode))
+
+    def update_crf(self, crf):
+        _check(self.L.adder_b200_video_update_crf(self.v, crf))
+
+    def update_quality_manual(self, c_base, c_max, dtm_mult, velocity, radius=0.0):
+        _check(self.L.adder_b200_video_update_quality_manual(self.v, c_base, c_max, dtm_mult, velocity, radius))
+
+    def set_crf_parameters(self, c_base, c_max, velocity, radius=0):
+        p = CrfParameters(c_base, c_max, velocity, 0, radius, 0)
+        _check(self.L.adder_b200_video_set_crf_parameters(self.v, C.byref(p)))
+
+    def update_delta_t_max(self, dtm):
+        _check(self.L.adder_b200_video_update_delta_t_max(self.v, dtm))
+
+    def c_thresh_pos(self, c):
+        _check(self.L.adder_b200_video_c_thresh_pos(self.v, c))
+
+    def set_c_thresh_rect(self, x0, y0, x1, y1, value):
+        _check(self.L.adder_b200_video_set_c_thresh_rect(self.v, x0, y0, x1, y1, value))
+
+    def set_view_mode(self, m):
+        _check(self.L.adder_b200_video_set_view_mode(self.v, m))
+
+    def set_in_interval_count(self, n):
+        _check(self.L.adder_b200_video_set_in_interval_count(self.v, n))
+
+    def reset_state(self):
+        _check(self.L.adder_b200_video_reset_state(self.v))
+
+    # ---- getters ----
+    def info(self) -> VideoInfo:
+        out = VideoInfo()
+        _check(self.L.adder_b200_video_get_info(self.v, C.byref(out)))
+        return out
+
+    @property
+    def in_interval_count(self):
+        return self.info().in_interval_count
+
+    @property
+    def n_chunks(self):
+        return self.info().n_chunks
+
+    @property
+    def launch_count(self) -> int:
+        return self.L.adder_b200_video_launch_count(self.v)
+
+    def events_emitted(self) -> int:
+        out = C.c_uint64()
+        _check(self.L.adder_b200_video_events_emitted(self.v, C.byref(out)))
+        return out.value
+
+    def px(self, index) -> PxState:
+        out = PxState()
+        _check(self.L.adder_b200_video_read_px(self.v, index, C.byref(out)))
+        return out
+
+    def px_dict(self, index) -> dict:
+        s = self.px(index)
+        return dict(last_fired_t=s.last_fired_t, base_val=s.base_val, c_thresh=s.c_thresh,
+                    c_increase_counter=s.c_increase_counter, length=s.length, popped_dtm=s.popped_dtm,
+                    nodes=[dict(integration=n.integration, delta_t=n.delta_t, best_delta_t=n.best_delta_t, d=n.d,
+                                best_d=n.best_d, has_best=n.has_best) for n in list(s.nodes)[:s.length]])
+
+    # ---- the hot path ----
+    def integrate_matrix(self, frame: np.ndarray, time_spanned: float, events_out: np.ndarray | None = None):
+        """One frame, host buffers (Framed::consume's call, framed.rs:131).  Returns (events, chunk_counts)."""
+        frame = np.ascontiguousarray(frame, dtype=np.uint8)
+        assert frame.size == self.w * self.h * self.c
+        counts = np.empty(self.n_chunks, dtype=np.uint32)
+        n = C.c_uint64()
+        if events_out is None:
+            events_out = np.empty(self.w * self.h * self.c * 2, dtype=EVENT_DTYPE)
+        rc = self.L.adder_b200_video_integrate_matrix(self.v, frame.ctypes.data, 0, time_spanned, events_out.ctypes.data,
+                                                      len(events_out), counts.ctypes.data, C.byref(n))
+        if rc == ERR_CAPACITY:  # nothing is lost: re-read into a buffer of the reported size
+            events_out = np.empty(n.value, dtype=EVENT_DTYPE)
+            rc = self.L.adder_b200_video_fetch_events(self.v, events_out.ctypes.data, len(events_out), counts.ctypes.data, C.byref(n))
+        _check(rc)
+        return events_out[: n.value], counts
+
+    def integrate_frames_host(self, frames: np.ndarray, time_spanned: float, events_out: np.ndarray):
+        """n frames, host buffers, copies and kernels pipelined.  Returns (events, frame_counts, chunk_counts)."""
+        assert frames.dtype == np.uint8 and frames.flags.c_contiguous
+        nf = frames.shape[0]
+        assert frames[0].size == self.w * self.h * self.c
+        fc = np.zeros(nf, dtype=np.uint64)
+        cc = np.zeros((nf, self.n_chunks), dtype=np.uint32)
+        n, done = C.c_uint64(), C.c_uint32()
+        rc = self.L.adder_b200_video_integrate_frames_host(self.v, frames.ctypes.data, frames[0].size, nf, time_spanned,
+                                                           events_out.ctypes.data, len(events_out), fc.ctypes.data,
+                                                           cc.ctypes.data, C.byref(n), C.byref(done))
+        _check(rc)
+        return events_out[: n.value], fc, cc
+
+    def running_intensities(self) -> np.ndarray:
+        out = np.empty((self.h, self.w, self.c), dtype=np.uint8)
+        _check(self.L.adder_b200_video_running_intensities(self.v, out.ctypes.data))
+        return out
+
+    # ---- device-resident form ----
+    def device_alloc(self, nbytes) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def synth_frames(self, dbuf: DeviceBuffer, f0, n_frames, kind, seed, frame_stride=0, offset=0):
+        _check(self.L.adder_b200_synth_frames(self.v, dbuf.ptr + offset, frame_stride, f0, n_frames, kind, seed))
+
+    def integrate_frames_device(self, d_frames, frame_stride, n_frames, time_spanned, d_events, events_stride, d_chunk_offsets=None):
+        _check(self.L.adder_b200_video_integrate_frames_device(self.v, d_frames, frame_stride, n_frames, time_spanned,
+                                                               d_events, events_stride, d_chunk_offsets))
+
+    def sync(self):
+        _check(self.L.adder_b200_video_sync(self.v))
+
+    def timer_start(self):
+        _check(self.L.adder_b200_video_timer_start(self.v))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _check(self.L.adder_b200_video_timer_stop(self.v, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,820 @@
+/*
+ * adder_b200.cu — C ABI (include/adder_b200.h) over the sm_100a kernels in px_kernel.cuh.
+ *
+ * Host-side counterpart of Video<W>'s transcode state (adder-codec-rs/src/transcoder/source/video.rs:
+ * 186-243 VideoState, :322-345 Video, :350-438 new, :493-537 time_parameters, :1241-1287 quality
+ * setters, :651-778 integrate_matrix).  No CPU fallback: every entry point that touches pixel state
+ * needs a CUDA device and fails with ADDER_ERR_NO_DEVICE / ADDER_ERR_CUDA otherwise.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/adder_b200.h"
+#include "px_kernel.cuh"
+#include "synth.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(_e == cudaErrorMemoryAllocation ? ADDER_ERR_NOMEM : ADDER_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(_e), __FILE__, __LINE__);                                    \
+  } while (0)
+
+/* CRF table, adder-codec-core/src/codec/rate_controller.rs:5-18:
+ * {c_thresh_baseline, c_thresh_max, c_increase_velocity, feature_c_radius_denom} */
+const float kCrf[10][4] = {
+    {0.0f, 0.0f, 10.0f, 1E-9f},        {0.0f, 1.0f, 9.0f, 1.0f / 12.0f},  {1.0f, 3.0f, 8.0f, 1.0f / 14.0f},
+    {2.0f, 7.0f, 7.0f, 1.0f / 15.0f},  {5.0f, 9.0f, 6.0f, 1.0f / 18.0f},  {6.0f, 10.0f, 5.0f, 1.0f / 20.0f},
+    {7.0f, 13.0f, 4.0f, 1.0f / 25.0f}, {8.0f, 16.0f, 3.0f, 1.0f / 30.0f}, {10.0f, 20.0f, 2.0f, 1.0f / 30.0f},
+    {15.0f, 25.0f, 1.0f, 1.0f / 30.0f},
+};
+
+void crf_lookup(uint8_t crf, uint16_t w, uint16_t h, adder_crf_parameters_t* out) { /* Crf::new :55-70 */
+  memset(out, 0, sizeof(*out));
+  if (crf > 9) crf = 9;
+  const uint16_t min_res = w < h ? w : h;
+  out->c_thresh_baseline = (uint8_t)kCrf[crf][0];
+  out->c_thresh_max = (uint8_t)kCrf[crf][1];
+  out->c_increase_velocity = (uint8_t)kCrf[crf][2];
+  const float r = kCrf[crf][3] * (float)min_res;
+  out->feature_c_radius = r >= 65535.0f ? 65535 : (uint16_t)r;
+}
+
+/* fast-math 0.1 `log2_raw` as published (the crate is not vendored in the reference, Cargo.toml:45):
+ * exponent + quadratic in the significand.  Only feeds FramedViewMode::D (scale_intensity.rs:89-91). */
+float log2_raw(float x) {
+  uint32_t bits;
+  memcpy(&bits, &x, 4);
+  const int exponent = (int)((bits >> 23) & 0xFF) - 127;
+  const uint32_t mb = (bits & 0x007FFFFFu) | 0x3F800000u;
+  float m;
+  memcpy(&m, &mb, 4);
+  volatile float t = (-1.0f / 3.0f) * m;
+  t = t + 2.0f;
+  t = t * m;
+  t = t + (-2.0f / 3.0f);
+  return (float)exponent + t;
+}
+
+uint32_t f32_as_u32(float x) { /* Rust `as u32` */
+  if (!(x > 0.0f)) return 0u;
+  if (x >= 4294967296.0f) return 0xFFFFFFFFu;
+  return (uint32_t)x;
+}
+
+constexpr int kRing = 3; /* host-form pipeline depth */
+
+}  // namespace
+
+struct adder_b200_video {
+  uint16_t w = 0, h = 0;
+  uint8_t c = 0;
+  int device = 0;
+  int tree_mode = ADDER_MODE_FRAME_PERFECT, multi_mode = ADDER_MULTI_COLLAPSE, time_mode = ADDER_TIME_ABSOLUTE_T,
+      view_mode = ADDER_VIEW_INTENSITY;
+  uint32_t chunk_rows = 1, n_chunks = 0, in_interval_count = 1, tps = 7650, ref_time = 255, delta_t_max = 7650;
+  adder_crf_parameters_t crf{};
+  uint32_t want_depth = 0; /* caller's max_depth (0 = derive) */
+  uint32_t depth = 0;      /* allocated */
+  float running_t = 0.0f;
+  uint32_t P = 0, n_tiles = 0;
+  uint64_t Ppad = 0;
+
+  uint2* d_hdr = nullptr;
+  uint4* d_nodes = nullptr;
+  uint8_t* d_running = nullptr;
+  unsigned long long* d_status = nullptr;
+  uint32_t* d_ticket = nullptr;
+  uint32_t* d_err = nullptr;
+  unsigned long long* d_total = nullptr;
+  uint32_t* h_err = nullptr; /* pinned */
+  unsigned long long* h_total = nullptr;
+
+  /* host-form resources (allocated on first use) */
+  uint8_t* d_frame[kRing] = {nullptr, nullptr, nullptr};
+  adder_event_t* d_events[kRing] = {nullptr, nullptr, nullptr};
+  uint32_t* d_chunk_off[kRing] = {nullptr, nullptr, nullptr};
+  uint32_t* h_chunk_off[kRing] = {nullptr, nullptr, nullptr}; /* pinned */
+  uint64_t events_capacity = 0;                               /* records per slot */
+  int last_slot = -1;                                         /* slot holding the last single-frame call's events */
+
+  cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
+  cudaEvent_t ev_in[kRing] = {}, ev_k[kRing] = {}, ev_out[kRing] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+  uint64_t launches = 0;
+  uint32_t epoch = 0, ticket_base = 0;
+};
+
+namespace {
+
+uint32_t derive_depth(const adder_b200_video* v) {
+  if (v->want_depth) return std::min<uint32_t>(v->want_depth, ADDER_MAX_DEPTH);
+  /* live nodes grow like log2 of the frames a pixel can integrate before Δt_max pops the root
+   * (7 at Δt_max/ref = 24, 11 at 4096); +6 leaves two levels of margin over the
+   * floor(log2)+4 bound observed there.  The kernel reports ADDER_DEVERR_DEPTH if it is ever exceeded. */
+  uint32_t ratio = v->delta_t_max / std::max<uint32_t>(v->ref_time, 1u);
+  uint32_t lg = 0;
+  while ((ratio >> (lg + 1)) != 0) lg++;
+  return std::min<uint32_t>(lg + 6u, ADDER_MAX_DEPTH);
+}
+
+int set_device(const adder_b200_video* v) {
+  CU(cudaSetDevice(v->device));
+  return ADDER_OK;
+}
+
+int ensure_depth(adder_b200_video* v, uint32_t need) {
+  if (need <= v->depth) return ADDER_OK;
+  uint4* nn = nullptr;
+  CU(cudaMalloc(&nn, (size_t)need * v->Ppad * sizeof(uint4)));
+  if (v->d_nodes) {
+    CU(cudaMemcpyAsync(nn, v->d_nodes, (size_t)v->depth * v->Ppad * sizeof(uint4), cudaMemcpyDeviceToDevice, v->stream));
+    CU(cudaStreamSynchronize(v->stream));
+    CU(cudaFree(v->d_nodes));
+  }
+  v->d_nodes = nn;
+  const bool first = v->depth == 0;
+  v->depth = need;
+  if (first) {
+    adder::init_state_kernel<<<(v->P + 255) / 256, 256, 0, v->stream>>>(v->d_hdr, v->d_nodes, v->d_running, v->P);
+    v->launches++;
+    CU(cudaGetLastError());
+  }
+  /* the host-form event buffers are sized for the worst case of this depth: drop them */
+  for (int s = 0; s < kRing; s++) {
+    if (v->d_events[s]) {
+      CU(cudaStreamSynchronize(v->stream_out));
+      CU(cudaFree(v->d_events[s]));
+      v->d_events[s] = nullptr;
+    }
+  }
+  v->events_capacity = 0;
+  return ADDER_OK;
+}
+
+int ensure_host_form(adder_b200_video* v) {
+  const uint64_t cap = (uint64_t)v->P * (v->depth + 2u); /* 1 + max(L,2) + 1 events per pixel at most, SURVEY §8(a) */
+  for (int s = 0; s < kRing; s++) {
+    if (!v->d_frame[s]) CU(cudaMalloc(&v->d_frame[s], v->P));
+    if (!v->d_events[s]) CU(cudaMalloc(&v->d_events[s], cap * sizeof(adder_event_t)));
+  }
+  v->events_capacity = cap;
+  return ADDER_OK;
+}
+
+int realloc_chunks(adder_b200_video* v) {
+  v->n_chunks = (v->h + v->chunk_rows - 1) / v->chunk_rows;
+  for (int s = 0; s < kRing; s++) {
+    if (v->d_chunk_off[s]) CU(cudaFree(v->d_chunk_off[s]));
+    if (v->h_chunk_off[s]) CU(cudaFreeHost(v->h_chunk_off[s]));
+    CU(cudaMalloc(&v->d_chunk_off[s], ((size_t)v->n_chunks + 1) * sizeof(uint32_t)));
+    CU(cudaHostAlloc(&v->h_chunk_off[s], ((size_t)v->n_chunks + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+  }
+  return ADDER_OK;
+}
+
+/* Queue one frame on `stream`.  d_frame: P dense bytes on the device. */
+int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_frame, float time_spanned,
+                 adder_event_t* d_events, uint64_t cap, uint32_t* d_chunk_off) {
+  if (v->tree_mode != ADDER_MODE_FRAME_PERFECT)
+    return fail(ADDER_ERR_UNSUPPORTED, "Mode::Continuous is not on the framed path (framed.rs:67 always builds FramePerfect)");
+  if (int rc = ensure_depth(v, derive_depth(v))) return rc;
+
+  if (v->in_interval_count == 0) { /* video.rs:656-658 */
+    adder::set_initial_d_kernel<<<(v->P + 255) / 256, 256, 0, stream>>>(v->d_hdr, v->d_nodes, d_frame, v->P);
+    v->launches++;
+  }
+  v->in_interval_count += 1; /* :662 */
+
+  if (v->epoch == 0x3FFFFFFFu) { /* epoch wrap: forget all status words */
+    CU(cudaMemsetAsync(v->d_status, 0, (size_t)v->n_tiles * sizeof(unsigned long long), stream));
+    v->epoch = 0;
+  }
+  v->epoch += 1;
+
+  adder::FrameArgs a{};
+  a.frame = d_frame;
+  a.hdr = v->d_hdr;
+  a.nodes = v->d_nodes;
+  a.level_stride = v->Ppad;
+  a.running = v->d_running;
+  a.ev_words = reinterpret_cast<uint32_t*>(d_events);
+  a.ev_cap = cap;
+  a.chunk_off = d_chunk_off;
+  a.tile_status = v->d_status;
+  a.ticket = v->d_ticket;
+  a.err = v->d_err;
+  a.total_events = v->d_total;
+  a.ticket_base = v->ticket_base;
+  a.epoch = v->epoch;
+  a.P = v->P;
+  a.n_tiles = v->n_tiles;
+  a.C = v->c;
+  a.WC = (uint32_t)v->w * v->c;
+  a.chunk_px = v->chunk_rows * a.WC;
+  a.n_chunks = v->n_chunks;
+  a.ecap = v->depth + 2u;
+  adder::PxParams& p = a.px;
+  p.depth = v->depth;
+  p.time = time_spanned;
+  p.running_t_prev = v->running_t;
+  v->running_t = v->running_t + time_spanned; /* event_pixel_tree.rs:337, the same f32 add for every pixel */
+  p.running_t = v->running_t;
+  p.dtm_f = (float)v->delta_t_max;
+  p.ref = v->ref_time;
+  p.dtm = v->delta_t_max;
+  p.c_max = v->crf.c_thresh_max;
+  p.vel_m1 = (uint8_t)(v->crf.c_increase_velocity - 1);
+  p.cnt_inc = (uint8_t)(f32_as_u32(time_spanned) / v->ref_time);
+  p.collapse = v->multi_mode == ADDER_MULTI_COLLAPSE;
+  p.abs_time = v->time_mode == ADDER_TIME_ABSOLUTE_T;
+  p.view_mode = (uint32_t)v->view_mode;
+  p.display = 1;
+  p.tpf = (double)v->ref_time;                                                  /* video.rs:672 */
+  p.practical_d_max = log2_raw(255.0f * (float)(v->delta_t_max / v->ref_time)); /* :668-670 */
+
+  const size_t smem = (size_t)a.ecap * ADDER_TILE_PX * 5u + adder::kStageRecords * 12u;
+  adder::integrate_frame_kernel<<<v->n_tiles, ADDER_TILE_PX, smem, stream>>>(a);
+  v->ticket_base += v->n_tiles;
+  v->launches++;
+  CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
+int map_deverr(uint32_t e) {
+  if (e & ADDER_DEVERR_INTERNAL) return fail(ADDER_ERR_INTERNAL, "a pixel's root was popped with no child (state invariant)");
+  if (e & ADDER_DEVERR_DEPTH)
+    return fail(ADDER_ERR_ARENA_DEPTH, "a pixel's node stack outgrew the allocated depth (create with a larger max_depth)");
+  if (e & ADDER_DEVERR_CAPACITY) return fail(ADDER_ERR_CAPACITY, "device event buffer too small: records beyond capacity were dropped");
+  return ADDER_OK;
+}
+
+/* Read and clear the device error word (after the stream has been synchronised up to the copy). */
+int collect_errors(adder_b200_video* v, cudaStream_t stream) {
+  CU(cudaMemcpyAsync(v->h_err, v->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  CU(cudaStreamSynchronize(stream));
+  const uint32_t e = *v->h_err;
+  if (e) CU(cudaMemsetAsync(v->d_err, 0, sizeof(uint32_t), stream));
+  return map_deverr(e);
+}
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return fail(ADDER_ERR_NOMEM, "host allocation failed");
+  } catch (...) {
+    return fail(ADDER_ERR_INTERNAL, "unexpected exception");
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int adder_b200_abi_version(void) { return ADDER_B200_ABI_VERSION; }
+const char* adder_b200_last_error(void) { return g_err; }
+
+int adder_b200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail(ADDER_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return -ADDER_ERR_NO_DEVICE;
+  }
+  return n;
+}
+
+int adder_b200_crf_parameters(uint8_t crf, uint16_t plane_w, uint16_t plane_h, adder_crf_parameters_t* out) {
+  if (!out || crf > 9) return fail(ADDER_ERR_BAD_PARAMS, "crf must be 0..=9");
+  crf_lookup(crf, plane_w, plane_h, out);
+  return ADDER_OK;
+}
+
+int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, int pixel_tree_mode, int device,
+                            uint32_t max_depth, adder_b200_video** out) {
+  return guarded([&]() -> int {
+    if (!out) return fail(ADDER_ERR_BAD_PARAMS, "out is NULL");
+    *out = nullptr;
+    if (width == 0 || height == 0 || channels == 0) /* PlaneSize::new, lib.rs:105-117 */
+      return fail(ADDER_ERR_BAD_PARAMS, "plane dimensions must be non-zero");
+    if (pixel_tree_mode != ADDER_MODE_FRAME_PERFECT && pixel_tree_mode != ADDER_MODE_CONTINUOUS)
+      return fail(ADDER_ERR_BAD_PARAMS, "unknown pixel_tree_mode");
+    const uint64_t P64 = (uint64_t)width * height * channels;
+    if (P64 * (ADDER_MAX_DEPTH + 2ull) >= (1ull << 32))
+      return fail(ADDER_ERR_BAD_PARAMS, "plane too large: per-frame event offsets are 32-bit");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      return fail(ADDER_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(ADDER_ERR_BAD_PARAMS, "device %d out of range (0..%d)", device, n - 1);
+
+    adder_b200_video* v = new adder_b200_video();
+    v->w = width;
+    v->h = height;
+    v->c = channels;
+    v->device = device;
+    v->tree_mode = pixel_tree_mode;
+    v->want_depth = max_depth;
+    crf_lookup(3, width, height, &v->crf); /* EncoderOptions::default -> Crf::new(None) -> quality 3 */
+    v->P = (uint32_t)P64;
+    v->Ppad = (P64 + 255ull) & ~255ull;
+    v->n_tiles = (uint32_t)((P64 + ADDER_TILE_PX - 1) / ADDER_TILE_PX);
+
+    auto build = [&]() -> int {
+      CU(cudaSetDevice(device));
+      CU(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&v->stream_in, cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&v->stream_out, cudaStreamNonBlocking));
+      for (int s = 0; s < kRing; s++) {
+        CU(cudaEventCreateWithFlags(&v->ev_in[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&v->ev_k[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&v->ev_out[s], cudaEventDisableTiming));
+      }
+      CU(cudaEventCreate(&v->ev_t0));
+      CU(cudaEventCreate(&v->ev_t1));
+      CU(cudaMalloc(&v->d_hdr, (size_t)v->Ppad * sizeof(uint2)));
+      CU(cudaMalloc(&v->d_running, (size_t)v->Ppad));
+      CU(cudaMalloc(&v->d_status, (size_t)v->n_tiles * sizeof(unsigned long long)));
+      CU(cudaMalloc(&v->d_ticket, sizeof(uint32_t)));
+      CU(cudaMalloc(&v->d_err, sizeof(uint32_t)));
+      CU(cudaMalloc(&v->d_total, sizeof(unsigned long long)));
+      CU(cudaHostAlloc(&v->h_err, sizeof(uint32_t), cudaHostAllocDefault));
+      CU(cudaHostAlloc(&v->h_total, sizeof(unsigned long long), cudaHostAllocDefault));
+      CU(cudaMemsetAsync(v->d_status, 0, (size_t)v->n_tiles * sizeof(unsigned long long), v->stream));
+      CU(cudaMemsetAsync(v->d_ticket, 0, sizeof(uint32_t), v->stream));
+      CU(cudaMemsetAsync(v->d_err, 0, sizeof(uint32_t), v->stream));
+      CU(cudaMemsetAsync(v->d_total, 0, sizeof(unsigned long long), v->stream));
+      CU(cudaFuncSetAttribute(adder::integrate_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)((ADDER_MAX_DEPTH + 2u) * ADDER_TILE_PX * 5u + adder::kStageRecords * 12u)));
+      if (int rc = realloc_chunks(v)) return rc;
+      if (int rc = ensure_depth(v, derive_depth(v))) return rc;
+      CU(cudaStreamSynchronize(v->stream));
+      return ADDER_OK;
+    };
+    if (int rc = build()) {
+      adder_b200_video_destroy(v);
+      return rc;
+    }
+    *out = v;
+    return ADDER_OK;
+  });
+}
+
+void adder_b200_video_destroy(adder_b200_video* v) {
+  if (!v) return;
+  cudaSetDevice(v->device);
+  if (v->stream) cudaStreamSynchronize(v->stream);
+  if (v->stream_in) cudaStreamSynchronize(v->stream_in);
+  if (v->stream_out) cudaStreamSynchronize(v->stream_out);
+  cudaFree(v->d_hdr);
+  cudaFree(v->d_nodes);
+  cudaFree(v->d_running);
+  cudaFree(v->d_status);
+  cudaFree(v->d_ticket);
+  cudaFree(v->d_err);
+  cudaFree(v->d_total);
+  if (v->h_err) cudaFreeHost(v->h_err);
+  if (v->h_total) cudaFreeHost(v->h_total);
+  for (int s = 0; s < kRing; s++) {
+    cudaFree(v->d_frame[s]);
+    cudaFree(v->d_events[s]);
+    cudaFree(v->d_chunk_off[s]);
+    if (v->h_chunk_off[s]) cudaFreeHost(v->h_chunk_off[s]);
+    if (v->ev_in[s]) cudaEventDestroy(v->ev_in[s]);
+    if (v->ev_k[s]) cudaEventDestroy(v->ev_k[s]);
+    if (v->ev_out[s]) cudaEventDestroy(v->ev_out[s]);
+  }
+  if (v->ev_t0) cudaEventDestroy(v->ev_t0);
+  if (v->ev_t1) cudaEventDestroy(v->ev_t1);
+  if (v->stream) cudaStreamDestroy(v->stream);
+  if (v->stream_in) cudaStreamDestroy(v->stream_in);
+  if (v->stream_out) cudaStreamDestroy(v->stream_out);
+  delete v;
+}
+
+/* ---- setters ---------------------------------------------------------------------------------- */
+
+int adder_b200_video_chunk_rows(adder_b200_video* v, uint32_t chunk_rows) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (chunk_rows == 0) return fail(ADDER_ERR_BAD_PARAMS, "chunk_rows must be > 0"); /* ndarray chunk size must be non-zero */
+  if (int rc = set_device(v)) return rc;
+  CU(cudaStreamSynchronize(v->stream));
+  v->chunk_rows = chunk_rows;
+  return realloc_chunks(v);
+}
+
+int adder_b200_video_time_parameters(adder_b200_video* v, uint32_t tps, uint32_t ref_time, uint32_t delta_t_max,
+                                     int time_mode, int* applied) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (time_mode > ADDER_TIME_MIXED) return fail(ADDER_ERR_BAD_PARAMS, "unknown time_mode");
+  if (time_mode >= 0) v->time_mode = time_mode; /* :500-502 runs before the range checks */
+  int ok = 1;
+  if (delta_t_max < ref_time) ok = 0; /* :518-523 eprintln + keep */
+  if (ref_time == 0) return fail(ADDER_ERR_BAD_PARAMS, "ref_time must be > 0");
+  if (ok) {
+    v->delta_t_max = delta_t_max;
+    v->ref_time = ref_time;
+    v->tps = tps;
+  }
+  if (applied) *applied = ok;
+  return ADDER_OK;
+}
+
+int adder_b200_video_write_out(adder_b200_video* v, int time_mode, int pixel_multi_mode) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (time_mode > ADDER_TIME_MIXED || pixel_multi_mode > ADDER_MULTI_COLLAPSE) return fail(ADDER_ERR_BAD_PARAMS, "unknown mode");
+  v->multi_mode = pixel_multi_mode < 0 ? ADDER_MULTI_COLLAPSE : pixel_multi_mode; /* unwrap_or_default */
+  if (time_mode >= 0) v->time_mode = time_mode;
+  return ADDER_OK;
+}
+
+static int reset_c(adder_b200_video* v, uint8_t c, int reset_counter) {
+  if (int rc = set_device(v)) return rc;
+  adder::reset_c_kernel<<<(v->P + 255) / 256, 256, 0, v->stream>>>(v->d_hdr, v->P, c, reset_counter);
+  v->launches++;
+  CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
+int adder_b200_video_update_crf(adder_b200_video* v, uint8_t crf) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (crf > 9) return fail(ADDER_ERR_BAD_PARAMS, "crf must be 0..=9");
+  crf_lookup(crf, v->w, v->h, &v->crf);
+  return reset_c(v, v->crf.c_thresh_baseline, 1);
+}
+
+int adder_b200_video_update_quality_manual(adder_b200_video* v, uint8_t c_thresh_baseline, uint8_t c_thresh_max,
+                                           uint32_t delta_t_max_multiplier, uint8_t c_increase_velocity,
+                                           float feature_c_radius) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  v->crf.c_thresh_baseline = c_thresh_baseline;
+  v->crf.c_thresh_max = c_thresh_max;
+  v->crf.c_increase_velocity = c_increase_velocity;
+  v->crf.feature_c_radius = feature_c_radius >= 65535.0f ? 65535 : (feature_c_radius > 0.0f ? (uint16_t)feature_c_radius : 0);
+  v->delta_t_max = delta_t_max_multiplier * v->ref_time;
+  return reset_c(v, c_thresh_baseline, 1);
+}
+
+int adder_b200_video_set_crf_parameters(adder_b200_video* v, const adder_crf_parameters_t* params) {
+  if (!v || !params) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  v->crf = *params;
+  return ADDER_OK;
+}
+
+int adder_b200_video_update_delta_t_max(adder_b200_video* v, uint32_t delta_t_max) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  v->delta_t_max = std::max(v->ref_time, delta_t_max); /* video.rs:819-822 */
+  return ADDER_OK;
+}
+
+int adder_b200_video_c_thresh_pos(adder_b200_video* v, uint8_t c) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  v->crf.c_thresh_baseline = c;
+  return reset_c(v, c, 0);
+}
+
+int adder_b200_video_set_c_thresh_rect(adder_b200_video* v, uint16_t x0, uint16_t y0, uint16_t x1, uint16_t y1, uint8_t value) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (x0 >= v->w || y0 >= v->h || x1 < x0 || y1 < y0) return ADDER_OK; /* empty after clipping */
+  if (int rc = set_device(v)) return rc;
+  const uint32_t rw = std::min<uint32_t>(x1, v->w - 1u) - x0 + 1u, rh = std::min<uint32_t>(y1, v->h - 1u) - y0 + 1u;
+  const uint32_t n = rw * v->c * rh;
+  adder::rect_c_kernel<<<(n + 255) / 256, 256, 0, v->stream>>>(v->d_hdr, v->w, v->c, x0, y0, rw, rh, value);
+  v->launches++;
+  CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
+int adder_b200_video_set_view_mode(adder_b200_video* v, int view_mode) {
+  if (!v || view_mode < 0 || view_mode > ADDER_VIEW_SAE) return fail(ADDER_ERR_BAD_PARAMS, "unknown view mode");
+  v->view_mode = view_mode;
+  return ADDER_OK;
+}
+
+int adder_b200_video_set_in_interval_count(adder_b200_video* v, uint32_t n) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  v->in_interval_count = n;
+  return ADDER_OK;
+}
+
+int adder_b200_video_get_info(const adder_b200_video* v, adder_b200_video_info_t* out) {
+  if (!v || !out) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  memset(out, 0, sizeof(*out));
+  out->width = v->w;
+  out->height = v->h;
+  out->channels = v->c;
+  out->pixel_tree_mode = (uint8_t)v->tree_mode;
+  out->pixel_multi_mode = (uint8_t)v->multi_mode;
+  out->time_mode = (uint8_t)v->time_mode;
+  out->view_mode = (uint8_t)v->view_mode;
+  out->chunk_rows = v->chunk_rows;
+  out->n_chunks = v->n_chunks;
+  out->in_interval_count = v->in_interval_count;
+  out->tps = v->tps;
+  out->ref_time = v->ref_time;
+  out->delta_t_max = v->delta_t_max;
+  out->crf = v->crf;
+  out->max_depth = v->depth;
+  out->device = (uint32_t)v->device;
+  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)v->depth * sizeof(uint4));
+  out->events_capacity = v->events_capacity;
+  return ADDER_OK;
+}
+
+int adder_b200_video_reset_state(adder_b200_video* v) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (int rc = set_device(v)) return rc;
+  adder::init_state_kernel<<<(v->P + 255) / 256, 256, 0, v->stream>>>(v->d_hdr, v->d_nodes, v->d_running, v->P);
+  v->launches++;
+  CU(cudaGetLastError());
+  v->running_t = 0.0f;
+  v->in_interval_count = 1;
+  return ADDER_OK;
+}
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+
+static void offsets_to_counts(const uint32_t* off, uint32_t n_chunks, uint32_t* counts) {
+  for (uint32_t i = 0; i < n_chunks; i++) counts[i] = off[i + 1] - off[i];
+}
+
+int adder_b200_video_integrate_matrix(adder_b200_video* v, const uint8_t* frame, size_t row_pitch, float time_spanned,
+                                      adder_event_t* events_out, size_t events_cap, uint32_t* chunk_counts,
+                                      uint64_t* n_events) {
+  return guarded([&]() -> int {
+    if (!v || !frame) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (int rc = set_device(v)) return rc;
+    if (int rc = ensure_depth(v, derive_depth(v))) return rc;
+    if (int rc = ensure_host_form(v)) return rc;
+    const size_t row = (size_t)v->w * v->c;
+    if (row_pitch == 0) row_pitch = row;
+    if (row_pitch < row) return fail(ADDER_ERR_BAD_PARAMS, "row_pitch smaller than a row");
+    const int s = 0;
+    CU(cudaMemcpy2DAsync(v->d_frame[s], row, frame, row_pitch, row, v->h, cudaMemcpyHostToDevice, v->stream));
+    if (int rc = launch_frame(v, v->stream, v->d_frame[s], time_spanned, v->d_events[s], v->events_capacity, v->d_chunk_off[s]))
+      return rc;
+    v->last_slot = s;
+    CU(cudaMemcpyAsync(v->h_chunk_off[s], v->d_chunk_off[s], ((size_t)v->n_chunks + 1) * sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, v->stream));
+    if (int rc = collect_errors(v, v->stream)) return rc;
+    return adder_b200_video_fetch_events(v, events_out, events_cap, chunk_counts, n_events);
+  });
+}
+
+int adder_b200_video_fetch_events(adder_b200_video* v, adder_event_t* events_out, size_t events_cap,
+                                  uint32_t* chunk_counts, uint64_t* n_events) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (v->last_slot < 0) return fail(ADDER_ERR_BAD_PARAMS, "no frame has been integrated through the host form yet");
+  if (int rc = set_device(v)) return rc;
+  const int s = v->last_slot;
+  const uint64_t total = v->h_chunk_off[s][v->n_chunks];
+  if (n_events) *n_events = total;
+  if (chunk_counts) offsets_to_counts(v->h_chunk_off[s], v->n_chunks, chunk_counts);
+  if (total > events_cap)
+    return fail(ADDER_ERR_CAPACITY, "events_out holds %zu records, the frame produced %llu", events_cap, (unsigned long long)total);
+  if (total) {
+    if (!events_out) return fail(ADDER_ERR_BAD_PARAMS, "events_out is NULL");
+    CU(cudaMemcpyAsync(events_out, v->d_events[s], total * sizeof(adder_event_t), cudaMemcpyDeviceToHost, v->stream));
+    CU(cudaStreamSynchronize(v->stream));
+  }
+  return ADDER_OK;
+}
+
+int adder_b200_video_integrate_frames_host(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
+                                           uint32_t n_frames, float time_spanned, adder_event_t* events_out,
+                                           size_t events_cap, uint64_t* frame_counts, uint32_t* chunk_counts,
+                                           uint64_t* n_events, uint32_t* frames_done) {
+  return guarded([&]() -> int {
+    if (!v || (!frames && n_frames)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (int rc = set_device(v)) return rc;
+    if (int rc = ensure_depth(v, derive_depth(v))) return rc;
+    if (int rc = ensure_host_form(v)) return rc;
+    if (frame_stride == 0) frame_stride = v->P;
+    if (frame_stride < v->P) return fail(ADDER_ERR_BAD_PARAMS, "frame_stride smaller than a frame");
+    if (n_events) *n_events = 0;
+    if (frames_done) *frames_done = 0;
+    CU(cudaStreamSynchronize(v->stream)); /* setters queued on the main stream come first */
+
+    uint64_t written = 0;
+    uint32_t submitted = 0, delivered = 0;
+    int rc_final = ADDER_OK;
+    /* Frame f uses ring slot f % kRing.  Its kernel waits for its H2D copy (ev_in) and for the D2H
+     * copy that last used the slot (ev_out); its D2H copy is issued once the host knows the count. */
+    auto deliver = [&](uint32_t f) -> int {
+      const int s = f % kRing;
+      CU(cudaEventSynchronize(v->ev_k[s]));
+      const uint32_t* off = v->h_chunk_off[s];
+      const uint64_t total = off[v->n_chunks];
+      if (written + total > events_cap)
+        return fail(ADDER_ERR_CAPACITY, "events_out holds %zu records; frame %u needs %llu more than fit", events_cap, f,
+                    (unsigned long long)(written + total - events_cap));
+      if (total)
+        CU(cudaMemcpyAsync(events_out + written, v->d_events[s], total * sizeof(adder_event_t), cudaMemcpyDeviceToHost,
+                           v->stream_out));
+      CU(cudaEventRecord(v->ev_out[s], v->stream_out));
+      if (frame_counts) frame_counts[f] = total;
+      if (chunk_counts) offsets_to_counts(off, v->n_chunks, chunk_counts + (size_t)f * v->n_chunks);
+      written += total;
+      return ADDER_OK;
+    };
+
+    for (uint32_t f = 0; f < n_frames; f++) {
+      const int s = f % kRing;
+      if (f >= (uint32_t)kRing) { /* the slot's previous tenant must be delivered before it is reused */
+        if (int rc = deliver(f - kRing)) {
+          rc_final = rc;
+          break;
+        }
+        delivered++;
+      }
+      CU(cudaStreamWaitEvent(v->stream_in, v->ev_k[s], 0)); /* previous kernel on this slot has read its frame */
+      CU(cudaMemcpyAsync(v->d_frame[s], frames + (size_t)f * frame_stride, v->P, cudaMemcpyHostToDevice, v->stream_in));
+      CU(cudaEventRecord(v->ev_in[s], v->stream_in));
+      CU(cudaStreamWaitEvent(v->stream, v->ev_in[s], 0));
+      CU(cudaStreamWaitEvent(v->stream, v->ev_out[s], 0));
+      if (int rc = launch_frame(v, v->stream, v->d_frame[s], time_spanned, v->d_events[s], v->events_capacity, v->d_chunk_off[s]))
+        return rc;
+      CU(cudaMemcpyAsync(v->h_chunk_off[s], v->d_chunk_off[s], ((size_t)v->n_chunks + 1) * sizeof(uint32_t),
+                         cudaMemcpyDeviceToHost, v->stream));
+      CU(cudaEventRecord(v->ev_k[s], v->stream));
+      submitted++;
+    }
+    while (rc_final == ADDER_OK && delivered < submitted) {
+      if (int rc = deliver(delivered)) {
+        rc_final = rc;
+        break;
+      }
+      delivered++;
+    }
+    CU(cudaStreamSynchronize(v->stream_out));
+    CU(cudaStreamSynchronize(v->stream));
+    v->last_slot = -1;
+    if (n_events) *n_events = written;
+    if (frames_done) *frames_done = delivered;
+    if (int rc = collect_errors(v, v->stream)) return rc;
+    return rc_final;
+  });
+}
+
+int adder_b200_video_running_intensities(adder_b200_video* v, uint8_t* out) {
+  if (!v || !out) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaMemcpyAsync(out, v->d_running, v->P, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  return ADDER_OK;
+}
+
+int adder_b200_video_integrate_frames_device(adder_b200_video* v, const uint8_t* d_frames, size_t frame_stride,
+                                             uint32_t n_frames, float time_spanned, adder_event_t* d_events,
+                                             size_t events_stride, uint32_t* d_chunk_offsets) {
+  return guarded([&]() -> int {
+    if (!v || (!d_frames && n_frames) || (!d_events && events_stride)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (int rc = set_device(v)) return rc;
+    if (frame_stride == 0) frame_stride = v->P;
+    for (uint32_t f = 0; f < n_frames; f++) {
+      uint32_t* off = d_chunk_offsets ? d_chunk_offsets + (size_t)f * (v->n_chunks + 1) : nullptr;
+      if (int rc = launch_frame(v, v->stream, d_frames + (size_t)f * frame_stride, time_spanned,
+                                d_events + (size_t)f * events_stride, events_stride, off))
+        return rc;
+    }
+    return ADDER_OK;
+  });
+}
+
+int adder_b200_video_sync(adder_b200_video* v) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (int rc = set_device(v)) return rc;
+  return collect_errors(v, v->stream);
+}
+
+void* adder_b200_video_stream(adder_b200_video* v) { return v ? (void*)v->stream : nullptr; }
+uint64_t adder_b200_video_launch_count(const adder_b200_video* v) { return v ? v->launches : 0; }
+
+int adder_b200_video_events_emitted(adder_b200_video* v, uint64_t* out) {
+  if (!v || !out) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaMemcpyAsync(v->h_total, v->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  *out = *v->h_total;
+  return ADDER_OK;
+}
+
+int adder_b200_video_read_px(adder_b200_video* v, size_t index, adder_b200_px_state_t* out) {
+  if (!v || !out || index >= v->P) return fail(ADDER_ERR_BAD_PARAMS, "bad argument");
+  if (int rc = set_device(v)) return rc;
+  memset(out, 0, sizeof(*out));
+  CU(cudaStreamSynchronize(v->stream));
+  uint2 h;
+  CU(cudaMemcpy(&h, v->d_hdr + index, sizeof(h), cudaMemcpyDeviceToHost));
+  memcpy(&out->last_fired_t, &h.x, 4);
+  out->running_t = v->running_t;
+  out->base_val = HDR_BASE(h.y);
+  out->c_thresh = HDR_CTHRESH(h.y);
+  out->c_increase_counter = HDR_COUNTER(h.y);
+  out->length = HDR_LENGTH(h.y);
+  out->dtm_reached = HDR_DTM_REACHED(h.y);
+  out->popped_dtm = HDR_POPPED(h.y);
+  out->time_mode = (uint8_t)v->time_mode;
+  for (uint32_t k = 0; k < out->length && k < v->depth; k++) {
+    uint4 n;
+    CU(cudaMemcpy(&n, v->d_nodes + (size_t)k * v->Ppad + index, sizeof(n), cudaMemcpyDeviceToHost));
+    memcpy(&out->nodes[k].integration, &n.x, 4);
+    memcpy(&out->nodes[k].delta_t, &n.y, 4);
+    memcpy(&out->nodes[k].best_delta_t, &n.z, 4);
+    out->nodes[k].d = NODE_D(n.w);
+    out->nodes[k].best_d = NODE_BEST_D(n.w);
+    out->nodes[k].has_best = NODE_HAS_BEST(n.w);
+  }
+  return ADDER_OK;
+}
+
+/* ---- plumbing --------------------------------------------------------------------------------- */
+
+int adder_b200_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(ADDER_ERR_BAD_PARAMS, "out is NULL");
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return ADDER_OK;
+}
+int adder_b200_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return ADDER_OK;
+}
+int adder_b200_device_alloc(adder_b200_video* v, size_t bytes, void** out) {
+  if (!v || !out) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaMalloc(out, bytes ? bytes : 1));
+  return ADDER_OK;
+}
+int adder_b200_device_free(adder_b200_video* v, void* p) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaStreamSynchronize(v->stream));
+  CU(cudaFree(p));
+  return ADDER_OK;
+}
+int adder_b200_copy_to_device(adder_b200_video* v, void* dst, const void* src, size_t bytes) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  return ADDER_OK;
+}
+int adder_b200_copy_to_host(adder_b200_video* v, void* dst, const void* src, size_t bytes) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  return ADDER_OK;
+}
+int adder_b200_video_timer_start(adder_b200_video* v) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaEventRecord(v->ev_t0, v->stream));
+  return ADDER_OK;
+}
+int adder_b200_video_timer_stop(adder_b200_video* v, float* ms) {
+  if (!v || !ms) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaEventRecord(v->ev_t1, v->stream));
+  CU(cudaEventSynchronize(v->ev_t1));
+  CU(cudaEventElapsedTime(ms, v->ev_t0, v->ev_t1));
+  return ADDER_OK;
+}
+
+int adder_b200_synth_frames(adder_b200_video* v, uint8_t* d_frames, size_t frame_stride, uint32_t f0, uint32_t n_frames,
+                            int kind, uint64_t seed) {
+  if (!v || !d_frames) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (kind < 0 || kind > 3) return fail(ADDER_ERR_BAD_PARAMS, "unknown synthetic kind");
+  if (int rc = set_device(v)) return rc;
+  if (frame_stride == 0) frame_stride = v->P;
+  const uint32_t blocks = (v->P + 255) / 256;
+  for (uint32_t f = 0; f < n_frames; f++) {
+    adder::synth_frame_kernel<<<blocks, 256, 0, v->stream>>>(d_frames + (size_t)f * frame_stride, v->P, v->w, v->c, f0 + f, kind, seed);
+    v->launches++;
+  }
+  CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
+}  /* extern "C" */

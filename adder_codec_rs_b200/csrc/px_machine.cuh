@@ -1,0 +1,329 @@
+/*
+ * px_machine.cuh — one pixel-channel, one frame: the FramePerfect state machine of the reference,
+ * written once for the device (px_kernel.cuh) and, for local checking without a GPU, for the host
+ * (tests/host_sim builds this header with g++ and compares it with the oracle; the product never
+ * runs it on the CPU).
+ *
+ * It restates
+ *   integrate_for_px            adder-codec-rs/src/transcoder/source/video.rs:1317-1380
+ *   PixelArena::pop_best_events adder-codec-rs/src/transcoder/event_pixel_tree.rs:213-287
+ *   PixelArena::integrate       :317-413,  integrate_main :418-479
+ *   PixelArena::pop_top_event   :139-210,  delta_t_to_absolute_t :113-137
+ *   u8::get_frame_value         adder-codec-rs/src/framer/scale_intensity.rs:58-104
+ * as ONE streaming pass over the pixel's node stack: node k is read once (Mem::load), updated in
+ * registers and written once to level k - shift (Mem::store), where shift = 1 iff the root is popped
+ * this frame — the reference's arena shift (:201-204) becomes a change of destination level instead
+ * of extra traffic.  Events go to Sink::push in the reference's push order.
+ *
+ * All f32/f64 arithmetic goes through the rn_* wrappers: explicit round-to-nearest intrinsics on the
+ * device (never contracted into an FMA), plain operators on the host (built with -ffp-contract=off).
+ */
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "state_layout.h"
+
+#ifndef ADDER_D_MAX
+#define ADDER_D_MAX 127u
+#define ADDER_D_ZERO_INTEGRATION 128u
+#define ADDER_D_EMPTY 255u
+#define ADDER_C_NONE 0xFFu
+#endif
+
+#if defined(__CUDACC__)
+#define ADDER_HD __host__ __device__ __forceinline__
+#else
+#define ADDER_HD inline
+#endif
+
+namespace adder {
+
+#if defined(__CUDA_ARCH__)
+ADDER_HD float rn_add(float a, float b) { return __fadd_rn(a, b); }
+ADDER_HD float rn_sub(float a, float b) { return __fsub_rn(a, b); }
+ADDER_HD float rn_mul(float a, float b) { return __fmul_rn(a, b); }
+ADDER_HD float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+ADDER_HD double rn_ddiv(double a, double b) { return __ddiv_rn(a, b); }
+ADDER_HD double rn_dmul(double a, double b) { return __dmul_rn(a, b); }
+ADDER_HD uint32_t f2u(float x) { return __float2uint_rz(x); }   /* Rust `as u32`: truncating, saturating, NaN -> 0 */
+ADDER_HD uint32_t d2u(double x) { return __double2uint_rz(x); }
+ADDER_HD float u2f(uint32_t x) { return __uint2float_rn(x); }
+ADDER_HD uint32_t clz32(uint32_t x) { return (uint32_t)__clz((int)x); }
+ADDER_HD uint32_t f_bits(float x) { return __float_as_uint(x); }
+ADDER_HD float bits_f(uint32_t x) { return __uint_as_float(x); }
+ADDER_HD double bits_d(uint64_t x) { return __longlong_as_double((long long)x); }
+#else
+ADDER_HD float rn_add(float a, float b) { volatile float r = a + b; return r; }
+ADDER_HD float rn_sub(float a, float b) { volatile float r = a - b; return r; }
+ADDER_HD float rn_mul(float a, float b) { volatile float r = a * b; return r; }
+ADDER_HD float rn_div(float a, float b) { volatile float r = a / b; return r; }
+ADDER_HD double rn_ddiv(double a, double b) { volatile double r = a / b; return r; }
+ADDER_HD double rn_dmul(double a, double b) { volatile double r = a * b; return r; }
+ADDER_HD uint32_t f2u(float x) { if (!(x > 0.0f)) return 0u; if (x >= 4294967296.0f) return 0xFFFFFFFFu; return (uint32_t)x; }
+ADDER_HD uint32_t d2u(double x) { if (!(x > 0.0)) return 0u; if (x >= 4294967296.0) return 0xFFFFFFFFu; return (uint32_t)x; }
+ADDER_HD float u2f(uint32_t x) { return (float)x; }
+ADDER_HD uint32_t clz32(uint32_t x) { return x ? (uint32_t)__builtin_clz(x) : 32u; }
+ADDER_HD uint32_t f_bits(float x) { uint32_t b; memcpy(&b, &x, 4); return b; }
+ADDER_HD float bits_f(uint32_t x) { float f; memcpy(&f, &x, 4); return f; }
+ADDER_HD double bits_d(uint64_t x) { double f; memcpy(&f, &x, 8); return f; }
+#endif
+
+/* per-frame constants of the state machine (VideoStateParams video.rs:160-182, CrfParameters
+ * rate_controller.rs:40-53, and what integrate_matrix derives per frame, video.rs:660-672) */
+struct PxParams {
+  float time, running_t_prev, running_t, dtm_f;
+  uint32_t ref, dtm;
+  uint32_t c_max, vel_m1, cnt_inc;
+  uint32_t collapse, abs_time, view_mode, display;
+  uint32_t depth;
+  double tpf;
+  float practical_d_max;
+};
+
+struct Node {
+  float integ, dt, best_dt;
+  uint32_t w; /* d | best_d<<8 | has_best<<16 */
+};
+
+struct PxHeader {
+  float lf;   /* last_fired_t */
+  uint32_t y; /* packed, state_layout.h */
+};
+
+ADDER_HD uint32_t get_d_from_intensity(float x) { /* event_pixel_tree.rs:482-499 */
+  if (x < 1.0f) return ADDER_D_ZERO_INTEGRATION;
+  uint32_t d = ((f_bits(x) >> 23) & 0xFFu) - 127u; /* x >= 1 (or NaN/inf): exponent >= 127 */
+  return d > ADDER_D_MAX ? ADDER_D_MAX : d;
+}
+ADDER_HD float d_shift_f32(uint32_t d) { /* D_SHIFT_F32, lib.rs:229-235: [128] = 0 */
+  return d >= 128u ? 0.0f : bits_f((d + 127u) << 23);
+}
+ADDER_HD Node fresh_node(float intensity) { /* PixelNode::new :502-514 */
+  Node n;
+  n.integ = 0.0f;
+  n.dt = 0.0f;
+  n.best_dt = 0.0f;
+  n.w = NODE_PACK(get_d_from_intensity(intensity), 0, 0);
+  return n;
+}
+
+/* integrate_main, FramePerfect arm (:418-479).  Returns true when the node fires. */
+ADDER_HD bool integrate_main(Node& n, float intensity, float time) {
+  const uint32_t d = NODE_D(n.w);
+  const float sum = rn_add(n.integ, intensity);
+  if (sum >= d_shift_f32(d)) {
+    const uint32_t nd = get_d_from_intensity(sum);
+    float prop = rn_div(rn_sub(d_shift_f32(nd), n.integ), intensity);
+    if (nd == ADDER_D_ZERO_INTEGRATION || d == ADDER_D_ZERO_INTEGRATION || intensity < 1.1920929e-07f) prop = 1.0f;
+    n.best_dt = rn_add(n.dt, rn_mul(time, prop)); /* :445, two roundings */
+    uint32_t d_after = nd;
+    if (nd < ADDER_D_MAX) { /* :449-461; the D_SHIFT walk always ends at nd+1 because 2^(nd+1) > sum */
+      n.integ = sum;
+      n.dt = rn_add(n.dt, time);
+      d_after = nd + 1u;
+    }
+    n.w = NODE_PACK(d_after, nd, 1);
+    return true;
+  }
+  n.integ = sum;
+  n.dt = rn_add(n.dt, time);
+  return false;
+}
+
+/* u8::get_frame_value, SourceType::U8 arm (scale_intensity.rs:58-104, :262-270) */
+ADDER_HD uint8_t frame_value_u8(const PxParams& a, uint32_t d, uint32_t t, float lf) {
+  float q;
+  switch (a.view_mode) {
+    case 0: { /* Intensity: f64 */
+      double inten;
+      if (d >= 129u) {
+        inten = 0.0;
+      } else {
+        const double p = d >= 128u ? 0.0 : bits_d((uint64_t)(d + 1023u) << 52); /* D_SHIFT_F64[d] */
+        inten = t == 0u ? p : rn_ddiv(p, (double)t);
+      }
+      const uint32_t u = d2u(rn_dmul(inten, a.tpf)); /* saturating, NaN -> 0 */
+      return (uint8_t)(u > 255u ? 255u : u);
+    }
+    case 1: q = rn_div((float)d, a.practical_d_max); break;
+    case 2: q = rn_div(u2f(t), u2f(a.dtm)); break;
+    default: { /* SAE */
+      const uint32_t diff = f2u(a.running_t) - f2u(lf);
+      q = rn_div(u2f(diff), u2f(a.dtm));
+      break;
+    }
+  }
+  const uint32_t u = f2u(rn_mul(q, 255.0f));
+  return (uint8_t)(u > 255u ? 255u : u);
+}
+
+/* delta_t_to_absolute_t, FramePerfect (:113-137), then Sink::push(d, t) */
+template <class Sink>
+ADDER_HD void emit_abs(const PxParams& a, Sink& sink, float& lf, uint32_t d, float dt) {
+  if (a.abs_time) {
+    dt = rn_add(dt, lf);
+    lf = dt;
+    const uint32_t u = f2u(lf);
+    const uint32_t q = u / a.ref;
+    lf = (u - q * a.ref == 0u) ? u2f(u) : u2f((q + 1u) * a.ref);
+  }
+  sink.push(d, f2u(dt));
+}
+
+/*
+ * One pixel, one frame.  `v` is the u8 sample, `h` the pixel's header (updated in place), `n0` its
+ * root node (already loaded).  Returns true and sets *disp when running_intensities must be written.
+ */
+template <class Mem, class Sink>
+ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& mem, Sink& sink, uint32_t& errbits,
+                      uint8_t* disp) {
+  const float intensity = (float)v; /* matrix.mapv(f32::from), video.rs:665 */
+  const float time = a.time;
+  float lf = h.lf;
+  uint32_t base = HDR_BASE(h.y), cth = HDR_CTHRESH(h.y), cnt = HDR_COUNTER(h.y);
+  uint32_t len = HDR_LENGTH(h.y);
+  uint32_t popped = HDR_POPPED(h.y);
+
+  /* ---- video.rs:1338-1358: the pixel changed by more than c_thresh -> pop_best_events -------- */
+  const uint32_t lo = base > cth ? base - cth : 0u;          /* saturating_sub */
+  const uint32_t hi = base + cth > 255u ? 255u : base + cth; /* saturating_add */
+  if (v < lo || v > hi) {
+    const bool collapse_case = popped && a.collapse;
+    bool any = false;
+    Node tail = n0;
+    for (uint32_t k = 0; k < len; k++) {
+      Node nk = (k == 0) ? n0 : mem.load(k);
+      if (NODE_HAS_BEST(nk.w)) {
+        emit_abs(a, sink, lf, NODE_BEST_D(nk.w), nk.best_dt);
+        any = true;
+      } else if (nk.dt > 0.0f && nk.integ == 0.0f) { /* get_zero_event(idx, None) :96-111 */
+        emit_abs(a, sink, lf, ADDER_D_ZERO_INTEGRATION, nk.dt);
+        nk.dt = 0.0f;
+        any = true;
+      }
+      tail = nk;
+      /* Collapse after a Δt_max pop keeps only the first event (:249-265): later nodes would only
+       * touch last_fired_t, which is overwritten below, and a root that is replaced. */
+      if (collapse_case && any) break;
+    }
+    if (collapse_case && any) {
+      lf = a.running_t_prev; /* running_t before this frame's `+= time` (:337 runs later) */
+      sink.push(ADDER_D_EMPTY, f2u(a.running_t_prev));
+      n0 = fresh_node(intensity);
+    } else {
+      n0 = tail; /* :267-270, the tail becomes the root */
+    }
+    len = 1;
+    popped = 0;
+    base = v;
+  }
+
+  /* ---- integrate (:317-413), node 0 ---------------------------------------------------------- */
+  if (len == 1u && n0.dt == 0.0f && n0.integ == 0.0f) /* :332-335, the tail is the root */
+    n0.w = (n0.w & ~0xFFu) | get_d_from_intensity(intensity);
+  const bool fired0 = integrate_main(n0, intensity, time);
+  const bool only_root = popped && a.collapse;             /* :360-362 */
+  const uint32_t dtm_reached = n0.dt >= a.dtm_f ? 1u : 0u; /* :394 */
+  const bool need_pop = NODE_D(n0.w) == ADDER_D_MAX || (dtm_reached && !popped);
+
+  if (cth < a.c_max) { /* :402-412 */
+    if (cnt >= a.vel_m1) {
+      cth = cth + 1u > 255u ? 255u : cth + 1u;
+      cnt = 0;
+    } else {
+      cnt = cnt + a.cnt_inc > 255u ? 255u : cnt + a.cnt_inc;
+    }
+  }
+
+  /* ---- the rest of the stack + pop_top_event (video.rs:1371-1374, :139-210) ------------------ */
+  bool disp_has = false;
+  uint32_t disp_d = 0;
+  float disp_dt = 0.0f;
+  uint32_t new_len = 1;
+  if (fired0) { /* :344-355: child seeded from this intensity, deeper nodes dropped (FramePerfect :366) */
+    if (need_pop) {
+      emit_abs(a, sink, lf, NODE_BEST_D(n0.w), n0.best_dt);
+      popped = 1;
+      mem.store(0, fresh_node(intensity));
+      new_len = 1;
+    } else {
+      mem.store(0, n0);
+      if (a.depth > 1u) mem.store(1, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+      new_len = 2;
+      disp_has = true;
+      disp_d = NODE_BEST_D(n0.w);
+      disp_dt = n0.best_dt;
+    }
+  } else {
+    uint32_t shift = 0;
+    bool cut = false;
+    if (need_pop) {
+      popped = 1;
+      if (!NODE_HAS_BEST(n0.w)) {
+        if (n0.integ == 0.0f && n0.dt > 0.0f) { /* zero event, :155-160 */
+          emit_abs(a, sink, lf, ADDER_D_ZERO_INTEGRATION, n0.dt);
+          n0.dt = 0.0f;
+          n0.w = (n0.w & ~0xFFu) | get_d_from_intensity(intensity);
+          mem.store(0, n0);
+        } else { /* :164-193 synthesise a best event, then pop it: the root becomes a fresh node */
+          const uint32_t sd = n0.integ < 1.0f ? ADDER_D_ZERO_INTEGRATION : 31u - clz32(f2u(n0.integ));
+          emit_abs(a, sink, lf, sd, n0.dt);
+          mem.store(0, fresh_node(intensity));
+          new_len = 1;
+          cut = true;
+        }
+      } else {
+        emit_abs(a, sink, lf, NODE_BEST_D(n0.w), n0.best_dt);
+        shift = 1;
+        if (len < 2u) errbits |= ADDER_DEVERR_INTERNAL;
+      }
+    } else {
+      mem.store(0, n0);
+      if (NODE_HAS_BEST(n0.w)) {
+        disp_has = true;
+        disp_d = NODE_BEST_D(n0.w);
+        disp_dt = n0.best_dt;
+      }
+    }
+    if (!cut) {
+      new_len = len;
+      /* Collapse after a Δt_max pop integrates the root only (:360-362): unless the stack moves up
+       * a level, nothing below the root changes and nothing below it is read. */
+      const uint32_t k_end = (only_root && !shift) ? 1u : len;
+      for (uint32_t k = 1; k < k_end; k++) {
+        Node nk = mem.load(k);
+        bool fired = false;
+        if (!only_root) {
+          if (k == len - 1u && nk.dt == 0.0f && nk.integ == 0.0f) /* :332-335 */
+            nk.w = (nk.w & ~0xFFu) | get_d_from_intensity(intensity);
+          fired = integrate_main(nk, intensity, time);
+        }
+        mem.store(k - shift, nk);
+        if (k == 1u && shift && NODE_HAS_BEST(nk.w)) {
+          disp_has = true;
+          disp_d = NODE_BEST_D(nk.w);
+          disp_dt = nk.best_dt;
+        }
+        if (fired) {
+          if (k + 1u - shift < a.depth) mem.store(k + 1u - shift, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+          new_len = k + 2u;
+          break;
+        }
+      }
+      new_len -= shift;
+      if (new_len == 0u) new_len = 1u; /* flagged INTERNAL above */
+      if (new_len > a.depth) new_len = a.depth;
+    }
+  }
+
+  h.lf = lf;
+  h.y = HDR_PACK(base, cth, cnt, new_len, dtm_reached, popped);
+  if (a.display && disp_has) { /* video.rs:713-730 */
+    *disp = frame_value_u8(a, disp_d, f2u(disp_dt), lf);
+    return true;
+  }
+  return false;
+}
+
+}  // namespace adder

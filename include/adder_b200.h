@@ -123,6 +123,10 @@ int adder_b200_video_update_crf(adder_b200_video* v, uint8_t crf);
 int adder_b200_video_update_quality_manual(adder_b200_video* v, uint8_t c_thresh_baseline, uint8_t c_thresh_max,
                                            uint32_t delta_t_max_multiplier, uint8_t c_increase_velocity,
                                            float feature_c_radius);
+/* Video::update_encoder_options (video.rs:1289-1291) and the `encoder_options` argument of write_out
+ * (video.rs:553, :634): replaces the CRF parameter set (c_thresh_max, c_increase_velocity, ...) that
+ * integrate_matrix reads (video.rs:660) WITHOUT touching any pixel's c_thresh or counter. */
+int adder_b200_video_set_crf_parameters(adder_b200_video* v, const adder_crf_parameters_t* params);
 /* Video::update_delta_t_max, video.rs:819-822 */
 int adder_b200_video_update_delta_t_max(adder_b200_video* v, uint32_t delta_t_max);
 /* Video::c_thresh_pos / update_adder_thresh_pos (deprecated), video.rs:445-455, :842-851 */
@@ -192,6 +196,63 @@ int adder_b200_video_sync(adder_b200_video* v);
 void* adder_b200_video_stream(adder_b200_video* v);
 /* Number of kernels this handle has launched so far. */
 uint64_t adder_b200_video_launch_count(const adder_b200_video* v);
+
+/* Cumulative number of events emitted by this handle (all frames, both forms of the step). */
+int adder_b200_video_events_emitted(adder_b200_video* v, uint64_t* out);
+/* Device error word accumulated by the kernels since the last sync (ADDER_DEVERR_* bits OR-ed),
+ * as sync() saw it; sync() maps it to ADDER_ERR_CAPACITY / _ARENA_DEPTH / _INTERNAL. */
+
+/* Batched host-buffer form: n_frames consecutive calls of integrate_matrix in one submission, with
+ * the H2D copy of frame f+1, the kernel of frame f and the D2H copy of frame f-1's events
+ * overlapped on three streams (what a caller looping on Source::consume() would want, simulproc.rs:229-277).
+ *   frames           n_frames frames of H*W*C bytes, `frame_stride` bytes apart (pinned memory for
+ *                    full PCIe rate: adder_b200_host_alloc)                                      [host]
+ *   events_out       all frames' events back to back, capacity `events_cap` records              [host]
+ *   frame_counts     n_frames entries: events of each frame                          [host, may be NULL]
+ *   chunk_counts     n_frames * n_chunks entries                                     [host, may be NULL]
+ *   n_events         total
+ * Unlike the single-frame call this one cannot keep a frame's events for a retry: when
+ * `events_cap` is too small it stops BEFORE integrating the first frame that does not fit, returns
+ * ADDER_ERR_CAPACITY and reports in *frames_done how many frames were integrated and delivered. */
+int adder_b200_video_integrate_frames_host(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
+                                           uint32_t n_frames, float time_spanned, adder_event_t* events_out,
+                                           size_t events_cap, uint64_t* frame_counts, uint32_t* chunk_counts,
+                                           uint64_t* n_events, uint32_t* frames_done);
+
+/* Back to the state of a fresh Video::new (video.rs:350-438) with the current parameters kept:
+ * what adder-viz does on EOF by rebuilding the source (adder.rs:151-166). */
+int adder_b200_video_reset_state(adder_b200_video* v);
+
+/* ---- inspection (tests / debugging): one pixel's state, PixelArena fields :53-66 ------------- */
+typedef struct adder_b200_px_node {
+  float integration, delta_t, best_delta_t;
+  uint8_t d, best_d, has_best, reserved;
+} adder_b200_px_node_t;
+typedef struct adder_b200_px_state {
+  float last_fired_t, running_t;
+  uint8_t base_val, c_thresh, c_increase_counter, length, dtm_reached, popped_dtm, time_mode, reserved;
+  adder_b200_px_node_t nodes[31];
+} adder_b200_px_state_t;
+int adder_b200_video_read_px(adder_b200_video* v, size_t index, adder_b200_px_state_t* out);
+
+/* ---- plumbing for callers without a CUDA runtime of their own --------------------------------- */
+/* Page-locked host memory (cudaHostAlloc) so H2D/D2H run at full PCIe rate. */
+int adder_b200_host_alloc(size_t bytes, void** out);
+int adder_b200_host_free(void* p);
+/* Device memory on the handle's device, and copies ordered on the handle's stream (synchronous to the host). */
+int adder_b200_device_alloc(adder_b200_video* v, size_t bytes, void** out);
+int adder_b200_device_free(adder_b200_video* v, void* p);
+int adder_b200_copy_to_device(adder_b200_video* v, void* dst, const void* src, size_t bytes);
+int adder_b200_copy_to_host(adder_b200_video* v, void* dst, const void* src, size_t bytes);
+/* CUDA-event stopwatch on the handle's stream: start records an event, stop records another, waits
+ * for it and returns the device time between the two in milliseconds. */
+int adder_b200_video_timer_start(adder_b200_video* v);
+int adder_b200_video_timer_stop(adder_b200_video* v, float* ms);
+/* Synthetic frames generated on the device (bench input; tests/synth.py holds the same generator in
+ * numpy): n_frames frames of `px` bytes, frame index starting at f0.  kind: 0 gradient (x+2y+3f)&255,
+ * 1 uniform noise h(seed,f,i), 2 base +-10 jitter, 3 static base with rare changes (p = 2/256). */
+int adder_b200_synth_frames(adder_b200_video* v, uint8_t* d_frames, size_t frame_stride, uint32_t f0,
+                            uint32_t n_frames, int kind, uint64_t seed);
 
 #ifdef __cplusplus
 }

@@ -636,6 +636,9 @@ void oracle_video_update_quality_manual(oracle_video* v, uint8_t c_base, uint8_t
   video_reset_c(v, c_base);
 }
 
+/* Video::update_encoder_options (video.rs:1289-1291) / write_out's encoder_options (:553, :634) */
+void oracle_video_set_crf_parameters(oracle_video* v, const adder_crf_parameters_t* p) { v->crf = *p; }
+
 void oracle_video_update_delta_t_max(oracle_video* v, uint32_t dtm) {
   v->delta_t_max = v->ref_time > dtm ? v->ref_time : dtm;
 }

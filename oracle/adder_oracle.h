@@ -110,6 +110,7 @@ void oracle_video_write_out(oracle_video* v, int time_mode, int pixel_multi_mode
 void oracle_video_update_crf(oracle_video* v, uint8_t crf);                                  /* :1241-1251 */
 void oracle_video_update_quality_manual(oracle_video* v, uint8_t c_base, uint8_t c_max, uint32_t dtm_mult,
                                         uint8_t velocity, float radius);                    /* :1264-1287 */
+void oracle_video_set_crf_parameters(oracle_video* v, const adder_crf_parameters_t* p);     /* :1289-1291, :553 */
 void oracle_video_update_delta_t_max(oracle_video* v, uint32_t dtm);                        /* :819-822 */
 void oracle_video_c_thresh_pos(oracle_video* v, uint8_t c);                                  /* :445-455 */
 void oracle_video_set_c_thresh_rect(oracle_video* v, uint16_t x0, uint16_t y0, uint16_t x1, uint16_t y1, uint8_t value); /* :865-881 */

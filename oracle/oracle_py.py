@@ -132,6 +132,7 @@ def lib() -> C.CDLL:
     L.oracle_video_write_out.argtypes = [vp, i32, i32]
     L.oracle_video_update_crf.argtypes = [vp, u8]
     L.oracle_video_update_quality_manual.argtypes = [vp, u8, u8, u32, u8, f32]
+    L.oracle_video_set_crf_parameters.argtypes = [vp, C.POINTER(CrfParameters)]
     L.oracle_video_update_delta_t_max.argtypes = [vp, u32]
     L.oracle_video_c_thresh_pos.argtypes = [vp, u8]
     L.oracle_video_set_c_thresh_rect.argtypes = [vp, u16, u16, u16, u16, u8]
@@ -239,6 +240,10 @@ class Video:
 
     def update_quality_manual(self, c_base, c_max, dtm_mult, velocity, radius=0.0):
         self._L.oracle_video_update_quality_manual(self._v, c_base, c_max, dtm_mult, velocity, radius)
+
+    def set_crf_parameters(self, c_base, c_max, velocity, radius=0):
+        p = CrfParameters(c_base, c_max, velocity, 0, radius, 0)
+        self._L.oracle_video_set_crf_parameters(self._v, C.byref(p))
 
     def update_delta_t_max(self, dtm):
         self._L.oracle_video_update_delta_t_max(self._v, dtm)

@@ -1,0 +1,107 @@
+/*
+ * px_sim.cpp — TEST INFRASTRUCTURE: runs the product's per-pixel state machine
+ * (adder_codec_rs_b200/csrc/px_machine.cuh, the very header the CUDA kernel compiles) serially on
+ * the host, over the same SoA state layout, so its restructuring of the reference algorithm
+ * (streaming node pass, shift-on-pop, lazy tail fix) can be checked against the oracle in this
+ * GPU-less container.  Nothing in the product links or calls this.
+ */
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/adder_b200.h"
+#include "../../adder_codec_rs_b200/csrc/px_machine.cuh"
+
+namespace {
+struct HostNodes {
+  adder::Node* p;
+  size_t stride;
+  adder::Node load(uint32_t k) const { return p[(size_t)k * stride]; }
+  void store(uint32_t k, const adder::Node& n) const { p[(size_t)k * stride] = n; }
+};
+struct VecSink {
+  std::vector<adder_event_t>* out;
+  uint16_t x, y;
+  uint8_t c;
+  void push(uint32_t d, uint32_t t) {
+    adder_event_t e;
+    e.x = x; e.y = y; e.c = c; e.d = (uint8_t)d; e.reserved = 0; e.t = t;
+    out->push_back(e);
+  }
+};
+}  // namespace
+
+struct sim_video {
+  uint32_t w, h, c, depth;
+  size_t P;
+  std::vector<adder::PxHeader> hdr;
+  std::vector<adder::Node> nodes;
+  std::vector<uint8_t> running;
+  std::vector<adder_event_t> events;
+  float running_t;
+  uint32_t err;
+};
+
+extern "C" {
+
+sim_video* sim_new(uint32_t w, uint32_t h, uint32_t c, uint32_t depth) {
+  sim_video* v = new sim_video();
+  v->w = w; v->h = h; v->c = c; v->depth = depth;
+  v->P = (size_t)w * h * c;
+  v->hdr.assign(v->P, adder::PxHeader{0.0f, HDR_PACK(0, 10, 1, 1, 0, 0)});
+  v->nodes.assign(v->P * depth, adder::Node{0.0f, 0.0f, 0.0f, NODE_PACK(0, 0, 0)});
+  v->running.assign(v->P, 0);
+  v->running_t = 0.0f;
+  v->err = 0;
+  return v;
+}
+void sim_delete(sim_video* v) { delete v; }
+
+void sim_reset_c(sim_video* v, uint32_t cth, int reset_counter) {
+  for (auto& h : v->hdr) {
+    h.y = (h.y & ~0xFF00u) | (cth << 8);
+    if (reset_counter) h.y &= ~0xFF0000u;
+  }
+}
+
+size_t sim_integrate(sim_video* v, const uint8_t* frame, float time, uint32_t ref, uint32_t dtm, uint32_t c_max,
+                     uint32_t vel, int collapse, int abs_time, int view_mode, float practical_d_max) {
+  adder::PxParams p{};
+  p.time = time;
+  p.running_t_prev = v->running_t;
+  v->running_t = v->running_t + time;
+  p.running_t = v->running_t;
+  p.dtm_f = (float)dtm;
+  p.ref = ref;
+  p.dtm = dtm;
+  p.c_max = c_max;
+  p.vel_m1 = (uint8_t)(vel - 1);
+  p.cnt_inc = (uint8_t)(adder::f2u(time) / ref);
+  p.collapse = collapse;
+  p.abs_time = abs_time;
+  p.view_mode = view_mode;
+  p.display = 1;
+  p.depth = v->depth;
+  p.tpf = (double)ref;
+  p.practical_d_max = practical_d_max;
+  v->events.clear();
+  for (size_t i = 0; i < v->P; i++) {
+    HostNodes mem{v->nodes.data() + i, v->P};
+    const uint32_t ch = (uint32_t)(i % v->c), x = (uint32_t)((i / v->c) % v->w), y = (uint32_t)(i / ((size_t)v->c * v->w));
+    VecSink sink{&v->events, (uint16_t)x, (uint16_t)y, (uint8_t)(v->c == 1 ? ADDER_C_NONE : ch)};
+    uint8_t disp = 0;
+    if (adder::px_step(p, frame[i], v->hdr[i], mem.load(0), mem, sink, v->err, &disp)) v->running[i] = disp;
+  }
+  return v->events.size();
+}
+const adder_event_t* sim_events(const sim_video* v) { return v->events.data(); }
+const uint8_t* sim_running(const sim_video* v) { return v->running.data(); }
+uint32_t sim_err(const sim_video* v) { return v->err; }
+/* header words + node k of pixel i, for state comparison */
+void sim_px(const sim_video* v, size_t i, float* lf, uint32_t* y) { *lf = v->hdr[i].lf; *y = v->hdr[i].y; }
+void sim_node(const sim_video* v, size_t i, uint32_t k, float* integ, float* dt, float* best_dt, uint32_t* w) {
+  const adder::Node& n = v->nodes[(size_t)k * v->P + i];
+  *integ = n.integ; *dt = n.dt; *best_dt = n.best_dt; *w = n.w;
+}
+}

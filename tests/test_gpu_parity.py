@@ -1,0 +1,212 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (GPU box only)."""
+import numpy as np
+import pytest
+
+import adder_codec_rs_b200 as A
+from adder_codec_rs_b200 import binding as B
+from oracle import oracle_py as O
+from tests import cases, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(case, **kw):
+    gv = A.Video(case.w, case.h, case.c, A.MODE_FRAME_PERFECT, **kw)
+    ov = O.Video(case.w, case.h, case.c, O.MODE_FRAME_PERFECT)
+    cases.configure(gv, case)
+    cases.configure(ov, case)
+    return gv, ov
+
+
+def _assert_state_equal(gv, ov, n, step=1):
+    for i in range(0, n, step):
+        a = cases.canonical_oracle_px(ov.px(i))
+        b = cases.canonical(gv.px_dict(i))
+        assert a == b, f"pixel {i}: state differs\noracle {a}\ngpu    {b}"
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=lambda c: c.name)
+def test_events_chunks_display_state_match_oracle(case):
+    """Frame by frame through integrate_matrix (host buffers): events bit-exact and in order,
+    per-chunk lengths, running_intensities, in_interval_count, and the final per-pixel state."""
+    gv, ov = _pair(case)
+    frames = case.frames()
+    total = 0
+    for f in range(case.n_frames):
+        if case.roi and case.roi[0] == f:
+            gv.set_c_thresh_rect(*case.roi[1:])
+            ov.set_c_thresh_rect(*case.roi[1:])
+        eg, cg = gv.integrate_matrix(frames[f], case.time)
+        eo, co = ov.integrate_matrix(frames[f], case.time)
+        assert len(eg) == len(eo), f"frame {f}: {len(eg)} vs {len(eo)} events"
+        assert eg.tobytes() == eo.tobytes(), f"frame {f}: event streams differ"
+        assert np.array_equal(cg, co), f"frame {f}: chunk counts differ"
+        assert np.array_equal(gv.running_intensities(), ov.running_intensities()), f"frame {f}: display bytes differ"
+        total += len(eg)
+    assert gv.in_interval_count == ov.in_interval_count
+    assert gv.events_emitted() == total
+    n = case.w * case.h * case.c
+    _assert_state_equal(gv, ov, n, step=max(1, n // 400))
+
+
+@pytest.mark.parametrize("name", ["cfg2_rgb_noise_crf3", "jitter_dtm4_collapse", "ragged_37x13x3_chunk4", "cfg5_static_normal"])
+def test_batched_host_form_equals_frame_by_frame(name):
+    """integrate_frames_host (pipelined copies) == n calls of integrate_matrix."""
+    case = cases.CASES_BY_NAME[name]
+    gv, ov = _pair(case)
+    frames = case.frames()
+    exp, exp_fc, exp_cc = [], [], []
+    for f in range(case.n_frames):
+        eo, co = ov.integrate_matrix(frames[f], case.time)
+        exp.append(eo)
+        exp_fc.append(len(eo))
+        exp_cc.append(co)
+    exp = np.concatenate(exp)
+    pinned_frames = A.pinned_empty(frames.shape, np.uint8)
+    pinned_frames[...] = frames
+    out = A.pinned_empty((len(exp) + 16,), A.EVENT_DTYPE)
+    ev, fc, cc = gv.integrate_frames_host(np.asarray(pinned_frames), case.time, np.asarray(out))
+    assert ev.tobytes() == exp.tobytes()
+    assert np.array_equal(fc, np.array(exp_fc, dtype=np.uint64))
+    assert np.array_equal(cc, np.stack(exp_cc))
+    assert np.array_equal(gv.running_intensities(), ov.running_intensities())
+
+
+@pytest.mark.parametrize("name", ["cfg2_rgb_noise_crf3", "cfg3_jitter_c5", "blips_dtm16_collapse"])
+def test_device_resident_form(name):
+    """Frames already in HBM (generated there by the synth kernel), events left in HBM."""
+    case = cases.CASES_BY_NAME[name]
+    gv, ov = _pair(case)
+    P = case.w * case.h * case.c
+    nf = case.n_frames
+    d_frames = gv.device_alloc(P * nf)
+    gv.synth_frames(d_frames, 0, nf, case.kind, case.seed)
+    host_frames = case.frames()
+    assert np.array_equal(d_frames.to_host().reshape(host_frames.shape), host_frames), "device and numpy generators differ"
+    stride = P * 3  # records per frame
+    d_events = gv.device_alloc(stride * nf * 12)
+    nck = gv.n_chunks
+    d_off = gv.device_alloc((nck + 1) * 4 * nf)
+    gv.integrate_frames_device(d_frames.ptr, P, nf, case.time, d_events.ptr, stride, d_off.ptr)
+    gv.sync()
+    offs = d_off.to_host(np.uint32).reshape(nf, nck + 1)
+    for f in range(nf):
+        eo, co = ov.integrate_matrix(host_frames[f], case.time)
+        assert offs[f, -1] == len(eo), f"frame {f}"
+        assert np.array_equal(np.diff(offs[f]), co)
+        eg = d_events.to_host(A.EVENT_DTYPE, nbytes=len(eo) * 12, offset=f * stride * 12)
+        assert eg.tobytes() == eo.tobytes(), f"frame {f}"
+    for b in (d_frames, d_events, d_off):
+        b.free()
+
+
+def test_capacity_error_keeps_the_events():
+    case = cases.CASES_BY_NAME["cfg2_rgb_noise_crf3"]
+    gv, ov = _pair(case)
+    frames = case.frames()
+    for f in range(3):
+        eo, _ = ov.integrate_matrix(frames[f], case.time)
+        small = np.empty(4, dtype=A.EVENT_DTYPE)
+        n = B.C.c_uint64()
+        rc = gv.L.adder_b200_video_integrate_matrix(gv.v, frames[f].ctypes.data, 0, case.time, small.ctypes.data, len(small), None, B.C.byref(n))
+        if len(eo) > 4:
+            assert rc == B.ERR_CAPACITY and n.value == len(eo)
+            big = np.empty(n.value, dtype=A.EVENT_DTYPE)
+            rc = gv.L.adder_b200_video_fetch_events(gv.v, big.ctypes.data, len(big), None, B.C.byref(n))
+            assert rc == 0 and big.tobytes() == eo.tobytes()
+        else:
+            assert rc == 0
+
+
+def test_device_capacity_overflow_is_reported():
+    case = cases.CASES_BY_NAME["cfg2_rgb_noise_crf3"]
+    gv, _ = _pair(case)
+    P = case.w * case.h * case.c
+    d_frames = gv.device_alloc(P * 4)
+    gv.synth_frames(d_frames, 0, 4, case.kind, case.seed)
+    d_events = gv.device_alloc(16 * 4 * 12)
+    gv.integrate_frames_device(d_frames.ptr, P, 4, case.time, d_events.ptr, 16, None)
+    with pytest.raises(A.AdderError) as e:
+        gv.sync()
+    assert e.value.code == B.ERR_CAPACITY
+
+
+def test_arena_depth_overflow_is_reported():
+    case = cases.CASES_BY_NAME["cfg5_static_collapse"]
+    gv, _ = _pair(case, max_depth=3)
+    frames = case.frames()
+    with pytest.raises(A.AdderError) as e:
+        for f in range(case.n_frames):
+            gv.integrate_matrix(frames[f], case.time)
+    assert e.value.code == B.ERR_ARENA_DEPTH
+
+
+def test_continuous_mode_is_refused():
+    gv = A.Video(8, 8, 1, A.MODE_CONTINUOUS)
+    with pytest.raises(A.AdderError) as e:
+        gv.integrate_matrix(np.zeros((8, 8, 1), np.uint8), 255.0)
+    assert e.value.code == B.ERR_UNSUPPORTED
+
+
+def test_bad_params():
+    with pytest.raises(A.AdderError):
+        A.Video(0, 8, 1)
+    gv = A.Video(8, 8, 1)
+    assert gv.time_parameters(100, 255, 100, None) is False  # dtm < ref: kept, like video.rs:518-523
+    assert gv.info().delta_t_max == 7650
+    with pytest.raises(A.AdderError):
+        gv.chunk_rows(0)
+
+
+def test_reset_state_equals_fresh_video():
+    case = cases.CASES_BY_NAME["cfg3_jitter_c5"]
+    gv, ov = _pair(case)
+    frames = case.frames()
+    for f in range(10):
+        gv.integrate_matrix(frames[f], case.time)
+    gv.reset_state()
+    cases.configure(gv, case)
+    for f in range(20):
+        eg, _ = gv.integrate_matrix(frames[f], case.time)
+        eo, _ = ov.integrate_matrix(frames[f], case.time)
+        assert eg.tobytes() == eo.tobytes()
+
+
+def test_mid_size_noise_against_oracle():
+    """A plane spanning thousands of tiles (look-back chains, many chunks): 640x360x3 noise, crf 3."""
+    case = cases.Case("mid_noise", 640, 360, 3, synth.NOISE, 12, crf=3)
+    gv, ov = _pair(case)
+    frames = case.frames()
+    nthreads = O.max_threads()
+    for f in range(case.n_frames):
+        eg, cg = gv.integrate_matrix(frames[f], case.time)
+        eo, co = ov.integrate_matrix(frames[f], case.time, nthreads)
+        assert eg.tobytes() == eo.tobytes(), f"frame {f}"
+        assert np.array_equal(cg, co)
+    assert np.array_equal(gv.running_intensities(), ov.running_intensities())
+
+
+def test_framed_source_mirror():
+    """Framed(...).crf().auto_time_parameters().write_out() ... consume(): the reference's usage
+    (examples/framed_video_to_adder.rs:20-57) against the oracle driven the same way."""
+    w, h = 48, 20
+    rgb = synth.frames(synth.JITTER, 7, 0, 30, w, h, 3)
+    src = A.Framed(list(rgb), w, h, color_input=False, source_fps=24.0)
+    src = src.crf(0).frame_start(1).auto_time_parameters(255, 6120, None).write_out(A.TIME_DELTA_T, A.MULTI_NORMAL, (0, 0, 10))
+    with pytest.raises(Exception):
+        src.auto_time_parameters(255, 6121, None)
+    ov = O.Video(w, h, 1, O.MODE_FRAME_PERFECT)
+    ov.update_crf(0)
+    assert ov.time_parameters(int(255 * 24), 255, 6120, None)
+    ov.write_out(O.TIME_DELTA_T, O.MULTI_NORMAL)
+    ov.set_crf_parameters(0, 0, 10)
+    from adder_codec_rs_b200.framed import handle_color
+
+    for f in range(1, 30):
+        chunks = src.consume()
+        assert len(chunks) == h  # chunk_rows 1 -> one Vec<Event> per row (driver.rs:566)
+        eo, co = ov.integrate_matrix(handle_color(rgb[f], False), 255.0)
+        assert np.concatenate(chunks).tobytes() == eo.tobytes()
+        assert [len(c) for c in chunks] == list(co)
+    with pytest.raises(Exception):
+        src.consume()
