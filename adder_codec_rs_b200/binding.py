@@ -30,6 +30,7 @@ SYMBOLS = [
     "adder_b200_video_time_parameters", "adder_b200_video_write_out", "adder_b200_video_update_crf",
     "adder_b200_video_update_quality_manual", "adder_b200_video_set_crf_parameters", "adder_b200_video_update_delta_t_max", "adder_b200_video_c_thresh_pos",
     "adder_b200_video_set_c_thresh_rect", "adder_b200_video_set_view_mode", "adder_b200_video_set_in_interval_count",
+    "adder_b200_video_set_row_offset", "adder_b200_video_set_counting", "adder_b200_video_read_counters",
     "adder_b200_video_get_info", "adder_b200_video_integrate_matrix", "adder_b200_video_fetch_events",
     "adder_b200_video_running_intensities", "adder_b200_video_integrate_frames_device", "adder_b200_video_sync",
     "adder_b200_video_stream", "adder_b200_video_launch_count", "adder_b200_video_events_emitted",
@@ -118,6 +119,9 @@ def lib() -> C.CDLL:
         "adder_b200_video_set_c_thresh_rect": (i32, [vp, u16, u16, u16, u16, u8]),
         "adder_b200_video_set_view_mode": (i32, [vp, i32]),
         "adder_b200_video_set_in_interval_count": (i32, [vp, u32]),
+        "adder_b200_video_set_row_offset": (i32, [vp, u16]),
+        "adder_b200_video_set_counting": (i32, [vp, i32]),
+        "adder_b200_video_read_counters": (i32, [vp, P(u64)]),
         "adder_b200_video_get_info": (i32, [vp, P(VideoInfo)]),
         "adder_b200_video_integrate_matrix": (i32, [vp, vp, sz, f32, vp, sz, vp, P(u64)]),
         "adder_b200_video_fetch_events": (i32, [vp, vp, sz, vp, P(u64)]),
@@ -180,23 +184,14 @@ class _Pinned:
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:
-    """A numpy array over page-locked host memory (adder_b200_host_alloc); freed with the array."""
+    """A numpy array over page-locked host memory (adder_b200_host_alloc).  The allocation lives as
+    long as any view of the array does (the ctypes buffer at the bottom of numpy's base chain owns it)."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     owner = _Pinned(max(n, 1))
     buf = (C.c_uint8 * max(n, 1)).from_address(owner.p.value)
-    arr = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
-    return _PinnedArray(arr, owner)
-
-
-class _PinnedArray(np.ndarray):
-    def __new__(cls, arr, owner):
-        obj = arr.view(cls)
-        obj._owner = owner
-        return obj
-
-    def __array_finalize__(self, obj):
-        self._owner = getattr(obj, "_owner", None)
+    buf._adder_owner = owner
+    return np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
 
 
 class DeviceBuffer:
@@ -293,6 +288,17 @@ class Video:
 
     def set_in_interval_count(self, n):
         _check(self.L.adder_b200_video_set_in_interval_count(self.v, n))
+
+    def set_row_offset(self, row0):
+        _check(self.L.adder_b200_video_set_row_offset(self.v, row0))
+
+    def set_counting(self, on: bool):
+        _check(self.L.adder_b200_video_set_counting(self.v, int(on)))
+
+    def read_counters(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        _check(self.L.adder_b200_video_read_counters(self.v, out))
+        return dict(node_loads=out[0], node_stores=out[1], display_writes=out[2], events=out[3])
 
     def reset_state(self):
         _check(self.L.adder_b200_video_reset_state(self.v))

@@ -97,7 +97,8 @@ struct adder_b200_video {
   uint32_t want_depth = 0; /* caller's max_depth (0 = derive) */
   uint32_t depth = 0;      /* allocated */
   float running_t = 0.0f;
-  uint32_t P = 0, n_tiles = 0;
+  uint32_t P = 0, n_tiles = 0;   /* n_tiles: 256-pixel tiles (upper bound, sizes the status array) */
+  uint32_t R = 1, n_tiles_r = 0; /* sub-tiles per CTA and the grid that goes with it */
   uint64_t Ppad = 0;
 
   uint2* d_hdr = nullptr;
@@ -122,12 +123,15 @@ struct adder_b200_video {
   cudaEvent_t ev_in[kRing] = {}, ev_k[kRing] = {}, ev_out[kRing] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
   uint64_t launches = 0;
   uint32_t epoch = 0, ticket_base = 0;
+  uint32_t row0 = 0;
+  bool counting = false;
+  unsigned long long* d_counters = nullptr;
 };
 
 namespace {
 
 uint32_t derive_depth(const adder_b200_video* v) {
-  if (v->want_depth) return std::min<uint32_t>(v->want_depth, ADDER_MAX_DEPTH);
+  if (v->want_depth) return std::min<uint32_t>(std::max<uint32_t>(v->want_depth, 2u), ADDER_MAX_DEPTH);
   /* live nodes grow like log2 of the frames a pixel can integrate before Δt_max pops the root
    * (7 at Δt_max/ref = 24, 11 at 4096); +6 leaves two levels of margin over the
    * floor(log2)+4 bound observed there.  The kernel reports ADDER_DEVERR_DEPTH if it is ever exceeded. */
@@ -192,6 +196,41 @@ int realloc_chunks(adder_b200_video* v) {
   return ADDER_OK;
 }
 
+template <int R>
+void launch_r(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
+  const size_t smem = adder::frame_kernel_smem(R);
+  if (v->counting)
+    adder::integrate_frame_kernel<R, true><<<v->n_tiles_r, ADDER_TILE_PX, smem, stream>>>(a);
+  else
+    adder::integrate_frame_kernel<R, false><<<v->n_tiles_r, ADDER_TILE_PX, smem, stream>>>(a);
+}
+void launch_variant(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
+  switch (v->R) {
+    case 1: launch_r<1>(v, a, stream); break;
+    case 2: launch_r<2>(v, a, stream); break;
+    case 4: launch_r<4>(v, a, stream); break;
+    default: launch_r<8>(v, a, stream); break;
+  }
+}
+template <int R>
+int set_smem_attr() {
+  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  return ADDER_OK;
+}
+/* pixels per thread: large planes take 8 sub-tiles per CTA (one look-back per 2048 pixels); small
+ * planes take fewer so that the grid still covers the 148 SMs several times over. */
+uint32_t choose_r(uint32_t P) {
+  if (const char* e = getenv("ADDER_B200_R")) {
+    const int r = atoi(e);
+    if (r == 1 || r == 2 || r == 4 || r == 8) return (uint32_t)r;
+  }
+  const uint32_t want_ctas = 148u * 8u;
+  for (uint32_t r = 8; r > 1; r >>= 1)
+    if (P / (ADDER_TILE_PX * r) >= want_ctas) return r;
+  return 1;
+}
+
 /* Queue one frame on `stream`.  d_frame: P dense bytes on the device. */
 int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_frame, float time_spanned,
                  adder_event_t* d_events, uint64_t cap, uint32_t* d_chunk_off) {
@@ -227,12 +266,13 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   a.ticket_base = v->ticket_base;
   a.epoch = v->epoch;
   a.P = v->P;
-  a.n_tiles = v->n_tiles;
+  a.n_tiles = v->n_tiles_r;
   a.C = v->c;
   a.WC = (uint32_t)v->w * v->c;
   a.chunk_px = v->chunk_rows * a.WC;
   a.n_chunks = v->n_chunks;
-  a.ecap = v->depth + 2u;
+  a.row0 = v->row0;
+  a.counters = v->d_counters;
   adder::PxParams& p = a.px;
   p.depth = v->depth;
   p.time = time_spanned;
@@ -252,9 +292,8 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   p.tpf = (double)v->ref_time;                                                  /* video.rs:672 */
   p.practical_d_max = log2_raw(255.0f * (float)(v->delta_t_max / v->ref_time)); /* :668-670 */
 
-  const size_t smem = (size_t)a.ecap * ADDER_TILE_PX * 5u + adder::kStageRecords * 12u;
-  adder::integrate_frame_kernel<<<v->n_tiles, ADDER_TILE_PX, smem, stream>>>(a);
-  v->ticket_base += v->n_tiles;
+  launch_variant(v, a, stream);
+  v->ticket_base += v->n_tiles_r;
   v->launches++;
   CU(cudaGetLastError());
   return ADDER_OK;
@@ -340,6 +379,8 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
     v->P = (uint32_t)P64;
     v->Ppad = (P64 + 255ull) & ~255ull;
     v->n_tiles = (uint32_t)((P64 + ADDER_TILE_PX - 1) / ADDER_TILE_PX);
+    v->R = choose_r(v->P);
+    v->n_tiles_r = (uint32_t)((P64 + (uint64_t)ADDER_TILE_PX * v->R - 1) / ((uint64_t)ADDER_TILE_PX * v->R));
 
     auto build = [&]() -> int {
       CU(cudaSetDevice(device));
@@ -365,8 +406,12 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       CU(cudaMemsetAsync(v->d_ticket, 0, sizeof(uint32_t), v->stream));
       CU(cudaMemsetAsync(v->d_err, 0, sizeof(uint32_t), v->stream));
       CU(cudaMemsetAsync(v->d_total, 0, sizeof(unsigned long long), v->stream));
-      CU(cudaFuncSetAttribute(adder::integrate_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)((ADDER_MAX_DEPTH + 2u) * ADDER_TILE_PX * 5u + adder::kStageRecords * 12u)));
+      if (int rc = set_smem_attr<1>()) return rc;
+      if (int rc = set_smem_attr<2>()) return rc;
+      if (int rc = set_smem_attr<4>()) return rc;
+      if (int rc = set_smem_attr<8>()) return rc;
+      CU(cudaMalloc(&v->d_counters, 4 * sizeof(unsigned long long)));
+      CU(cudaMemsetAsync(v->d_counters, 0, 4 * sizeof(unsigned long long), v->stream));
       if (int rc = realloc_chunks(v)) return rc;
       if (int rc = ensure_depth(v, derive_depth(v))) return rc;
       CU(cudaStreamSynchronize(v->stream));
@@ -394,6 +439,7 @@ void adder_b200_video_destroy(adder_b200_video* v) {
   cudaFree(v->d_ticket);
   cudaFree(v->d_err);
   cudaFree(v->d_total);
+  cudaFree(v->d_counters);
   if (v->h_err) cudaFreeHost(v->h_err);
   if (v->h_total) cudaFreeHost(v->h_total);
   for (int s = 0; s < kRing; s++) {
@@ -515,6 +561,31 @@ int adder_b200_video_set_view_mode(adder_b200_video* v, int view_mode) {
 int adder_b200_video_set_in_interval_count(adder_b200_video* v, uint32_t n) {
   if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
   v->in_interval_count = n;
+  return ADDER_OK;
+}
+
+int adder_b200_video_set_row_offset(adder_b200_video* v, uint16_t row0) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if ((uint32_t)row0 + v->h > 65536u) return fail(ADDER_ERR_BAD_PARAMS, "row offset + height exceeds the u16 coordinate range");
+  v->row0 = row0;
+  return ADDER_OK;
+}
+
+int adder_b200_video_set_counting(adder_b200_video* v, int on) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (int rc = set_device(v)) return rc;
+  v->counting = on != 0;
+  CU(cudaMemsetAsync(v->d_counters, 0, 4 * sizeof(unsigned long long), v->stream));
+  return ADDER_OK;
+}
+
+int adder_b200_video_read_counters(adder_b200_video* v, uint64_t out[4]) {
+  if (!v || !out) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (int rc = set_device(v)) return rc;
+  unsigned long long h[4];
+  CU(cudaMemcpyAsync(h, v->d_counters, sizeof(h), cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  for (int i = 0; i < 4; i++) out[i] = h[i];
   return ADDER_OK;
 }
 

@@ -140,6 +140,16 @@ int adder_b200_video_set_view_mode(adder_b200_video* v, int view_mode);
 /* VideoState.in_interval_count, video.rs:203 (adder-viz zeroes it on restart, adder.rs:155-166) */
 int adder_b200_video_set_in_interval_count(adder_b200_video* v, uint32_t n);
 
+/* Row-band sharding: this handle holds rows [row0, row0+height) of a taller frame
+ * owned by several GPUs; row0 is added to the y of every event it emits, so that concatenating the
+ * bands' streams in band order IS the reference's raster order (video.rs:677-734).  Default 0. */
+int adder_b200_video_set_row_offset(adder_b200_video* v, uint16_t row0);
+/* Measurement aid: while on, frames run through an instrumented twin of the kernel that also counts
+ * node loads, node stores, display-byte writes and events (the data-dependent terms of the
+ * algorithmic bytes).  Turning it on or off zeroes the counters.  Never on in timed runs. */
+int adder_b200_video_set_counting(adder_b200_video* v, int on);
+int adder_b200_video_read_counters(adder_b200_video* v, uint64_t out[4]);
+
 /* ---- getters ---------------------------------------------------------------------------------- */
 typedef struct adder_b200_video_info {
   uint16_t width, height;

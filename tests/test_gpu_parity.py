@@ -210,3 +210,45 @@ def test_framed_source_mirror():
         assert [len(c) for c in chunks] == list(co)
     with pytest.raises(Exception):
         src.consume()
+
+
+@pytest.mark.parametrize("r", [1, 2, 4, 8])
+@pytest.mark.parametrize("name", ["cfg2_rgb_noise_crf3", "cfg5_static_normal", "ragged_37x13x3_chunk4", "ragged_3x700_chunk64",
+                                  "jitter_dtm4_normal", "cfg1_gradient_dtm_eq_ref", "ragged_300x2x2_chunk5"])
+def test_every_tile_shape(name, r, monkeypatch):
+    """The kernel is compiled for 1, 2, 4 and 8 sub-tiles per CTA (chosen by plane size): force each."""
+    monkeypatch.setenv("ADDER_B200_R", str(r))
+    case = cases.CASES_BY_NAME[name]
+    gv, ov = _pair(case)
+    frames = case.frames()
+    for f in range(case.n_frames):
+        eg, cg = gv.integrate_matrix(frames[f], case.time)
+        eo, co = ov.integrate_matrix(frames[f], case.time)
+        assert eg.tobytes() == eo.tobytes(), f"frame {f}"
+        assert np.array_equal(cg, co), f"frame {f}"
+    assert np.array_equal(gv.running_intensities(), ov.running_intensities())
+    n = case.w * case.h * case.c
+    _assert_state_equal(gv, ov, n, step=max(1, n // 200))
+
+
+def test_many_events_per_pixel_use_the_dead_level_park():
+    """Normal mode, long integration under a wide threshold, then the threshold drops to 0 over the
+    whole plane (the ROI write): every pixel pops a deep stack in one frame — up to 7 events per pixel,
+    more than the shared-memory slots hold, 3.7 events per pixel on average in that frame."""
+    case = cases.Case("deep_pop", 64, 32, 1, synth.JITTER, 170, manual=(25, 25, 4096, 1), ref=256, dtm=1 << 20,
+                      multi_mode=O.MULTI_NORMAL, roi=(150, 0, 0, 63, 31, 0))
+    gv, ov = _pair(case)
+    frames = case.frames()
+    most = 0
+    for f in range(case.n_frames):
+        if case.roi[0] == f:
+            gv.set_c_thresh_rect(*case.roi[1:])
+            ov.set_c_thresh_rect(*case.roi[1:])
+        eg, cg = gv.integrate_matrix(frames[f], case.time)
+        eo, co = ov.integrate_matrix(frames[f], case.time)
+        assert eg.tobytes() == eo.tobytes(), f"frame {f}"
+        assert np.array_equal(cg, co)
+        if len(eo):
+            most = max(most, np.bincount(eo["y"].astype(np.int64) * case.w + eo["x"]).max())
+    assert most >= 6, most
+    _assert_state_equal(gv, ov, case.w * case.h, step=7)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# One GPU visit: parity tests, a short bench, the ncu launch list and one full capture of the hot kernel.
+# Usage (under gpurun): bash tools/gpu_round.sh <tag>
+set -u
+TAG=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+echo "== bench"; timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
+echo "== profile_run (plain)"; timeout 300 python tools/profile_run.py --reps 3 2>&1 | tail -4
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/${TAG}_launches.csv python tools/profile_run.py --frames 48 > gpurun_out/${TAG}_ncu_list.log 2>&1; tail -2 gpurun_out/${TAG}_ncu_list.log
+echo "== ncu full"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:integrate_frame -s 40 -c 3 -f -o gpurun_out/${TAG}_prof python tools/profile_run.py --frames 48 > gpurun_out/${TAG}_ncu_full.log 2>&1; tail -2 gpurun_out/${TAG}_ncu_full.log
+ls -la gpurun_out | tail -12
