@@ -97,12 +97,17 @@ struct adder_b200_video {
   uint32_t want_depth = 0; /* caller's max_depth (0 = derive) */
   uint32_t depth = 0;      /* allocated */
   float running_t = 0.0f;
-  uint32_t P = 0, n_tiles = 0;   /* n_tiles: 256-pixel tiles (upper bound, sizes the status array) */
-  uint32_t R = 1, n_tiles_r = 0; /* sub-tiles per CTA and the grid that goes with it */
+  uint32_t P = 0, n_tiles = 0;   /* n_tiles: tiles of the smallest shape (upper bound, sizes the status array) */
+  uint32_t R = 1, n_tiles_r = 0; /* sub-tiles per tile and the number of tiles that goes with it */
+  uint32_t grid = 0;             /* persistent CTAs per launch */
+  bool display_force = true;     /* next frame recomputes every display byte (PxParams::display == 2) */
+  uint8_t* d_exact_lut = nullptr; /* [257] display bytes of exactly integral intensities, for lut_ref */
+  uint32_t lut_ref = 0;
   uint64_t Ppad = 0;
 
   uint2* d_hdr = nullptr;
   uint4* d_nodes = nullptr;
+  uint2* d_spill1 = nullptr;
   uint8_t* d_running = nullptr;
   unsigned long long* d_status = nullptr;
   uint32_t* d_ticket = nullptr;
@@ -200,9 +205,35 @@ template <int R>
 void launch_r(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
   const size_t smem = adder::frame_kernel_smem(R);
   if (v->counting)
-    adder::integrate_frame_kernel<R, true><<<v->n_tiles_r, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, true><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
   else
-    adder::integrate_frame_kernel<R, false><<<v->n_tiles_r, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, false><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+}
+template <int R>
+int occupancy_r(int* ctas_per_sm) {
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, adder::integrate_frame_kernel<R, false>, ADDER_TILE_PX,
+                                                   adder::frame_kernel_smem(R)));
+  return ADDER_OK;
+}
+/* persistent grid: every SM filled to the kernel's occupancy, never more CTAs than tiles */
+int choose_grid(adder_b200_video* v) {
+  int sms = 0, per_sm = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v->device));
+  int rc;
+  switch (v->R) {
+    case 1: rc = occupancy_r<1>(&per_sm); break;
+    case 2: rc = occupancy_r<2>(&per_sm); break;
+    case 4: rc = occupancy_r<4>(&per_sm); break;
+    default: rc = occupancy_r<8>(&per_sm); break;
+  }
+  if (rc) return rc;
+  if (per_sm < 1) return fail(ADDER_ERR_INTERNAL, "integrate_frame_kernel does not fit an SM");
+  if (const char* e = getenv("ADDER_B200_CTAS_PER_SM")) {
+    const int n = atoi(e);
+    if (n >= 1 && n < per_sm) per_sm = n;
+  }
+  v->grid = std::min<uint32_t>(v->n_tiles_r, (uint32_t)sms * (uint32_t)per_sm);
+  return ADDER_OK;
 }
 void launch_variant(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
   switch (v->R) {
@@ -218,8 +249,9 @@ int set_smem_attr() {
   CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
   return ADDER_OK;
 }
-/* pixels per thread: large planes take 8 sub-tiles per CTA (one look-back per 2048 pixels); small
- * planes take fewer so that the grid still covers the 148 SMs several times over. */
+/* rounds per tile: 8 (62 rows = 1984 pixels: with one shared-memory park slot per pixel the three park
+ * buffers of four CTAs fit an SM) unless the plane is so small that the persistent grid would not get
+ * a few tiles per CTA. */
 uint32_t choose_r(uint32_t P) {
   if (const char* e = getenv("ADDER_B200_R")) {
     const int r = atoi(e);
@@ -227,7 +259,7 @@ uint32_t choose_r(uint32_t P) {
   }
   const uint32_t want_ctas = 148u * 8u;
   for (uint32_t r = 8; r > 1; r >>= 1)
-    if (P / (ADDER_TILE_PX * r) >= want_ctas) return r;
+    if (P / adder::tile_px(r) >= want_ctas) return r;
   return 1;
 }
 
@@ -254,6 +286,7 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   a.frame = d_frame;
   a.hdr = v->d_hdr;
   a.nodes = v->d_nodes;
+  a.spill1 = v->d_spill1;
   a.level_stride = v->Ppad;
   a.running = v->d_running;
   a.ev_words = reinterpret_cast<uint32_t*>(d_events);
@@ -272,6 +305,9 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   a.chunk_px = v->chunk_rows * a.WC;
   a.n_chunks = v->n_chunks;
   a.row0 = v->row0;
+  a.wc_magic = adder::ref_magic_of(a.WC);
+  a.chunk_magic = adder::ref_magic_of(a.chunk_px);
+  a.c_magic = v->c > 1 ? (uint32_t)((0x100000000ull + v->c - 1u) / v->c) : 0u;
   a.counters = v->d_counters;
   adder::PxParams& p = a.px;
   p.depth = v->depth;
@@ -288,12 +324,22 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   p.collapse = v->multi_mode == ADDER_MULTI_COLLAPSE;
   p.abs_time = v->time_mode == ADDER_TIME_ABSOLUTE_T;
   p.view_mode = (uint32_t)v->view_mode;
-  p.display = 1;
-  p.tpf = (double)v->ref_time;                                                  /* video.rs:672 */
+  p.display = v->display_force ? 2u : 1u;
+  v->display_force = false;
+  p.ref_magic = adder::ref_magic_of(v->ref_time);
+  p.tpf = (double)v->ref_time; /* video.rs:672 */
+  p.tpf_f = (float)v->ref_time;
+  if (v->lut_ref != v->ref_time) {
+    uint8_t lut[257];
+    adder::build_exact_lut(v->ref_time, lut);
+    CU(cudaMemcpyAsync(v->d_exact_lut, lut, sizeof(lut), cudaMemcpyHostToDevice, stream)); /* pageable source: staged before the call returns */
+    v->lut_ref = v->ref_time;
+  }
+  p.exact_lut = v->d_exact_lut;
   p.practical_d_max = log2_raw(255.0f * (float)(v->delta_t_max / v->ref_time)); /* :668-670 */
 
   launch_variant(v, a, stream);
-  v->ticket_base += v->n_tiles_r;
+  v->ticket_base += v->n_tiles_r + v->grid; /* every CTA draws one ticket past the end */
   v->launches++;
   CU(cudaGetLastError());
   return ADDER_OK;
@@ -378,9 +424,9 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
     crf_lookup(3, width, height, &v->crf); /* EncoderOptions::default -> Crf::new(None) -> quality 3 */
     v->P = (uint32_t)P64;
     v->Ppad = (P64 + 255ull) & ~255ull;
-    v->n_tiles = (uint32_t)((P64 + ADDER_TILE_PX - 1) / ADDER_TILE_PX);
+    v->n_tiles = (uint32_t)((P64 + adder::tile_px(1) - 1) / adder::tile_px(1)); /* smallest tile: sizes the status array */
     v->R = choose_r(v->P);
-    v->n_tiles_r = (uint32_t)((P64 + (uint64_t)ADDER_TILE_PX * v->R - 1) / ((uint64_t)ADDER_TILE_PX * v->R));
+    v->n_tiles_r = (uint32_t)((P64 + adder::tile_px(v->R) - 1) / adder::tile_px(v->R));
 
     auto build = [&]() -> int {
       CU(cudaSetDevice(device));
@@ -396,6 +442,7 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       CU(cudaEventCreate(&v->ev_t1));
       CU(cudaMalloc(&v->d_hdr, (size_t)v->Ppad * sizeof(uint2)));
       CU(cudaMalloc(&v->d_running, (size_t)v->Ppad));
+      CU(cudaMalloc(&v->d_spill1, (size_t)v->Ppad * sizeof(uint2)));
       CU(cudaMalloc(&v->d_status, (size_t)v->n_tiles * sizeof(unsigned long long)));
       CU(cudaMalloc(&v->d_ticket, sizeof(uint32_t)));
       CU(cudaMalloc(&v->d_err, sizeof(uint32_t)));
@@ -410,6 +457,8 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       if (int rc = set_smem_attr<2>()) return rc;
       if (int rc = set_smem_attr<4>()) return rc;
       if (int rc = set_smem_attr<8>()) return rc;
+      if (int rc = choose_grid(v)) return rc;
+      CU(cudaMalloc(&v->d_exact_lut, 257));
       CU(cudaMalloc(&v->d_counters, 4 * sizeof(unsigned long long)));
       CU(cudaMemsetAsync(v->d_counters, 0, 4 * sizeof(unsigned long long), v->stream));
       if (int rc = realloc_chunks(v)) return rc;
@@ -435,11 +484,13 @@ void adder_b200_video_destroy(adder_b200_video* v) {
   cudaFree(v->d_hdr);
   cudaFree(v->d_nodes);
   cudaFree(v->d_running);
+  cudaFree(v->d_spill1);
   cudaFree(v->d_status);
   cudaFree(v->d_ticket);
   cudaFree(v->d_err);
   cudaFree(v->d_total);
   cudaFree(v->d_counters);
+  cudaFree(v->d_exact_lut);
   if (v->h_err) cudaFreeHost(v->h_err);
   if (v->h_total) cudaFreeHost(v->h_total);
   for (int s = 0; s < kRing; s++) {
@@ -482,6 +533,7 @@ int adder_b200_video_time_parameters(adder_b200_video* v, uint32_t tps, uint32_t
     v->delta_t_max = delta_t_max;
     v->ref_time = ref_time;
     v->tps = tps;
+    v->display_force = true;
   }
   if (applied) *applied = ok;
   return ADDER_OK;
@@ -519,6 +571,7 @@ int adder_b200_video_update_quality_manual(adder_b200_video* v, uint8_t c_thresh
   v->crf.c_increase_velocity = c_increase_velocity;
   v->crf.feature_c_radius = feature_c_radius >= 65535.0f ? 65535 : (feature_c_radius > 0.0f ? (uint16_t)feature_c_radius : 0);
   v->delta_t_max = delta_t_max_multiplier * v->ref_time;
+  v->display_force = true;
   return reset_c(v, c_thresh_baseline, 1);
 }
 
@@ -531,6 +584,7 @@ int adder_b200_video_set_crf_parameters(adder_b200_video* v, const adder_crf_par
 int adder_b200_video_update_delta_t_max(adder_b200_video* v, uint32_t delta_t_max) {
   if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
   v->delta_t_max = std::max(v->ref_time, delta_t_max); /* video.rs:819-822 */
+  v->display_force = true;
   return ADDER_OK;
 }
 
@@ -555,6 +609,7 @@ int adder_b200_video_set_c_thresh_rect(adder_b200_video* v, uint16_t x0, uint16_
 int adder_b200_video_set_view_mode(adder_b200_video* v, int view_mode) {
   if (!v || view_mode < 0 || view_mode > ADDER_VIEW_SAE) return fail(ADDER_ERR_BAD_PARAMS, "unknown view mode");
   v->view_mode = view_mode;
+  v->display_force = true;
   return ADDER_OK;
 }
 
@@ -608,7 +663,7 @@ int adder_b200_video_get_info(const adder_b200_video* v, adder_b200_video_info_t
   out->crf = v->crf;
   out->max_depth = v->depth;
   out->device = (uint32_t)v->device;
-  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)v->depth * sizeof(uint4));
+  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)v->depth * sizeof(uint4)); /* + 8 B/px of event spill scratch */
   out->events_capacity = v->events_capacity;
   return ADDER_OK;
 }
@@ -621,6 +676,7 @@ int adder_b200_video_reset_state(adder_b200_video* v) {
   CU(cudaGetLastError());
   v->running_t = 0.0f;
   v->in_interval_count = 1;
+  v->display_force = true;
   return ADDER_OK;
 }
 

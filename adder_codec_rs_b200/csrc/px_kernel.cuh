@@ -1,17 +1,32 @@
 /*
  * px_kernel.cuh — the framed→ADΔER per-pixel integrate / fire / pop kernel for sm_100a.
  *
- * One thread owns one pixel-channel for one frame (the state machine is px_machine.cuh); a CTA owns
- * a tile of 256 consecutive raster indices, i.e. what one chunk iteration of the reference's rayon
- * loop (video.rs:697-731) does for 256 pixels.
+ * One thread owns one pixel-channel for one frame (the state machine is px_machine.cuh).  A CTA of
+ * 256 threads is persistent: it takes tiles of 256*R consecutive raster indices by ticket and walks
+ * each as R sub-tiles of 256, so every header / node / sample access of a warp is one contiguous run
+ * — what one chunk iteration of the reference's rayon loop (video.rs:697-731) does for 256*R pixels.
  *
  * Events must come out in the reference's order (pixels in raster order, a pixel's events contiguous
  * in push order).  A thread cannot know its output offset before it has run the state machine, so
- * it parks its (d,t) pairs in a shared-memory scratch, the CTA scans the per-thread counts, a
+ * it parks its (d,t) pairs in shared memory; warp scans give every pixel its place in the tile; a
  * decoupled look-back over per-tile status words (one 64-bit word per tile: epoch|flag|count) turns
- * the tile aggregate into a frame-wide exclusive offset in the same pass, and the CTA then writes
- * its records through a shared staging buffer with fully coalesced 32-bit stores.  The same offsets
- * give the per-chunk lengths of the reference's Vec<Vec<Event>>.
+ * the tile aggregate into a frame-wide exclusive offset in the same pass.
+ *
+ * The CTA is a three-stage software pipeline over its tiles (parks are triple-buffered):
+ *   iteration n:  all warps   run the state machines of tile n            -> park[n%3], warp totals
+ *                 warp 0      scans the warp totals, publishes tile n's aggregate, draws ticket n+2
+ *                 warp 1      looks back for tile n-1 (its predecessors published long ago)
+ *                 all warps   write out tile n-2 (prefix known since iteration n-1); each thread
+ *                             stores its own records, a warp's records are contiguous in the output
+ * with ONE rendezvous per tile, split into two named barriers so that nobody waits for the serial
+ * work: the six plain warps only ARRIVE at barrier A when their state machines are done (warps 0/1
+ * wait there), and they wait at barrier B for the serial work of the PREVIOUS iteration, which
+ * warps 0/1 signalled a whole tile earlier.  The first version of this kernel did scan + look-back +
+ * write-out behind two CTA-wide barriers per tile and lost 22 % of its stall samples there
+ * (profiles/r01b), the second deferred only the look-back (17 %, profiles/r01c).
+ * Samples arrive through cp.async (128-bit, per-warp staging in shared memory, one tile ahead);
+ * header, root and level-1 node of the next sub-tile are requested before the current one is worked on.
+ * The same offsets give the per-chunk lengths of the reference's Vec<Vec<Event>>.
  */
 #pragma once
 
@@ -28,6 +43,7 @@ struct FrameArgs {
   const uint8_t* frame; /* P bytes, raster (y,x,c) */
   uint2* hdr;
   uint4* nodes;
+  uint2* spill1;                   /* P entries: a pixel's second event of the frame, when the park has one slot */
   unsigned long long level_stride; /* uint4 elements between levels */
   uint8_t* running;
   uint32_t* ev_words;        /* output records as 3 u32 words each */
@@ -40,6 +56,9 @@ struct FrameArgs {
   uint32_t ticket_base, epoch;
   uint32_t P, n_tiles, C, WC, chunk_px, n_chunks;
   uint32_t row0;  /* added to every event's y: this plane is a row band of a larger frame (multi-GPU sharding) */
+  unsigned long long wc_magic; /* ceil(2^64 / WC), 0 for WC == 1: i / WC without a divide */
+  unsigned long long chunk_magic; /* the same for chunk_px */
+  uint32_t c_magic;            /* ceil(2^32 / C), unused for C == 1: rem / C for rem < 2^24 */
   unsigned long long* counters; /* kCount only: [0] node loads [1] node stores [2] display writes [3] events */
 };
 
@@ -65,29 +84,36 @@ struct GlobalNodes {
     n_stores++;
     p[(unsigned long long)k * stride] = make_uint4(__float_as_uint(n.integ), __float_as_uint(n.dt), __float_as_uint(n.best_dt), n.w);
   }
+  /* level 1 is fetched with the root, before the length is known: it counts as algorithmic traffic
+   * only when the state machine needed it; a level requested ahead and then dropped does not count */
+  __device__ __forceinline__ void used_preloaded() { n_loads++; }
+  __device__ __forceinline__ void unused_load() { n_loads--; }
 };
 
-constexpr uint32_t kSlots = 3; /* events per pixel parked in shared memory */
-
 /*
- * Where a pixel parks its events until the tile's output offset is known.  The first kSlots go to
- * shared memory ([slot][pixel-in-tile]).  A pixel that emits more (a deep pop_best in Normal mode,
- * rare) parks event #e >= kSlots in ITS OWN node column at level e: that level is dead by then —
+ * Where a pixel parks its events until the tile's output offset is known.  The first S go to
+ * shared memory ([slot][pixel-in-tile]).  With S = 1 (the large tile) a second event goes to the
+ * pixel's entry of a global spill array.  Events beyond that (a deep pop_best in Normal mode, rare)
+ * park event #e >= 2 in the pixel's OWN node column at level e: that level is dead by then —
  * pop_best produces event #e at node k >= e, i.e. after level e has been consumed, and after a
  * pop_best only levels 0 and 1 are written again this frame (length becomes 1, at most 2) — so no
  * extra memory is needed and no live state is touched.  Needs e < depth.
  */
+template <uint32_t S>
 struct EventPark {
-  uint32_t* t; /* &slot_t[pixel-in-tile] */
-  uint8_t* d;  /* &slot_d[pixel-in-tile] */
-  uint4* col;  /* &nodes[i] */
+  uint32_t* t;  /* &slot_t[pixel-in-tile] */
+  uint8_t* d;   /* &slot_d[pixel-in-tile] */
+  uint4* col;   /* &nodes[i] */
+  uint2* spill; /* &spill1[i] (S == 1 only) */
   unsigned long long stride;
   uint32_t tile_px, depth;
   uint32_t n, overflow;
   __device__ __forceinline__ void push(uint32_t dd, uint32_t tt) {
-    if (n < kSlots) {
+    if (n < S) {
       t[n * tile_px] = tt;
       d[n * tile_px] = (uint8_t)dd;
+    } else if (S == 1u && n == 1u) {
+      *spill = make_uint2(tt, dd);
     } else if (n < depth) {
       col[(unsigned long long)n * stride] = make_uint4(tt, dd, 0u, 0u);
     } else {
@@ -97,9 +123,13 @@ struct EventPark {
     n++;
   }
   __device__ __forceinline__ void get(uint32_t e, uint32_t& dd, uint32_t& tt) const {
-    if (e < kSlots) {
+    if (e < S) {
       tt = t[e * tile_px];
       dd = d[e * tile_px];
+    } else if (S == 1u && e == 1u) {
+      const uint2 v = *spill;
+      tt = v.x;
+      dd = v.y;
     } else {
       const uint4 v = col[(unsigned long long)e * stride];
       tt = v.x;
@@ -118,252 +148,396 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
 constexpr uint32_t kThreads = ADDER_TILE_PX; /* 256 */
 constexpr uint32_t kWarps = kThreads / 32;
 
-__host__ __device__ constexpr uint32_t stage_records(uint32_t R) { return R >= 4 ? 1024u : 512u; }
+/*
+ * Tile geometry.  A tile is (8R - 2) rows of 32 consecutive pixels: in rounds 0..R-2 every warp takes
+ * one row (row = 8*round + warp), in the last round only warps 2..7 do (row = 8*(R-1) + warp - 2).
+ * Warps 0 and 1 carry the CTA's serial work (scan + publish, look-back) and would otherwise finish
+ * every iteration last, with the other six waiting for them (profiles/r01d).
+ */
+__host__ __device__ constexpr uint32_t tile_rows(uint32_t R) { return 8u * R - 2u; }
+__host__ __device__ constexpr uint32_t tile_px(uint32_t R) { return 32u * tile_rows(R); }
+/* shared-memory slots per pixel: 1 for the large tile (a pixel's second event goes to the global spill
+ * array) so that four CTAs with three park buffers each still fit an SM, else 3 */
+__host__ __device__ constexpr uint32_t park_slots(uint32_t R) { return R >= 8 ? 1u : 3u; }
+constexpr uint32_t kParkBufs = 3;
 __host__ __device__ constexpr size_t frame_kernel_smem(uint32_t R) {
-  /* slot_t[kSlots][TILE] u32 | stage[records*3] u32 | frame[TILE] u8 | slot_d[kSlots][TILE] u8 */
-  return (size_t)kSlots * kThreads * R * 4u + (size_t)stage_records(R) * 12u + (size_t)kThreads * R + (size_t)kSlots * kThreads * R;
+  /* frame[2][8 warps][R*32] u8 ; per park buffer: slot_t[S][TILE] u32 | info[TILE] u16 | slot_d[S][TILE] u8 ; three of them */
+  return 2u * (size_t)kThreads * R + kParkBufs * ((size_t)park_slots(R) * tile_px(R) * 4u + (size_t)tile_px(R) * 2u + (size_t)park_slots(R) * tile_px(R));
+}
+
+/* mbarriers in shared memory: A = "this warp's state machines of tile n are done" (8 arrivals per
+ * phase, warps 0/1 wait), B = "serial work of iteration n done" (2 arrivals, the other warps wait for
+ * the phase of the PREVIOUS iteration).  Arriving never blocks and waiting does not count as arriving,
+ * so a warp waits only for the event it needs — a bar.sync would also make the six plain warps wait
+ * for each other (profiles/r01e). */
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) { /* release.cta */
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) { /* acquire.cta */
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok;
+  do {
+    /* the last operand is the suspend-time hint (ns): the warp sleeps in hardware instead of polling */
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity), "r"(1000000u)
+                 : "memory");
+  } while (!ok);
+}
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+/* pull the line holding *p towards L2 (no register, no scoreboard) */
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+/*
+ * Frame-wide exclusive offset of tile `tile` (run by warp 0): sum of the aggregates of the nearest
+ * predecessors back to the first one that already knows its own prefix.  128 predecessors per L2
+ * round trip (lane l looks at j-l, j-32-l, j-64-l, j-96-l).
+ */
+__device__ __forceinline__ uint32_t look_back(const FrameArgs& a, uint32_t tile, uint32_t lane) {
+  uint32_t excl = 0;
+  int j = (int)tile - 1;
+  for (;;) {
+    uint32_t flag[4], val[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+      const int idx = j - 32 * w - (int)lane;
+      flag[w] = kFlagPrefix;
+      val[w] = 0;
+      if (idx >= 0) {
+        unsigned long long s;
+        uint32_t shi;
+        do {
+          s = ld_status(&a.tile_status[idx]);
+          shi = (uint32_t)(s >> 32);
+        } while ((shi >> 2) != a.epoch || (shi & 3u) == 0u);
+        flag[w] = shi & 3u;
+        val[w] = (uint32_t)s;
+      }
+    }
+    /* windows are in order of distance: take everything up to and including the nearest prefix */
+    uint32_t contrib = 0;
+    bool done = false;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+      const uint32_t pm = __ballot_sync(kFull, flag[w] == kFlagPrefix);
+      if (!done) {
+        if (pm) {
+          const uint32_t first = (uint32_t)__ffs((int)pm) - 1u;
+          contrib += lane <= first ? val[w] : 0u;
+          done = true;
+        } else {
+          contrib += val[w];
+        }
+      }
+    }
+#pragma unroll
+    for (uint32_t o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(kFull, contrib, o);
+    excl += contrib;
+    if (done) break;
+    j -= 128;
+  }
+  return excl;
 }
 
 /*
- * A CTA owns a tile of 256*R consecutive raster indices and walks it as R sub-tiles of 256: in
- * sub-tile r thread t owns pixel tile_start + r*256 + t, so every header / node / sample access of
- * a warp is one contiguous run.  The header and root node of sub-tile r+1 are requested before the
- * state machine of sub-tile r runs (register double buffer).  Events are parked (EventPark), then
- * ONE scan + ONE look-back per tile gives the tile its place in the frame's event stream: the
- * serial look-back chain advances 64 tiles = 64*256*R pixels per L2 round trip, which is why R > 1
- * (at R = 1 the chain, not HBM, bounded the kernel: profiles/r01a).
  * kCount = true is the instrumented twin used (untimed) to measure the algorithmic bytes of a
  * workload: it additionally sums node loads / stores, display writes and events into a.counters.
  */
 template <int R, bool kCount>
-__global__ void __launch_bounds__(ADDER_TILE_PX) integrate_frame_kernel(const FrameArgs a) {
-  constexpr uint32_t TILE = kThreads * R;
-  constexpr uint32_t kStage = stage_records(R);
+__global__ void __launch_bounds__(ADDER_TILE_PX, 4) integrate_frame_kernel(const FrameArgs a) {
+  constexpr uint32_t ROWS = tile_rows(R), TILE = tile_px(R);
+  constexpr uint32_t S = park_slots(R);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
-  uint32_t* s_slot_t = reinterpret_cast<uint32_t*>(smem_dyn);
-  uint32_t* s_stage = s_slot_t + kSlots * TILE;
-  uint8_t* s_frame = reinterpret_cast<uint8_t*>(s_stage + kStage * 3u);
-  uint8_t* s_slot_d = s_frame + TILE;
+  /* frame[2][kWarps][R*32] u8 | slot_t[3][S][TILE] u32 | info[3][TILE] u16 | slot_d[3][S][TILE] u8 */
+  uint8_t* const s_frame = smem_dyn;
+  uint32_t* const s_slot_t = reinterpret_cast<uint32_t*>(smem_dyn + 2u * kThreads * R);
+  uint16_t* const s_info = reinterpret_cast<uint16_t*>(s_slot_t + kParkBufs * S * TILE);
+  uint8_t* const s_slot_d = reinterpret_cast<uint8_t*>(s_info + kParkBufs * TILE);
 
-  __shared__ uint32_t s_tile, s_prefix, s_total;
-  __shared__ uint32_t s_wtot[R * kWarps];
+  __shared__ uint32_t s_ticket[2], s_prefix[2], s_tot[kParkBufs];
+  __shared__ uint32_t s_wtot[kParkBufs][ROWS];
+  __shared__ __align__(8) unsigned long long s_bar_a, s_bar_b;
+  __shared__ uint8_t s_lut[260];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const bool duty = warp < 2u;
+  const uint32_t my_rows = duty ? (uint32_t)R - 1u : (uint32_t)R;
+  const bool frame_aligned = (reinterpret_cast<uintptr_t>(a.frame) & 15u) == 0;
+  /* this warp's row of round r, and the tile-relative index of this thread's pixel in it */
+  auto row_of = [&](uint32_t r) { return r + 1u < (uint32_t)R ? 8u * r + warp : 8u * ((uint32_t)R - 1u) + warp - 2u; };
 
-  /* tiles are handed out in ticket order so that a tile's predecessors are always already running:
-   * the look-back below can then never wait on a CTA that has not been scheduled. */
-  if (tid == 0) s_tile = atomicAdd(a.ticket, 1u) - a.ticket_base;
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const uint32_t tile_start = tile * TILE;
-
-  /* ---- frame bytes: 128-bit loads of the tile's samples, staged in shared memory -------------- */
-  if (tile_start + TILE <= a.P && ((reinterpret_cast<uintptr_t>(a.frame) & 15u) == 0)) {
-    for (uint32_t j = tid; j < TILE / 16; j += kThreads)
-      reinterpret_cast<uint4*>(s_frame)[j] = __ldg(reinterpret_cast<const uint4*>(a.frame + tile_start) + j);
-  } else {
-    for (uint32_t j = tid; j < TILE; j += kThreads)
-      if (tile_start + j < a.P) s_frame[j] = a.frame[tile_start + j];
+  /* tiles are handed out in ticket order so that a tile's predecessors are always held by CTAs that
+   * are already running: the look-back can then never wait on a CTA that has not been scheduled. */
+  if (tid == 0) {
+    const uint32_t t0 = atomicAdd(a.ticket, 1u) - a.ticket_base;
+    s_ticket[0] = t0;
+    s_ticket[1] = t0 < a.n_tiles ? atomicAdd(a.ticket, 1u) - a.ticket_base : kNone;
+    mbar_init(&s_bar_a, kWarps);
+    mbar_init(&s_bar_b, 2u);
   }
-
-  uint2 h_next = make_uint2(0u, 0u);
-  uint4 n_next = make_uint4(0u, 0u, 0u, 0u);
-  if (tile_start + tid < a.P) {
-    h_next = a.hdr[tile_start + tid];
-    n_next = a.nodes[tile_start + tid];
-  }
+  for (uint32_t j = tid; j < 257u; j += kThreads) s_lut[j] = a.px.exact_lut[j];
+  PxParams px = a.px; /* the display table is read from shared memory */
+  px.exact_lut = s_lut;
   __syncthreads();
+  uint32_t t_cur = s_ticket[0], t_m1 = kNone, t_m2 = kNone; /* tiles of iteration n, n-1, n-2 */
+  uint32_t n = 0, b = 0;                                     /* iteration, n % 3 */
 
-  uint32_t errbits = 0;
-  unsigned long long cnt_pack = 0; /* events of this thread's pixel in sub-tile r: byte r */
-  unsigned long long c_loads = 0, c_stores = 0, c_disp = 0;
-#pragma unroll 1
-  for (uint32_t r = 0; r < (uint32_t)R; r++) {
-    const uint32_t q = r * kThreads + tid; /* pixel-in-tile */
-    const uint32_t i = tile_start + q;
-    const uint2 hraw = h_next;
-    const uint4 nraw = n_next;
-    if (r + 1 < (uint32_t)R && i + kThreads < a.P) { /* next sub-tile's header and root */
-      h_next = a.hdr[i + kThreads];
-      n_next = a.nodes[i + kThreads];
-    }
-    if (i < a.P) {
-      GlobalNodes mem{a.nodes + i, a.level_stride, 1u, 0u};
-      EventPark park{s_slot_t + q, s_slot_d + q, a.nodes + i, a.level_stride, TILE, a.px.depth, 0u, 0u};
-      PxHeader h{__uint_as_float(hraw.x), hraw.y};
-      Node n0{__uint_as_float(nraw.x), __uint_as_float(nraw.y), __uint_as_float(nraw.z), nraw.w};
-      uint8_t disp;
-      const bool show = px_step(a.px, s_frame[q], h, n0, mem, park, errbits, &disp);
-      a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
-      if (show) a.running[i] = disp;
-      if (park.overflow) errbits |= ADDER_DEVERR_DEPTH;
-      cnt_pack |= (unsigned long long)park.n << (8u * r);
-      if (kCount) {
-        c_loads += mem.n_loads;
-        c_stores += mem.n_stores;
-        c_disp += show ? 1u : 0u;
+  /* samples of tile t -> this warp's staging area fb (asynchronously when whole and aligned) */
+  auto fetch_frame = [&](uint32_t t, uint32_t fb) {
+    const uint32_t start = t * TILE;
+    uint8_t* dst = s_frame + fb * (kThreads * R) + warp * (R * 32u);
+    if (start + TILE <= a.P && frame_aligned) {
+      if (lane < 2u * my_rows) cp_async16(dst + lane * 16u, a.frame + start + 32u * row_of(lane >> 1) + (lane & 1u) * 16u);
+    } else {
+      for (uint32_t r = 0; r < my_rows; r++) {
+        const uint32_t i = start + 32u * row_of(r) + lane;
+        if (i < a.P) dst[r * 32u + lane] = a.frame[i];
       }
     }
+  };
+  /* header, root and level 1 of the next row are requested before the current row is worked on
+   * (root and level 1 do not need the header: both are fetched before the length is known) */
+  uint2 h_next = make_uint2(0u, 0u);
+  uint4 n0_next = make_uint4(0u, 0u, 0u, 0u), n1_next = n0_next;
+  auto fetch_px = [&](uint32_t i) {
+    if (i < a.P) {
+      h_next = a.hdr[i];
+      n0_next = a.nodes[i];
+      n1_next = a.nodes[a.level_stride + i];
+    }
+  };
+  if (t_cur < a.n_tiles) {
+    fetch_frame(t_cur, 0u);
+    if (my_rows) fetch_px(t_cur * TILE + 32u * row_of(0u) + lane);
   }
-  if (kCount) {
-    atomicAdd(&a.counters[0], c_loads);
-    atomicAdd(&a.counters[1], c_stores);
-    atomicAdd(&a.counters[2], c_disp);
-  }
-  if (errbits) atomicOr(a.err, errbits);
 
-  /* ---- ordered compaction: tile scan, decoupled look-back across tiles, staged coalesced write -- */
-  uint32_t off[R]; /* first record of this thread's pixel in sub-tile r, tile-relative (after the scan) */
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    const uint32_t nev = (uint32_t)(cnt_pack >> (8 * r)) & 0xFFu;
-    uint32_t incl = nev;
-#pragma unroll
-    for (uint32_t o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_wtot[r * kWarps + warp] = incl;
-    off[r] = incl - nev;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    /* exclusive scan of the R*8 (sub-tile, warp) totals, in pixel order */
-    constexpr uint32_t kPer = (R * kWarps + 31) / 32;
-    uint32_t mine[kPer], sum = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < kPer; j++) {
-      const uint32_t idx = lane * kPer + j;
-      mine[j] = idx < R * kWarps ? s_wtot[idx] : 0u;
-      sum += mine[j];
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (uint32_t o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const uint32_t tot = __shfl_sync(kFull, incl, 31);
-    uint32_t run = incl - sum;
-#pragma unroll
-    for (uint32_t j = 0; j < kPer; j++) {
-      const uint32_t idx = lane * kPer + j;
-      if (idx < R * kWarps) s_wtot[idx] = run;
-      run += mine[j];
-    }
+  while (t_cur < a.n_tiles || t_m1 < a.n_tiles || t_m2 < a.n_tiles) {
+    const bool have_tile = t_cur < a.n_tiles;
+    /* ticket of iteration n+2, requested now and needed after the state machines (drawn only while
+     * the previous one was a tile: every CTA draws exactly one ticket past the end, which is what the
+     * host advances ticket_base by) */
+    uint32_t t_next2 = kNone;
+    if (tid == 0 && s_ticket[(n + 1u) & 1u] < a.n_tiles) t_next2 = atomicAdd(a.ticket, 1u) - a.ticket_base;
 
-    const unsigned long long tag = (unsigned long long)a.epoch << 2;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      if (lane == 0) st_status(&a.tile_status[0], ((tag | kFlagPrefix) << 32) | tot);
-    } else {
-      if (lane == 0) st_status(&a.tile_status[tile], ((tag | kFlagAggregate) << 32) | tot);
-      int j = (int)tile - 1;
-      for (;;) { /* 64 predecessors per round trip: lane l looks at j-l and j-32-l */
-        uint32_t flag[2], val[2];
-#pragma unroll
-        for (int w = 0; w < 2; w++) {
-          const int idx = j - 32 * w - (int)lane;
-          flag[w] = kFlagPrefix;
-          val[w] = 0;
-          if (idx >= 0) {
-            unsigned long long s;
-            uint32_t shi;
-            do {
-              s = ld_status(&a.tile_status[idx]);
-              shi = (uint32_t)(s >> 32);
-            } while ((shi >> 2) != a.epoch || (shi & 3u) == 0u);
-            flag[w] = shi & 3u;
-            val[w] = (uint32_t)s;
+    /* ---- stage 1: the state machines of tile n --------------------------------------------------- */
+    if (have_tile) {
+      const uint32_t tile_start = t_cur * TILE;
+      uint32_t* const slot_t = s_slot_t + b * (S * TILE);
+      uint8_t* const slot_d = s_slot_d + b * (S * TILE);
+      uint16_t* const info = s_info + b * TILE;
+      const uint8_t* const samples = s_frame + (n & 1u) * (kThreads * R) + warp * (R * 32u);
+      cp_async_wait_all();
+      __syncwarp();
+
+      uint32_t errbits = 0;
+      unsigned long long c_loads = 0, c_stores = 0, c_disp = 0;
+#pragma unroll 1
+      for (uint32_t r = 0; r < my_rows; r++) {
+        const uint32_t row = row_of(r);
+        const uint32_t q = 32u * row + lane; /* pixel-in-tile */
+        const uint32_t i = tile_start + q;
+        const uint2 hraw = h_next;
+        const uint4 n0raw = n0_next, n1raw = n1_next;
+        if (r + 1u < my_rows) fetch_px(tile_start + 32u * row_of(r + 1u) + lane);
+        uint32_t nev = 0;
+        if (i < a.P) {
+          GlobalNodes mem{a.nodes + i, a.level_stride, 1u, 0u};
+          EventPark<S> park{slot_t + q, slot_d + q, a.nodes + i, a.spill1 + i, a.level_stride, TILE, a.px.depth, 0u, 0u};
+          PxHeader h{__uint_as_float(hraw.x), hraw.y};
+          const Node n0{__uint_as_float(n0raw.x), __uint_as_float(n0raw.y), __uint_as_float(n0raw.z), n0raw.w};
+          const Node n1{__uint_as_float(n1raw.x), __uint_as_float(n1raw.y), __uint_as_float(n1raw.z), n1raw.w};
+          uint8_t disp;
+          const bool show = px_step(px, samples[r * 32u + lane], h, n0, n1, mem, park, errbits, &disp);
+          a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
+          if (show) a.running[i] = disp;
+          if (park.overflow) errbits |= ADDER_DEVERR_DEPTH;
+          nev = park.n;
+          if (kCount) {
+            c_loads += mem.n_loads;
+            c_stores += mem.n_stores;
+            c_disp += show ? 1u : 0u;
           }
         }
-        const uint32_t pm0 = __ballot_sync(kFull, flag[0] == kFlagPrefix);
-        const uint32_t pm1 = __ballot_sync(kFull, flag[1] == kFlagPrefix);
-        uint32_t contrib;
-        if (pm0) { /* nearest predecessor holding a prefix is in the first window */
-          const uint32_t first = (uint32_t)__ffs((int)pm0) - 1u;
-          contrib = lane <= first ? val[0] : 0u;
+        /* place of this pixel's records inside its row's run: two ballots cover 0..2 events per
+         * pixel, the shuffle scan is only taken when some pixel of the row emitted more */
+        const uint32_t le = 0xFFFFFFFFu >> (31u - lane);
+        const uint32_t b1 = __ballot_sync(kFull, nev >= 1u), b2 = __ballot_sync(kFull, nev >= 2u);
+        uint32_t incl, wtotal;
+        if (__ballot_sync(kFull, nev >= 3u) == 0u) {
+          incl = (uint32_t)__popc(b1 & le) + (uint32_t)__popc(b2 & le);
+          wtotal = (uint32_t)__popc(b1) + (uint32_t)__popc(b2);
         } else {
-          const uint32_t first = pm1 ? (uint32_t)__ffs((int)pm1) - 1u : 31u;
-          contrib = val[0] + (lane <= first ? val[1] : 0u);
+          incl = nev;
+#pragma unroll
+          for (uint32_t o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+          }
+          wtotal = __shfl_sync(kFull, incl, 31);
         }
-#pragma unroll
-        for (uint32_t o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(kFull, contrib, o);
-        excl += contrib;
-        if (pm0 | pm1) break;
-        j -= 64;
+        info[q] = (uint16_t)((incl - nev) | (nev << 10)); /* <= 31*33 = 1023 | <= 33 */
+        if (lane == 0) s_wtot[b][row] = wtotal;
       }
-      if (lane == 0) st_status(&a.tile_status[tile], ((tag | kFlagPrefix) << 32) | (excl + tot));
-    }
-    if (lane == 0) {
-      s_prefix = excl;
-      s_total = tot;
-      if (kCount) atomicAdd(&a.counters[3], (unsigned long long)tot);
-      if (tile == a.n_tiles - 1u) {
-        if (a.chunk_off) a.chunk_off[a.n_chunks] = excl + tot;
-        if (a.total_events) atomicAdd(a.total_events, (unsigned long long)(excl + tot));
+      if (kCount) {
+        atomicAdd(&a.counters[0], c_loads);
+        atomicAdd(&a.counters[1], c_stores);
+        atomicAdd(&a.counters[2], c_disp);
       }
+      if (errbits) atomicOr(a.err, errbits);
     }
-  }
-  __syncthreads();
-  const uint32_t prefix = s_prefix, total = s_total;
-#pragma unroll
-  for (int r = 0; r < R; r++) off[r] += s_wtot[r * kWarps + warp];
 
-  if (a.chunk_off) { /* lengths of the reference's Vec<Vec<Event>>, video.rs:677-734 */
-    if (a.chunk_px >= TILE) { /* at most one chunk starts inside this tile */
-      const uint32_t cb = ((tile_start + a.chunk_px - 1u) / a.chunk_px) * a.chunk_px;
-      const uint32_t q = cb - tile_start;
-      if (cb < a.P && q < TILE && (q & (kThreads - 1u)) == tid) {
-        uint32_t o = 0;
+    /* ---- rendezvous + stage 2 (warps 0 and 1): the serial work ------------------------------------ */
+    /* The plain warps wait for B(n-1) BEFORE they arrive at A(n): warps 0/1 can then not complete
+     * B(n) (which would alias B(n-1)'s parity) while somebody still waits for B(n-1). */
+    if (!duty && n != 0u) mbar_wait(&s_bar_b, (n - 1u) & 1u); /* serial work of iteration n-1 (signalled a tile ago) */
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_bar_a); /* this warp's rows of tile n are parked, their totals stored */
+    if (duty) {
+      mbar_wait(&s_bar_a, n & 1u); /* every row total of tile n is in shared memory */
+      const unsigned long long tag = (unsigned long long)a.epoch << 2;
+      if (warp == 0) {
+        if (have_tile) {
+          /* exclusive scan of the row totals, in pixel order; publish the aggregate */
+          constexpr uint32_t kPer = (ROWS + 31) / 32;
+          uint32_t mine[kPer], sum = 0;
 #pragma unroll
-        for (int r = 0; r < R; r++)
-          if ((q >> 8) == (uint32_t)r) o = off[r];
-        a.chunk_off[cb / a.chunk_px] = prefix + o;
+          for (uint32_t j = 0; j < kPer; j++) {
+            const uint32_t idx = lane * kPer + j;
+            mine[j] = idx < ROWS ? s_wtot[b][idx] : 0u;
+            sum += mine[j];
+          }
+          uint32_t incl = sum;
+#pragma unroll
+          for (uint32_t o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const uint32_t tot = __shfl_sync(kFull, incl, 31);
+          uint32_t run = incl - sum;
+#pragma unroll
+          for (uint32_t j = 0; j < kPer; j++) {
+            const uint32_t idx = lane * kPer + j;
+            if (idx < ROWS) s_wtot[b][idx] = run;
+            run += mine[j];
+          }
+          if (lane == 0) {
+            /* tile 0 knows its prefix (0) at once; the others publish their aggregate now and their
+             * inclusive prefix after their look-back, one iteration later */
+            st_status(&a.tile_status[t_cur], ((tag | (t_cur == 0u ? kFlagPrefix : kFlagAggregate)) << 32) | tot);
+            s_tot[b] = tot;
+            if (kCount) atomicAdd(&a.counters[3], (unsigned long long)tot);
+          }
+        }
+        if (lane == 0) s_ticket[n & 1u] = t_next2; /* slot (n+2) & 1 */
+      } else if (t_m1 < a.n_tiles) {
+        const uint32_t excl = t_m1 != 0u ? look_back(a, t_m1, lane) : 0u;
+        if (lane == 0) {
+          const uint32_t incl_all = excl + s_tot[b == 0u ? 2u : b - 1u];
+          if (t_m1 != 0u) st_status(&a.tile_status[t_m1], ((tag | kFlagPrefix) << 32) | incl_all);
+          s_prefix[(n + 1u) & 1u] = excl; /* slot (n-1) & 1 */
+          if (t_m1 == a.n_tiles - 1u) {
+            if (a.chunk_off) a.chunk_off[a.n_chunks] = incl_all;
+            if (a.total_events) atomicAdd(a.total_events, (unsigned long long)incl_all);
+          }
+        }
       }
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        const uint32_t i = tile_start + r * kThreads + tid;
-        if (i < a.P && i % a.chunk_px == 0u) a.chunk_off[i / a.chunk_px] = prefix + off[r];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_bar_b); /* serial work of iteration n done */
+    }
+
+    /* ---- what iteration n+1 will need: its samples and its first row ------------------------------ */
+    const uint32_t t_next = s_ticket[(n + 1u) & 1u];
+    if (t_next < a.n_tiles) {
+      fetch_frame(t_next, (n + 1u) & 1u);
+      const uint32_t i = t_next * TILE + 32u * row_of(0u) + lane;
+      if (my_rows && i < a.P) { /* towards L2 now, into registers after the write-out */
+        if ((lane & 15u) == 0u) prefetch_l2(a.hdr + i);
+        if ((lane & 7u) == 0u) {
+          prefetch_l2(a.nodes + i);
+          prefetch_l2(a.nodes + a.level_stride + i);
+        }
       }
     }
-  }
 
-  if (total == 0u) return;
-  for (uint32_t sbase = 0; sbase < total; sbase += kStage) {
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const uint32_t nev = (uint32_t)(cnt_pack >> (8 * r)) & 0xFFu;
-      if (nev && off[r] + nev > sbase && off[r] < sbase + kStage) {
-        const uint32_t q = r * kThreads + tid;
-        const uint32_t i = tile_start + q;
-        const uint32_t row = i / a.WC, rem = i - row * a.WC;
-        const uint32_t x = rem / a.C, c = rem - x * a.C;
-        const uint32_t w0 = x | ((row + a.row0) << 16);
-        const uint32_t w1 = a.C == 1u ? ADDER_C_NONE : c;
-        EventPark park{s_slot_t + q, s_slot_d + q, a.nodes + i, a.level_stride, TILE, a.px.depth, nev, 0u};
-        for (uint32_t e = 0; e < nev; e++) {
-          const uint32_t li = off[r] + e - sbase; /* unsigned wrap: records before this window fail the test too */
-          if (li < kStage) {
+    /* ---- stage 3: write-out of tile n-2, every thread stores its own pixels' records ------------- */
+    if (t_m2 < a.n_tiles) {
+      const uint32_t pb = b == 2u ? 0u : b + 1u; /* (n-2) % 3 */
+      const uint32_t prefix = s_prefix[n & 1u];  /* slot (n-2) & 1 */
+      const uint32_t pstart = t_m2 * TILE;
+      const uint32_t* const pslot_t = s_slot_t + pb * (S * TILE);
+      const uint8_t* const pslot_d = s_slot_d + pb * (S * TILE);
+      const uint16_t* const pinfo = s_info + pb * TILE;
+      uint32_t capbits = 0;
+      if (a.chunk_off) { /* lengths of the reference's Vec<Vec<Event>>, video.rs:677-734 */
+        if (a.chunk_px >= TILE) { /* at most one chunk starts inside this tile */
+          const uint32_t t_end = pstart + TILE - 1u < a.P - 1u ? pstart + TILE - 1u : a.P - 1u;
+          const uint32_t ch = a.chunk_magic ? mulhi_u32_u64(t_end, a.chunk_magic) : t_end; /* chunk of the tile's last pixel */
+          const uint32_t cb = ch * a.chunk_px;                                              /* its first pixel */
+          if (cb >= pstart) {
+            const uint32_t qq = cb - pstart, row = qq >> 5;
+            const uint32_t owner = row < 8u * ((uint32_t)R - 1u) ? (row & 7u) : row - 8u * ((uint32_t)R - 1u) + 2u;
+            if (owner * 32u + (qq & 31u) == tid) a.chunk_off[ch] = prefix + s_wtot[pb][row] + (pinfo[qq] & 1023u);
+          }
+        } else {
+          for (uint32_t r = 0; r < my_rows; r++) {
+            const uint32_t row = row_of(r), q = 32u * row + lane, i = pstart + q;
+            if (i < a.P && i % a.chunk_px == 0u) a.chunk_off[i / a.chunk_px] = prefix + s_wtot[pb][row] + (pinfo[q] & 1023u);
+          }
+        }
+      }
+#pragma unroll 1
+      for (uint32_t r = 0; r < my_rows; r++) {
+        const uint32_t row = row_of(r);
+        const uint32_t q = 32u * row + lane;
+        const uint32_t inf = pinfo[q];
+        const uint32_t nev = inf >> 10;
+        if (nev) {
+          const uint32_t i = pstart + q;
+          const uint32_t first = prefix + s_wtot[pb][row] + (inf & 1023u);
+          const uint32_t y = a.wc_magic ? mulhi_u32_u64(i, a.wc_magic) : i;
+          const uint32_t rem = i - y * a.WC;
+          uint32_t x = rem, c = ADDER_C_NONE;
+          if (a.C != 1u) {
+            x = __umulhi(rem, a.c_magic);
+            c = rem - x * a.C;
+          }
+          const uint32_t w0 = x | ((y + a.row0) << 16);
+          EventPark<S> park{const_cast<uint32_t*>(pslot_t) + q, const_cast<uint8_t*>(pslot_d) + q, a.nodes + i, a.spill1 + i, a.level_stride, TILE, a.px.depth, nev, 0u};
+          for (uint32_t e = 0; e < nev; e++) {
             uint32_t dd, tt;
             park.get(e, dd, tt);
-            s_stage[li * 3u + 0u] = w0;
-            s_stage[li * 3u + 1u] = w1 | (dd << 8);
-            s_stage[li * 3u + 2u] = tt;
+            const unsigned long long rec = (unsigned long long)first + e;
+            if (rec < a.ev_cap) {
+              uint32_t* dst = a.ev_words + rec * 3ull;
+              dst[0] = w0;
+              dst[1] = c | (dd << 8);
+              dst[2] = tt;
+            } else {
+              capbits = ADDER_DEVERR_CAPACITY;
+            }
           }
         }
       }
+      if (capbits) atomicOr(a.err, capbits);
     }
-    __syncthreads();
-    const uint32_t n = total - sbase < kStage ? total - sbase : kStage;
-    const unsigned long long first = (unsigned long long)prefix + sbase;
-    uint32_t can = 0;
-    if (first < a.ev_cap) can = (a.ev_cap - first) < n ? (uint32_t)(a.ev_cap - first) : n;
-    if (can < n && tid == 0) atomicOr(a.err, ADDER_DEVERR_CAPACITY);
-    uint32_t* dst = a.ev_words + first * 3ull;
-    for (uint32_t j = tid; j < can * 3u; j += kThreads) dst[j] = s_stage[j];
-    __syncthreads();
+
+    if (t_next < a.n_tiles && my_rows) fetch_px(t_next * TILE + 32u * row_of(0u) + lane);
+    t_m2 = t_m1;
+    t_m1 = t_cur;
+    t_cur = t_next;
+    n++;
+    b = b == 2u ? 0u : b + 1u;
+    __syncwarp(); /* this warp's lanes leave the iteration together (its own s_wtot entries are reused) */
   }
 }
 

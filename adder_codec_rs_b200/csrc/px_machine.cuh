@@ -17,6 +17,15 @@
  *
  * All f32/f64 arithmetic goes through the rn_* wrappers: explicit round-to-nearest intrinsics on the
  * device (never contracted into an FMA), plain operators on the host (built with -ffp-contract=off).
+ *
+ * Three things are done differently from a literal transcription, each with identical results:
+ *  - `u / ref_time` in delta_t_to_absolute_t is a multiply by ceil(2^64 / ref) (exact for every u32);
+ *  - the Intensity display byte floor(fl64(fl64(2^d / t) * ref)) is first estimated in f32 (good to
+ *    ~1e-4 absolute below 256, the f64 value to ~1e-13, so away from integers both truncate alike);
+ *    within 2^-10 of an integer the side is decided by an exact u64 comparison, and the exactly
+ *    integral case by a 257-entry table of the reference's own f64 expression (frame_value_u8);
+ *  - the display byte is not recomputed while the root's best event is the one it was computed
+ *    from (same inputs -> same byte); PxParams::display == 2 forces it after a parameter change.
  */
 #pragma once
 #include <stdint.h>
@@ -53,6 +62,12 @@ ADDER_HD uint32_t clz32(uint32_t x) { return (uint32_t)__clz((int)x); }
 ADDER_HD uint32_t f_bits(float x) { return __float_as_uint(x); }
 ADDER_HD float bits_f(uint32_t x) { return __uint_as_float(x); }
 ADDER_HD double bits_d(uint64_t x) { return __longlong_as_double((long long)x); }
+ADDER_HD float fast_div(float a, float b) { return __fdividef(a, b); } /* estimate only, never a result */
+ADDER_HD uint32_t mulhi_u32_u64(uint32_t u, uint64_t m) { /* floor(u * m / 2^64) */
+  const uint64_t t = (uint64_t)u * (uint32_t)m;
+  const uint64_t s = (uint64_t)u * (uint32_t)(m >> 32) + (t >> 32);
+  return (uint32_t)(s >> 32);
+}
 #else
 ADDER_HD float rn_add(float a, float b) { volatile float r = a + b; return r; }
 ADDER_HD float rn_sub(float a, float b) { volatile float r = a - b; return r; }
@@ -67,6 +82,18 @@ ADDER_HD uint32_t clz32(uint32_t x) { return x ? (uint32_t)__builtin_clz(x) : 32
 ADDER_HD uint32_t f_bits(float x) { uint32_t b; memcpy(&b, &x, 4); return b; }
 ADDER_HD float bits_f(uint32_t x) { float f; memcpy(&f, &x, 4); return f; }
 ADDER_HD double bits_d(uint64_t x) { double f; memcpy(&f, &x, 8); return f; }
+#ifdef ADDER_HOST_SIM /* tests perturb the estimate by a few ulp to stand for __fdividef's error */
+extern int g_fast_div_ulps;
+ADDER_HD float fast_div(float a, float b) {
+  float r = a / b;
+  uint32_t bits = f_bits(r);
+  if (r > 0.0f && r < 3.0e38f) bits = (uint32_t)((int32_t)bits + g_fast_div_ulps);
+  return bits_f(bits);
+}
+#else
+ADDER_HD float fast_div(float a, float b) { return a / b; }
+#endif
+ADDER_HD uint32_t mulhi_u32_u64(uint32_t u, uint64_t m) { return (uint32_t)(((unsigned __int128)u * m) >> 64); }
 #endif
 
 /* per-frame constants of the state machine (VideoStateParams video.rs:160-182, CrfParameters
@@ -74,12 +101,33 @@ ADDER_HD double bits_d(uint64_t x) { double f; memcpy(&f, &x, 8); return f; }
 struct PxParams {
   float time, running_t_prev, running_t, dtm_f;
   uint32_t ref, dtm;
+  uint64_t ref_magic; /* ceil(2^64 / ref); 0 stands for ref == 1 (see ref_magic_of) */
   uint32_t c_max, vel_m1, cnt_inc;
-  uint32_t collapse, abs_time, view_mode, display;
+  uint32_t collapse, abs_time, view_mode;
+  uint32_t display; /* 0 off, 1 on, 2 on and recompute every pixel whose root holds a best event */
   uint32_t depth;
   double tpf;
+  float tpf_f; /* (float)tpf, for the display estimate only */
+  const uint8_t* exact_lut; /* [257]: min(255, trunc(fl64(fl64(k / ref) * ref))), build_exact_lut() */
   float practical_d_max;
 };
+
+inline uint64_t ref_magic_of(uint32_t ref) { /* host side */
+  if (ref <= 1u) return 0ull;
+  const uint64_t q = ~0ull / ref; /* floor((2^64 - 1) / ref) */
+  return q + 1ull;                /* = ceil(2^64 / ref) for every ref >= 2 (also powers of two) */
+}
+/* The Intensity display byte of an event whose 2^d / t * ref is exactly the integer k (host side, f64
+ * like the reference: scale_intensity.rs:262-270 then :58-68). */
+inline void build_exact_lut(uint32_t ref, uint8_t out[257]) {
+  for (uint32_t k = 0; k <= 256u; k++) {
+    volatile double q = (double)k / (double)ref;
+    volatile double r = q * (double)ref;
+    out[k] = (uint8_t)(r >= 255.0 ? 255u : (uint32_t)r);
+  }
+}
+/* u / ref for any u32 (error term u*e/(ref*2^64) < 2^-32 < 1/ref, so the floor is exact) */
+ADDER_HD uint32_t div_ref(const PxParams& a, uint32_t u) { return a.ref_magic ? mulhi_u32_u64(u, a.ref_magic) : u; }
 
 struct Node {
   float integ, dt, best_dt;
@@ -135,14 +183,27 @@ ADDER_HD bool integrate_main(Node& n, float intensity, float time) {
 ADDER_HD uint8_t frame_value_u8(const PxParams& a, uint32_t d, uint32_t t, float lf) {
   float q;
   switch (a.view_mode) {
-    case 0: { /* Intensity: f64 */
-      double inten;
-      if (d >= 129u) {
-        inten = 0.0;
-      } else {
-        const double p = d >= 128u ? 0.0 : bits_d((uint64_t)(d + 1023u) << 52); /* D_SHIFT_F64[d] */
-        inten = t == 0u ? p : rn_ddiv(p, (double)t);
+    case 0: { /* Intensity: f64 in the reference */
+      if (d >= 128u) return 0; /* D_SHIFT_F64[128] = 0; d >= 129 -> 0 (:262-270) */
+      const uint32_t tt = t == 0u ? 1u : t; /* t == 0 -> the intensity is 2^d itself */
+      const float est = rn_mul(fast_div(bits_f((d + 127u) << 23), u2f(tt)), a.tpf_f);
+      if (!(est < 256.5f)) return 255; /* also +inf; the exact value is > 256 */
+      const uint32_t k = f2u(est);
+      const float fr = rn_sub(est, u2f(k));
+      if (fr > 0.0009765625f && fr < 0.9990234375f) return (uint8_t)(k > 255u ? 255u : k);
+      if (d < 32u) {
+        /* X = 2^d*ref/tt is within 2^-9 of the integer kc.  If it is not kc itself it is at least
+         * 1/tt >= 2^-32 away, far more than the 2^-44 the two f64 roundings can move it, so the
+         * side it lies on decides the byte; if it IS kc the reference computes fl(fl(kc/ref)*ref),
+         * which depends on (kc, ref) only and is tabulated by the host in f64. */
+        const uint32_t kc = fr < 0.5f ? k : k + 1u;
+        const uint64_t n = (uint64_t)a.ref << d, m = (uint64_t)tt * kc;
+        if (n == m) return a.exact_lut[kc];
+        const uint32_t r = n > m ? kc : kc - 1u;
+        return (uint8_t)(r > 255u ? 255u : r);
       }
+      const double p = bits_d((uint64_t)(d + 1023u) << 52); /* D_SHIFT_F64[d] */
+      const double inten = t == 0u ? p : rn_ddiv(p, (double)t);
       const uint32_t u = d2u(rn_dmul(inten, a.tpf)); /* saturating, NaN -> 0 */
       return (uint8_t)(u > 255u ? 255u : u);
     }
@@ -163,20 +224,42 @@ template <class Sink>
 ADDER_HD void emit_abs(const PxParams& a, Sink& sink, float& lf, uint32_t d, float dt) {
   if (a.abs_time) {
     dt = rn_add(dt, lf);
-    lf = dt;
-    const uint32_t u = f2u(lf);
-    const uint32_t q = u / a.ref;
-    lf = (u - q * a.ref == 0u) ? u2f(u) : u2f((q + 1u) * a.ref);
+    const uint32_t u = f2u(dt);
+    const uint32_t m = div_ref(a, u) * a.ref;
+    lf = u2f(m == u ? u : m + a.ref);
+    sink.push(d, u);
+  } else {
+    sink.push(d, f2u(dt));
   }
-  sink.push(d, f2u(dt));
+}
+
+/* One node of pop_best_events (:223-247): its best event, or a zero event, if it has one to give. */
+template <class Sink>
+ADDER_HD bool pop_node(const PxParams& a, Sink& sink, float& lf, Node& nk) {
+  uint32_t ed;
+  float edt;
+  if (NODE_HAS_BEST(nk.w)) {
+    ed = NODE_BEST_D(nk.w);
+    edt = nk.best_dt;
+  } else if (nk.dt > 0.0f && nk.integ == 0.0f) { /* get_zero_event(idx, None) :96-111 */
+    ed = ADDER_D_ZERO_INTEGRATION;
+    edt = nk.dt;
+    nk.dt = 0.0f;
+  } else {
+    return false;
+  }
+  emit_abs(a, sink, lf, ed, edt);
+  return true;
 }
 
 /*
  * One pixel, one frame.  `v` is the u8 sample, `h` the pixel's header (updated in place), `n0` its
- * root node (already loaded).  Returns true and sets *disp when running_intensities must be written.
+ * root node and `n1` its level-1 node as loaded (n1 is only looked at when the stack has a level 1;
+ * the kernel fetches both before it knows the length).  Returns true and sets *disp when
+ * running_intensities must be written.
  */
 template <class Mem, class Sink>
-ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& mem, Sink& sink, uint32_t& errbits,
+ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node n1, Mem& mem, Sink& sink, uint32_t& errbits,
                       uint8_t* disp) {
   const float intensity = (float)v; /* matrix.mapv(f32::from), video.rs:665 */
   const float time = a.time;
@@ -184,39 +267,34 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& 
   uint32_t base = HDR_BASE(h.y), cth = HDR_CTHRESH(h.y), cnt = HDR_COUNTER(h.y);
   uint32_t len = HDR_LENGTH(h.y);
   uint32_t popped = HDR_POPPED(h.y);
+  bool root_new = false; /* the root's best event after this frame is not the one of the last frame */
 
   /* ---- video.rs:1338-1358: the pixel changed by more than c_thresh -> pop_best_events -------- */
   const uint32_t lo = base > cth ? base - cth : 0u;          /* saturating_sub */
   const uint32_t hi = base + cth > 255u ? 255u : base + cth; /* saturating_add */
   if (v < lo || v > hi) {
-    const bool collapse_case = popped && a.collapse;
-    bool any = false;
-    Node tail = n0;
-    for (uint32_t k = 0; k < len; k++) {
-      Node nk = (k == 0) ? n0 : mem.load(k);
-      if (NODE_HAS_BEST(nk.w)) {
-        emit_abs(a, sink, lf, NODE_BEST_D(nk.w), nk.best_dt);
-        any = true;
-      } else if (nk.dt > 0.0f && nk.integ == 0.0f) { /* get_zero_event(idx, None) :96-111 */
-        emit_abs(a, sink, lf, ADDER_D_ZERO_INTEGRATION, nk.dt);
-        nk.dt = 0.0f;
-        any = true;
+    /* Collapse after a Δt_max pop keeps only the first event (:249-265): later nodes would only
+     * touch last_fired_t, which is overwritten below, and a root that is replaced. */
+    const bool first_only = popped && a.collapse;
+    bool any = pop_node(a, sink, lf, n0);
+    if (len > 1u && !(first_only && any)) {
+      mem.used_preloaded(); /* n1 */
+      any |= pop_node(a, sink, lf, n1);
+      n0 = n1; /* the tail so far */
+      for (uint32_t k = 2; k < len && !(first_only && any); k++) {
+        n0 = mem.load(k);
+        any |= pop_node(a, sink, lf, n0);
       }
-      tail = nk;
-      /* Collapse after a Δt_max pop keeps only the first event (:249-265): later nodes would only
-       * touch last_fired_t, which is overwritten below, and a root that is replaced. */
-      if (collapse_case && any) break;
     }
-    if (collapse_case && any) {
+    if (first_only && any) {
       lf = a.running_t_prev; /* running_t before this frame's `+= time` (:337 runs later) */
       sink.push(ADDER_D_EMPTY, f2u(a.running_t_prev));
       n0 = fresh_node(intensity);
-    } else {
-      n0 = tail; /* :267-270, the tail becomes the root */
-    }
+    } /* else :267-270: the tail (now in n0) becomes the root */
     len = 1;
     popped = 0;
     base = v;
+    root_new = true;
   }
 
   /* ---- integrate (:317-413), node 0 ---------------------------------------------------------- */
@@ -242,11 +320,11 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& 
   float disp_dt = 0.0f;
   uint32_t new_len = 1;
   if (fired0) { /* :344-355: child seeded from this intensity, deeper nodes dropped (FramePerfect :366) */
+    root_new = true;
     if (need_pop) {
       emit_abs(a, sink, lf, NODE_BEST_D(n0.w), n0.best_dt);
       popped = 1;
       mem.store(0, fresh_node(intensity));
-      new_len = 1;
     } else {
       mem.store(0, n0);
       if (a.depth > 1u) mem.store(1, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
@@ -260,6 +338,7 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& 
     bool cut = false;
     if (need_pop) {
       popped = 1;
+      root_new = true;
       if (!NODE_HAS_BEST(n0.w)) {
         if (n0.integ == 0.0f && n0.dt > 0.0f) { /* zero event, :155-160 */
           emit_abs(a, sink, lf, ADDER_D_ZERO_INTEGRATION, n0.dt);
@@ -270,7 +349,6 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& 
           const uint32_t sd = n0.integ < 1.0f ? ADDER_D_ZERO_INTEGRATION : 31u - clz32(f2u(n0.integ));
           emit_abs(a, sink, lf, sd, n0.dt);
           mem.store(0, fresh_node(intensity));
-          new_len = 1;
           cut = true;
         }
       } else {
@@ -291,8 +369,11 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& 
       /* Collapse after a Δt_max pop integrates the root only (:360-362): unless the stack moves up
        * a level, nothing below the root changes and nothing below it is read. */
       const uint32_t k_end = (only_root && !shift) ? 1u : len;
+      Node nk = n1; /* level 1 is already here; level k+1 is requested before level k is worked on */
+      if (k_end > 1u) mem.used_preloaded(); /* n1 */
       for (uint32_t k = 1; k < k_end; k++) {
-        Node nk = mem.load(k);
+        Node nxt = nk;
+        if (k + 1u < k_end) nxt = mem.load(k + 1u);
         bool fired = false;
         if (!only_root) {
           if (k == len - 1u && nk.dt == 0.0f && nk.integ == 0.0f) /* :332-335 */
@@ -308,8 +389,10 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& 
         if (fired) {
           if (k + 1u - shift < a.depth) mem.store(k + 1u - shift, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
           new_len = k + 2u;
+          if (k + 1u < k_end) mem.unused_load(); /* the level requested ahead is dropped with the rest (:366) */
           break;
         }
+        nk = nxt;
       }
       new_len -= shift;
       if (new_len == 0u) new_len = 1u; /* flagged INTERNAL above */
@@ -319,7 +402,8 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Mem& 
 
   h.lf = lf;
   h.y = HDR_PACK(base, cth, cnt, new_len, dtm_reached, popped);
-  if (a.display && disp_has) { /* video.rs:713-730 */
+  /* video.rs:713-730.  An unchanged root best event gives the byte already in running_intensities. */
+  if (disp_has && a.display && (root_new || a.display == 2u || a.view_mode == 3u)) {
     *disp = frame_value_u8(a, disp_d, f2u(disp_dt), lf);
     return true;
   }

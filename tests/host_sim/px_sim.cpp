@@ -10,15 +10,21 @@
 #include <cstring>
 #include <vector>
 
+#define ADDER_HOST_SIM 1
 #include "../../include/adder_b200.h"
 #include "../../adder_codec_rs_b200/csrc/px_machine.cuh"
 
+namespace adder {
+int g_fast_div_ulps = 0;
+}
 namespace {
 struct HostNodes {
   adder::Node* p;
   size_t stride;
   adder::Node load(uint32_t k) const { return p[(size_t)k * stride]; }
   void store(uint32_t k, const adder::Node& n) const { p[(size_t)k * stride] = n; }
+  void used_preloaded() const {}
+  void unused_load() const {}
 };
 struct VecSink {
   std::vector<adder_event_t>* out;
@@ -41,6 +47,7 @@ struct sim_video {
   std::vector<adder_event_t> events;
   float running_t;
   uint32_t err;
+  int force_display;
 };
 
 extern "C" {
@@ -54,6 +61,7 @@ sim_video* sim_new(uint32_t w, uint32_t h, uint32_t c, uint32_t depth) {
   v->running.assign(v->P, 0);
   v->running_t = 0.0f;
   v->err = 0;
+  v->force_display = 1;
   return v;
 }
 void sim_delete(sim_video* v) { delete v; }
@@ -81,20 +89,48 @@ size_t sim_integrate(sim_video* v, const uint8_t* frame, float time, uint32_t re
   p.collapse = collapse;
   p.abs_time = abs_time;
   p.view_mode = view_mode;
-  p.display = 1;
+  p.display = v->force_display ? 2 : 1;
+  v->force_display = 0;
   p.depth = v->depth;
   p.tpf = (double)ref;
+  p.tpf_f = (float)ref;
+  p.ref_magic = adder::ref_magic_of(ref);
   p.practical_d_max = practical_d_max;
+  uint8_t lut[257];
+  adder::build_exact_lut(ref, lut);
+  p.exact_lut = lut;
   v->events.clear();
   for (size_t i = 0; i < v->P; i++) {
     HostNodes mem{v->nodes.data() + i, v->P};
     const uint32_t ch = (uint32_t)(i % v->c), x = (uint32_t)((i / v->c) % v->w), y = (uint32_t)(i / ((size_t)v->c * v->w));
     VecSink sink{&v->events, (uint16_t)x, (uint16_t)y, (uint8_t)(v->c == 1 ? ADDER_C_NONE : ch)};
     uint8_t disp = 0;
-    if (adder::px_step(p, frame[i], v->hdr[i], mem.load(0), mem, sink, v->err, &disp)) v->running[i] = disp;
+    /* like the kernel: level 1 is fetched before the length is known */
+    const adder::Node n1 = v->depth > 1 ? mem.load(1) : mem.load(0);
+    if (adder::px_step(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)) v->running[i] = disp;
   }
   return v->events.size();
 }
+/* unit hooks for the two exact-by-construction shortcuts of px_machine.cuh */
+void sim_set_fast_div_ulps(int n) { adder::g_fast_div_ulps = n; }
+uint32_t sim_div_ref(uint32_t u, uint32_t ref) {
+  adder::PxParams p{};
+  p.ref = ref;
+  p.ref_magic = adder::ref_magic_of(ref);
+  return adder::div_ref(p, u);
+}
+uint32_t sim_frame_value_intensity(uint32_t d, uint32_t t, uint32_t ref) {
+  adder::PxParams p{};
+  p.view_mode = 0;
+  p.tpf = (double)ref;
+  p.tpf_f = (float)ref;
+  p.ref = ref;
+  uint8_t lut[257];
+  adder::build_exact_lut(ref, lut);
+  p.exact_lut = lut;
+  return adder::frame_value_u8(p, d, t, 0.0f);
+}
+void sim_force_display(sim_video* v) { v->force_display = 1; }
 const adder_event_t* sim_events(const sim_video* v) { return v->events.data(); }
 const uint8_t* sim_running(const sim_video* v) { return v->running.data(); }
 uint32_t sim_err(const sim_video* v) { return v->err; }

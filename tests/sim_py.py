@@ -34,6 +34,12 @@ def lib():
         L.sim_events.argtypes = [vp]
         L.sim_running.restype = C.POINTER(C.c_uint8)
         L.sim_running.argtypes = [vp]
+        L.sim_force_display.argtypes = [vp]
+        L.sim_set_fast_div_ulps.argtypes = [i32]
+        L.sim_div_ref.restype = u32
+        L.sim_div_ref.argtypes = [u32, u32]
+        L.sim_frame_value_intensity.restype = u32
+        L.sim_frame_value_intensity.argtypes = [u32, u32, u32]
         L.sim_err.restype = u32
         L.sim_err.argtypes = [vp]
         L.sim_px.argtypes = [vp, sz, C.POINTER(f32), C.POINTER(u32)]
@@ -55,6 +61,10 @@ class SimVideo:
             self.L.sim_delete(self.v)
         except Exception:
             pass
+
+    def force_display(self):
+        """What the C ABI does after any setter that changes ref / dtm / view mode."""
+        self.L.sim_force_display(self.v)
 
     def reset_c(self, c, reset_counter=True):
         self.L.sim_reset_c(self.v, c, int(reset_counter))

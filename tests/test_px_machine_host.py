@@ -25,6 +25,7 @@ class _SimAdapter:
         if dtm < ref:
             return False
         self.s.ref, self.s.dtm = ref, dtm
+        self.s.force_display()
         return True
 
     def write_out(self, time_mode, multi_mode):
@@ -40,10 +41,12 @@ class _SimAdapter:
     def update_quality_manual(self, c_base, c_max, dtm_mult, velocity, radius):
         self.s.c_max, self.s.vel = c_max, velocity
         self.s.dtm = dtm_mult * self.s.ref
+        self.s.force_display()
         self.s.reset_c(c_base)
 
     def set_view_mode(self, m):
         self.s.view = m
+        self.s.force_display()
 
     def set_in_interval_count(self, n):
         self.in_interval = n

@@ -5,6 +5,8 @@ set -u
 TAG=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt
+echo "== smoke"; timeout -k 10 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 || { echo "smoke failed or hung: stopping"; exit 1; }
+[ "${PIPESTATUS[0]}" = "0" ] || { echo "smoke failed or hung: stopping"; exit 1; }
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 echo "== bench"; timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 echo "== profile_run (plain)"; timeout 300 python tools/profile_run.py --reps 3 2>&1 | tail -4

@@ -19,23 +19,47 @@ ap.add_argument("--crf", type=int, default=3)
 ap.add_argument("--ref", type=int, default=255)
 ap.add_argument("--dtm", type=int, default=7650)
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--manual", type=int, default=-1, help="quality_manual(c, c, dtm/ref, 1) instead of crf (BASELINE cfg 3 sweep)")
+ap.add_argument("--normal", action="store_true", help="PixelMultiMode::Normal")
+ap.add_argument("--count", action="store_true", help="one extra untimed pass with the counting twin: algorithmic bytes + roofline fraction")
 a = ap.parse_args()
 
 P = a.w * a.h * a.c
 v = A.Video(a.w, a.h, a.c)
 assert v.time_parameters(a.ref * 30, a.ref, a.dtm, None)
-v.update_crf(a.crf)
+def quality():
+    if a.manual >= 0:
+        v.update_quality_manual(a.manual, a.manual, a.dtm // a.ref, 1, 0.0)
+    else:
+        v.update_crf(a.crf)
+
+
+quality()
+if a.normal:
+    v.write_out(None, A.MULTI_NORMAL)
 d_frames = v.device_alloc(P * a.frames)
 v.synth_frames(d_frames, 0, a.frames, a.kind, 0xADDE5)
-stride = P * 2
+stride = P * 4
 d_events = v.device_alloc(stride * 12 * 4)
 v.sync()
+alg = None
+if a.count:
+    v.set_counting(True)
+    for f in range(a.frames):
+        v.integrate_frames_device(d_frames.ptr + f * P, P, 1, float(a.ref), d_events.ptr + (f % 4) * stride * 12, stride, None)
+    v.sync()
+    c = v.read_counters()
+    v.set_counting(False)
+    alg = (1 + 8 + 8) * P * a.frames + 16 * (c["node_loads"] + c["node_stores"]) + c["display_writes"] + 12 * c["events"]
+    print(f"counted: {alg / (P * a.frames):.2f} B/px-frame, loads {c['node_loads'] / (P * a.frames):.3f} stores {c['node_stores'] / (P * a.frames):.3f} "
+          f"display {c['display_writes'] / (P * a.frames):.3f} events {c['events'] / (P * a.frames):.3f} per px-frame")
 for rep in range(a.reps):
     v.reset_state()
-    v.update_crf(a.crf)
+    quality()
     v.timer_start()
     for f in range(a.frames):
         v.integrate_frames_device(d_frames.ptr + f * P, P, 1, float(a.ref), d_events.ptr + (f % 4) * stride * 12, stride, None)
     ms = v.timer_stop()
     v.sync()
-    print(f"rep {rep}: {a.frames} frames {ms:.3f} ms  -> {ms / a.frames * 1e3:.1f} us/frame, {P * a.frames / ms / 1e3:.1f} Mpx/s, events {v.events_emitted()}")
+    extra = f", {alg / ms / 1e6:.0f} GB/s = {alg / ms / 1e6 / 6540.2:.3f} of 6540" if alg else ""
+    print(f"rep {rep}: {a.frames} frames {ms:.3f} ms  -> {ms / a.frames * 1e3:.1f} us/frame, {P * a.frames / ms / 1e3:.1f} Mpx/s, events {v.events_emitted()}{extra}")
