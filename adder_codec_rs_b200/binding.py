@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libadder_b200.so")
+_SO = os.environ.get("ADDER_B200_SO") or os.path.join(_HERE, "libadder_b200.so")  # override: A/B builds of the kernel
 _CSRC = os.path.join(_HERE, "csrc")
 
 # adder_event_t (12 bytes, little-endian)
@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", ".h")) or f == "Makefile"]
     deps.append(os.path.join(os.path.dirname(_HERE), "include", "adder_b200.h"))
     stale = not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps)
-    if force or stale:
+    if (force or stale) and not os.environ.get("ADDER_B200_SO"):
         r = subprocess.run(["make", "-C", _CSRC] + (["-B"] if force else []), capture_output=True, text=True)
         if verbose or r.returncode:
             print(r.stdout, r.stderr)

@@ -154,7 +154,13 @@ constexpr uint32_t kWarps = kThreads / 32;
  * Warps 0 and 1 carry the CTA's serial work (scan + publish, look-back) and would otherwise finish
  * every iteration last, with the other six waiting for them (profiles/r01d).
  */
-__host__ __device__ constexpr uint32_t tile_rows(uint32_t R) { return 8u * R - 2u; }
+#ifndef ADDER_DUTY_LESS
+#define ADDER_DUTY_LESS 1u /* rows fewer for warps 0/1 in the last round (experiments: 0) */
+#endif
+#ifndef ADDER_MIN_CTAS
+#define ADDER_MIN_CTAS 4
+#endif
+__host__ __device__ constexpr uint32_t tile_rows(uint32_t R) { return 8u * R - 2u * ADDER_DUTY_LESS; }
 __host__ __device__ constexpr uint32_t tile_px(uint32_t R) { return 32u * tile_rows(R); }
 /* shared-memory slots per pixel: 1 for the large tile (a pixel's second event goes to the global spill
  * array) so that four CTAs with three park buffers each still fit an SM, else 3 */
@@ -254,7 +260,7 @@ __device__ __forceinline__ uint32_t look_back(const FrameArgs& a, uint32_t tile,
  * workload: it additionally sums node loads / stores, display writes and events into a.counters.
  */
 template <int R, bool kCount>
-__global__ void __launch_bounds__(ADDER_TILE_PX, 4) integrate_frame_kernel(const FrameArgs a) {
+__global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame_kernel(const FrameArgs a) {
   constexpr uint32_t ROWS = tile_rows(R), TILE = tile_px(R);
   constexpr uint32_t S = park_slots(R);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
@@ -271,10 +277,10 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, 4) integrate_frame_kernel(const
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const bool duty = warp < 2u;
-  const uint32_t my_rows = duty ? (uint32_t)R - 1u : (uint32_t)R;
+  const uint32_t my_rows = duty ? (uint32_t)R - ADDER_DUTY_LESS : (uint32_t)R;
   const bool frame_aligned = (reinterpret_cast<uintptr_t>(a.frame) & 15u) == 0;
   /* this warp's row of round r, and the tile-relative index of this thread's pixel in it */
-  auto row_of = [&](uint32_t r) { return r + 1u < (uint32_t)R ? 8u * r + warp : 8u * ((uint32_t)R - 1u) + warp - 2u; };
+  auto row_of = [&](uint32_t r) { return r + 1u < (uint32_t)R ? 8u * r + warp : 8u * ((uint32_t)R - 1u) + warp - 2u * ADDER_DUTY_LESS; };
 
   /* tiles are handed out in ticket order so that a tile's predecessors are always held by CTAs that
    * are already running: the look-back can then never wait on a CTA that has not been scheduled. */
@@ -299,6 +305,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, 4) integrate_frame_kernel(const
     if (start + TILE <= a.P && frame_aligned) {
       if (lane < 2u * my_rows) cp_async16(dst + lane * 16u, a.frame + start + 32u * row_of(lane >> 1) + (lane & 1u) * 16u);
     } else {
+#pragma unroll 1
       for (uint32_t r = 0; r < my_rows; r++) {
         const uint32_t i = start + 32u * row_of(r) + lane;
         if (i < a.P) dst[r * 32u + lane] = a.frame[i];
@@ -485,10 +492,11 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, 4) integrate_frame_kernel(const
           const uint32_t cb = ch * a.chunk_px;                                              /* its first pixel */
           if (cb >= pstart) {
             const uint32_t qq = cb - pstart, row = qq >> 5;
-            const uint32_t owner = row < 8u * ((uint32_t)R - 1u) ? (row & 7u) : row - 8u * ((uint32_t)R - 1u) + 2u;
+            const uint32_t owner = row < 8u * ((uint32_t)R - 1u) ? (row & 7u) : row - 8u * ((uint32_t)R - 1u) + 2u * ADDER_DUTY_LESS;
             if (owner * 32u + (qq & 31u) == tid) a.chunk_off[ch] = prefix + s_wtot[pb][row] + (pinfo[qq] & 1023u);
           }
         } else {
+#pragma unroll 1
           for (uint32_t r = 0; r < my_rows; r++) {
             const uint32_t row = row_of(r), q = 32u * row + lane, i = pstart + q;
             if (i < a.P && i % a.chunk_px == 0u) a.chunk_off[i / a.chunk_px] = prefix + s_wtot[pb][row] + (pinfo[q] & 1023u);
@@ -513,6 +521,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, 4) integrate_frame_kernel(const
           }
           const uint32_t w0 = x | ((y + a.row0) << 16);
           EventPark<S> park{const_cast<uint32_t*>(pslot_t) + q, const_cast<uint8_t*>(pslot_d) + q, a.nodes + i, a.spill1 + i, a.level_stride, TILE, a.px.depth, nev, 0u};
+#pragma unroll 1
           for (uint32_t e = 0; e < nev; e++) {
             uint32_t dd, tt;
             park.get(e, dd, tt);
