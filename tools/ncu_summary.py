@@ -17,6 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
+is_bench_workload = "--other" not in sys.argv  # pass --other for captures of workloads that are not bench.py's
 G, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(PR, exist_ok=True)
 
@@ -81,10 +82,11 @@ if os.path.exists(rep):
         for r in rows[2:]:
             traffic.append(num(r[iR]) * scale[units[iR]] + num(r[iW]) * scale[units[iW]])
         iT = hdr.index("gpu__time_duration.sum")
-    json.dump({"tag": tag, "kernel": rows[2][iN], "dram_bytes_per_launch": sum(traffic) / len(traffic),
-               "launches_captured": len(traffic), "duration_under_ncu": [r[iT] + " " + units[iT] for r in rows[2:]],
-               "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches"},
-              open(os.path.join(PR, "roofline_traffic.json"), "w"), indent=1)
+    if is_bench_workload:
+      json.dump({"tag": tag, "kernel": rows[2][iN], "dram_bytes_per_launch": sum(traffic) / len(traffic),
+                 "launches_captured": len(traffic), "duration_under_ncu": [r[iT] + " " + units[iT] for r in rows[2:]],
+                 "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches"},
+                open(os.path.join(PR, "roofline_traffic.json"), "w"), indent=1)
     cs = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-id", ":::1"],
                         capture_output=True, text=True).stdout
     tmp = os.path.join("/tmp", f"{tag}_cs.csv")
