@@ -26,5 +26,6 @@ from .binding import (  # noqa: F401
     device_count,
     lib,
     pinned_empty,
+    raw_eof,
 )
 from .framed import Framed  # noqa: F401

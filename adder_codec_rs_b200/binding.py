@@ -38,6 +38,9 @@ SYMBOLS = [
     "adder_b200_host_alloc", "adder_b200_host_free", "adder_b200_device_alloc", "adder_b200_device_free",
     "adder_b200_copy_to_device", "adder_b200_copy_to_host", "adder_b200_video_timer_start",
     "adder_b200_video_timer_stop", "adder_b200_synth_frames",
+    "adder_b200_video_raw_header", "adder_b200_raw_eof", "adder_b200_video_raw_event_size",
+    "adder_b200_video_raw_encode_device", "adder_b200_video_integrate_frames_host_raw",
+    "adder_b200_video_set_source_channels", "adder_b200_video_input_frame",
 ]
 
 
@@ -143,6 +146,13 @@ def lib() -> C.CDLL:
         "adder_b200_video_timer_start": (i32, [vp]),
         "adder_b200_video_timer_stop": (i32, [vp, P(f32)]),
         "adder_b200_synth_frames": (i32, [vp, vp, sz, u32, u32, i32, u64]),
+        "adder_b200_video_raw_header": (i32, [vp, u8, u32, u32, vp, sz, P(sz)]),
+        "adder_b200_raw_eof": (i32, [vp, sz, P(sz)]),
+        "adder_b200_video_raw_event_size": (i32, [vp]),
+        "adder_b200_video_raw_encode_device": (i32, [vp, vp, vp, u64, vp]),
+        "adder_b200_video_integrate_frames_host_raw": (i32, [vp, vp, sz, u32, f32, vp, sz, vp, vp, P(u64), P(u32)]),
+        "adder_b200_video_set_source_channels": (i32, [vp, u8]),
+        "adder_b200_video_input_frame": (i32, [vp, vp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -161,6 +171,14 @@ def _check(rc):
 def device_count() -> int:
     n = lib().adder_b200_device_count()
     return max(n, 0)
+
+
+def raw_eof() -> bytes:
+    """RawOutput::into_writer's EOF event (raw/stream.rs:79-92)."""
+    buf = (C.c_uint8 * 16)()
+    n = C.c_size_t()
+    _check(lib().adder_b200_raw_eof(buf, 16, C.byref(n)))
+    return bytes(buf[: n.value])
 
 
 def crf_parameters(crf, w, h) -> CrfParameters:
@@ -237,6 +255,7 @@ class Video:
     def __init__(self, width, height, channels, pixel_tree_mode=MODE_FRAME_PERFECT, device=0, max_depth=0):
         self.L = lib()
         self.w, self.h, self.c = width, height, channels
+        self.src_c = channels  # channels of the frames handed in (set_source_channels)
         self.v = C.c_void_p()
         _check(self.L.adder_b200_video_create(width, height, channels, pixel_tree_mode, device, max_depth, C.byref(self.v)))
 
@@ -288,6 +307,17 @@ class Video:
 
     def set_in_interval_count(self, n):
         _check(self.L.adder_b200_video_set_in_interval_count(self.v, n))
+
+    def set_source_channels(self, n):
+        """3 on a one-channel video: frames come in as (H, W, 3) and handle_color (utils/cv.rs:215-232) runs on the device."""
+        _check(self.L.adder_b200_video_set_source_channels(self.v, n))
+        self.src_c = n if n else self.c
+
+    def input_frame(self) -> np.ndarray:
+        """The (gray) frame the last integrate call worked on (Framed.input_frame, framed.rs:129)."""
+        out = np.empty((self.h, self.w, self.c), dtype=np.uint8)
+        _check(self.L.adder_b200_video_input_frame(self.v, out.ctypes.data))
+        return out
 
     def set_row_offset(self, row0):
         _check(self.L.adder_b200_video_set_row_offset(self.v, row0))
@@ -342,7 +372,7 @@ class Video:
     def integrate_matrix(self, frame: np.ndarray, time_spanned: float, events_out: np.ndarray | None = None):
         """One frame, host buffers (Framed::consume's call, framed.rs:131).  Returns (events, chunk_counts)."""
         frame = np.ascontiguousarray(frame, dtype=np.uint8)
-        assert frame.size == self.w * self.h * self.c
+        assert frame.size == self.w * self.h * self.src_c
         counts = np.empty(self.n_chunks, dtype=np.uint32)
         n = C.c_uint64()
         if events_out is None:
@@ -359,7 +389,7 @@ class Video:
         """n frames, host buffers, copies and kernels pipelined.  Returns (events, frame_counts, chunk_counts)."""
         assert frames.dtype == np.uint8 and frames.flags.c_contiguous
         nf = frames.shape[0]
-        assert frames[0].size == self.w * self.h * self.c
+        assert frames[0].size == self.w * self.h * self.src_c
         fc = np.zeros(nf, dtype=np.uint64)
         cc = np.zeros((nf, self.n_chunks), dtype=np.uint32)
         n, done = C.c_uint64(), C.c_uint32()
@@ -368,6 +398,35 @@ class Video:
                                                            cc.ctypes.data, C.byref(n), C.byref(done))
         _check(rc)
         return events_out[: n.value], fc, cc
+
+    # ---- raw .adder output ----
+    def raw_header(self, version=3, source_camera=0, adu_interval=0) -> bytes:
+        """EventStreamHeader + extensions for this plane and its time parameters (codec/header.rs, encoder.rs:170-229)."""
+        buf = (C.c_uint8 * 64)()
+        n = C.c_size_t()
+        _check(self.L.adder_b200_video_raw_header(self.v, version, source_camera, adu_interval, buf, 64, C.byref(n)))
+        return bytes(buf[: n.value])
+
+    @property
+    def raw_event_size(self) -> int:
+        return self.L.adder_b200_video_raw_event_size(self.v)
+
+    def raw_encode_device(self, d_events, d_n_events, n_events_max, d_out):
+        """Records in HBM -> wire bytes in HBM (RawOutput::ingest_event, raw/stream.rs:100-120), on the handle's stream."""
+        _check(self.L.adder_b200_video_raw_encode_device(self.v, d_events, d_n_events, n_events_max, d_out))
+
+    def integrate_frames_host_raw(self, frames: np.ndarray, time_spanned: float, bytes_out: np.ndarray):
+        """integrate_frames_host delivering the raw stream body.  Returns (bytes, frame_counts, chunk_counts)."""
+        assert frames.dtype == np.uint8 and frames.flags.c_contiguous and bytes_out.dtype == np.uint8
+        nf = frames.shape[0]
+        assert frames[0].size == self.w * self.h * self.src_c
+        fc = np.zeros(nf, dtype=np.uint64)
+        cc = np.zeros((nf, self.n_chunks), dtype=np.uint32)
+        n, done = C.c_uint64(), C.c_uint32()
+        _check(self.L.adder_b200_video_integrate_frames_host_raw(self.v, frames.ctypes.data, frames[0].size, nf, time_spanned,
+                                                                 bytes_out.ctypes.data, bytes_out.size, fc.ctypes.data,
+                                                                 cc.ctypes.data, C.byref(n), C.byref(done)))
+        return bytes_out[: n.value], fc, cc
 
     def running_intensities(self) -> np.ndarray:
         out = np.empty((self.h, self.w, self.c), dtype=np.uint8)

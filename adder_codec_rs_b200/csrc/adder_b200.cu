@@ -18,6 +18,7 @@
 
 #include "../../include/adder_b200.h"
 #include "px_kernel.cuh"
+#include "raw_kernel.cuh"
 #include "synth.cuh"
 
 namespace {
@@ -118,7 +119,12 @@ struct adder_b200_video {
 
   /* host-form resources (allocated on first use) */
   uint8_t* d_frame[kRing] = {nullptr, nullptr, nullptr};
+  uint8_t src_c = 0;                                   /* channels of the frames handed in; 0 = the video's own */
+  uint8_t* d_rgb[kRing] = {nullptr, nullptr, nullptr}; /* three-channel staging of the host forms (gray transcode of a colour source) */
+  uint8_t* d_gray = nullptr;                           /* the same for the device-resident form */
+  const uint8_t* d_last_input = nullptr;               /* the (gray) frame the last integrate call worked on */
   adder_event_t* d_events[kRing] = {nullptr, nullptr, nullptr};
+  uint8_t* d_raw[kRing] = {nullptr, nullptr, nullptr}; /* wire-format copies of d_events (raw host form only) */
   uint32_t* d_chunk_off[kRing] = {nullptr, nullptr, nullptr};
   uint32_t* h_chunk_off[kRing] = {nullptr, nullptr, nullptr}; /* pinned */
   uint64_t events_capacity = 0;                               /* records per slot */
@@ -174,6 +180,10 @@ int ensure_depth(adder_b200_video* v, uint32_t need) {
       CU(cudaStreamSynchronize(v->stream_out));
       CU(cudaFree(v->d_events[s]));
       v->d_events[s] = nullptr;
+    }
+    if (v->d_raw[s]) {
+      CU(cudaFree(v->d_raw[s]));
+      v->d_raw[s] = nullptr;
     }
   }
   v->events_capacity = 0;
@@ -338,8 +348,21 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   p.exact_lut = v->d_exact_lut;
   p.practical_d_max = log2_raw(255.0f * (float)(v->delta_t_max / v->ref_time)); /* :668-670 */
 
+  v->d_last_input = d_frame;
   launch_variant(v, a, stream);
   v->ticket_base += v->n_tiles_r + v->grid; /* every CTA draws one ticket past the end */
+  v->launches++;
+  CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
+bool rgb_in(const adder_b200_video* v) { return v->src_c == 3 && v->c == 1; }
+size_t in_frame_bytes(const adder_b200_video* v) { return rgb_in(v) ? (size_t)v->P * 3u : (size_t)v->P; }
+
+/* handle_color on the device (utils/cv.rs:215-232): d_rgb (P*3 bytes) -> d_gray (P bytes) */
+int launch_gray(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_rgb, uint8_t* d_gray) {
+  const uint32_t groups = (v->P + 3u) / 4u;
+  adder::rgb_to_gray_kernel<<<(groups + 255u) / 256u, 256, 0, stream>>>(d_rgb, d_gray, v->P);
   v->launches++;
   CU(cudaGetLastError());
   return ADDER_OK;
@@ -491,11 +514,14 @@ void adder_b200_video_destroy(adder_b200_video* v) {
   cudaFree(v->d_total);
   cudaFree(v->d_counters);
   cudaFree(v->d_exact_lut);
+  cudaFree(v->d_gray);
   if (v->h_err) cudaFreeHost(v->h_err);
   if (v->h_total) cudaFreeHost(v->h_total);
   for (int s = 0; s < kRing; s++) {
     cudaFree(v->d_frame[s]);
     cudaFree(v->d_events[s]);
+    cudaFree(v->d_rgb[s]);
+    cudaFree(v->d_raw[s]);
     cudaFree(v->d_chunk_off[s]);
     if (v->h_chunk_off[s]) cudaFreeHost(v->h_chunk_off[s]);
     if (v->ev_in[s]) cudaEventDestroy(v->ev_in[s]);
@@ -619,6 +645,23 @@ int adder_b200_video_set_in_interval_count(adder_b200_video* v, uint32_t n) {
   return ADDER_OK;
 }
 
+int adder_b200_video_set_source_channels(adder_b200_video* v, uint8_t source_channels) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (source_channels != 0 && source_channels != v->c && !(source_channels == 3 && v->c == 1))
+    return fail(ADDER_ERR_BAD_PARAMS, "source_channels must be the video's own channel count, or 3 for a one-channel video");
+  v->src_c = source_channels == v->c ? 0 : source_channels;
+  return ADDER_OK;
+}
+
+int adder_b200_video_input_frame(adder_b200_video* v, uint8_t* out) {
+  if (!v || !out) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (!v->d_last_input) return fail(ADDER_ERR_BAD_PARAMS, "no frame has been integrated yet");
+  if (int rc = set_device(v)) return rc;
+  CU(cudaMemcpyAsync(out, v->d_last_input, v->P, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  return ADDER_OK;
+}
+
 int adder_b200_video_set_row_offset(adder_b200_video* v, uint16_t row0) {
   if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
   if ((uint32_t)row0 + v->h > 65536u) return fail(ADDER_ERR_BAD_PARAMS, "row offset + height exceeds the u16 coordinate range");
@@ -694,11 +737,17 @@ int adder_b200_video_integrate_matrix(adder_b200_video* v, const uint8_t* frame,
     if (int rc = set_device(v)) return rc;
     if (int rc = ensure_depth(v, derive_depth(v))) return rc;
     if (int rc = ensure_host_form(v)) return rc;
-    const size_t row = (size_t)v->w * v->c;
+    const size_t row = (size_t)v->w * (rgb_in(v) ? 3u : v->c);
     if (row_pitch == 0) row_pitch = row;
     if (row_pitch < row) return fail(ADDER_ERR_BAD_PARAMS, "row_pitch smaller than a row");
     const int s = 0;
-    CU(cudaMemcpy2DAsync(v->d_frame[s], row, frame, row_pitch, row, v->h, cudaMemcpyHostToDevice, v->stream));
+    if (rgb_in(v)) { /* framed.rs:129: handle_color, here on the device */
+      if (!v->d_rgb[s]) CU(cudaMalloc(&v->d_rgb[s], (size_t)v->P * 3u));
+      CU(cudaMemcpy2DAsync(v->d_rgb[s], row, frame, row_pitch, row, v->h, cudaMemcpyHostToDevice, v->stream));
+      if (int rc = launch_gray(v, v->stream, v->d_rgb[s], v->d_frame[s])) return rc;
+    } else {
+      CU(cudaMemcpy2DAsync(v->d_frame[s], row, frame, row_pitch, row, v->h, cudaMemcpyHostToDevice, v->stream));
+    }
     if (int rc = launch_frame(v, v->stream, v->d_frame[s], time_spanned, v->d_events[s], v->events_capacity, v->d_chunk_off[s]))
       return rc;
     v->last_slot = s;
@@ -728,80 +777,192 @@ int adder_b200_video_fetch_events(adder_b200_video* v, adder_event_t* events_out
   return ADDER_OK;
 }
 
-int adder_b200_video_integrate_frames_host(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
-                                           uint32_t n_frames, float time_spanned, adder_event_t* events_out,
-                                           size_t events_cap, uint64_t* frame_counts, uint32_t* chunk_counts,
-                                           uint64_t* n_events, uint32_t* frames_done) {
-  return guarded([&]() -> int {
-    if (!v || (!frames && n_frames)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
-    if (int rc = set_device(v)) return rc;
-    if (int rc = ensure_depth(v, derive_depth(v))) return rc;
-    if (int rc = ensure_host_form(v)) return rc;
-    if (frame_stride == 0) frame_stride = v->P;
-    if (frame_stride < v->P) return fail(ADDER_ERR_BAD_PARAMS, "frame_stride smaller than a frame");
-    if (n_events) *n_events = 0;
-    if (frames_done) *frames_done = 0;
-    CU(cudaStreamSynchronize(v->stream)); /* setters queued on the main stream come first */
+namespace {
 
-    uint64_t written = 0;
-    uint32_t submitted = 0, delivered = 0;
-    int rc_final = ADDER_OK;
-    /* Frame f uses ring slot f % kRing.  Its kernel waits for its H2D copy (ev_in) and for the D2H
-     * copy that last used the slot (ev_out); its D2H copy is issued once the host knows the count. */
-    auto deliver = [&](uint32_t f) -> int {
-      const int s = f % kRing;
-      CU(cudaEventSynchronize(v->ev_k[s]));
-      const uint32_t* off = v->h_chunk_off[s];
-      const uint64_t total = off[v->n_chunks];
-      if (written + total > events_cap)
-        return fail(ADDER_ERR_CAPACITY, "events_out holds %zu records; frame %u needs %llu more than fit", events_cap, f,
-                    (unsigned long long)(written + total - events_cap));
-      if (total)
-        CU(cudaMemcpyAsync(events_out + written, v->d_events[s], total * sizeof(adder_event_t), cudaMemcpyDeviceToHost,
-                           v->stream_out));
-      CU(cudaEventRecord(v->ev_out[s], v->stream_out));
-      if (frame_counts) frame_counts[f] = total;
-      if (chunk_counts) offsets_to_counts(off, v->n_chunks, chunk_counts + (size_t)f * v->n_chunks);
-      written += total;
-      return ADDER_OK;
-    };
+uint32_t raw_event_size(const adder_b200_video* v) { return v->c == 1 ? 9u : 11u; } /* codec/header.rs:77-81 */
 
-    for (uint32_t f = 0; f < n_frames; f++) {
-      const int s = f % kRing;
-      if (f >= (uint32_t)kRing) { /* the slot's previous tenant must be delivered before it is reused */
-        if (int rc = deliver(f - kRing)) {
-          rc_final = rc;
-          break;
-        }
-        delivered++;
-      }
-      CU(cudaStreamWaitEvent(v->stream_in, v->ev_k[s], 0)); /* previous kernel on this slot has read its frame */
-      CU(cudaMemcpyAsync(v->d_frame[s], frames + (size_t)f * frame_stride, v->P, cudaMemcpyHostToDevice, v->stream_in));
-      CU(cudaEventRecord(v->ev_in[s], v->stream_in));
-      CU(cudaStreamWaitEvent(v->stream, v->ev_in[s], 0));
-      CU(cudaStreamWaitEvent(v->stream, v->ev_out[s], 0));
-      if (int rc = launch_frame(v, v->stream, v->d_frame[s], time_spanned, v->d_events[s], v->events_capacity, v->d_chunk_off[s]))
-        return rc;
-      CU(cudaMemcpyAsync(v->h_chunk_off[s], v->d_chunk_off[s], ((size_t)v->n_chunks + 1) * sizeof(uint32_t),
-                         cudaMemcpyDeviceToHost, v->stream));
-      CU(cudaEventRecord(v->ev_k[s], v->stream));
-      submitted++;
+int launch_raw_encode(adder_b200_video* v, cudaStream_t stream, const adder_event_t* d_events, const uint32_t* d_n, uint64_t n_max,
+                      uint8_t* d_out) {
+  if (n_max == 0) return ADDER_OK;
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v->device));
+  const uint64_t want = (n_max + adder::kRawThreads - 1) / adder::kRawThreads;
+  const uint32_t blocks = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 8u);
+  adder::raw_encode_kernel<<<blocks, adder::kRawThreads, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_events), d_n, n_max,
+                                                                      raw_event_size(v), d_out);
+  v->launches++;
+  CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
+/* n_frames consecutive calls of integrate_matrix with H2D / kernels / D2H overlapped on three streams.
+ * raw = false: 12-byte records to out; raw = true: the wire bytes of the same events. */
+int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_stride, uint32_t n_frames, float time_spanned,
+                     void* out, size_t out_cap /* records, or bytes when raw */, bool raw, uint64_t* frame_counts,
+                     uint32_t* chunk_counts, uint64_t* n_out, uint32_t* frames_done) {
+  if (!v || (!frames && n_frames)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (int rc = set_device(v)) return rc;
+  if (int rc = ensure_depth(v, derive_depth(v))) return rc;
+  if (int rc = ensure_host_form(v)) return rc;
+  const size_t unit = raw ? raw_event_size(v) : sizeof(adder_event_t);
+  if (raw)
+    for (int s = 0; s < kRing; s++)
+      if (!v->d_raw[s]) CU(cudaMalloc(&v->d_raw[s], v->events_capacity * 11u));
+  const size_t in_bytes = in_frame_bytes(v);
+  if (rgb_in(v))
+    for (int s = 0; s < kRing; s++)
+      if (!v->d_rgb[s]) CU(cudaMalloc(&v->d_rgb[s], in_bytes));
+  if (frame_stride == 0) frame_stride = in_bytes;
+  if (frame_stride < in_bytes) return fail(ADDER_ERR_BAD_PARAMS, "frame_stride smaller than a frame");
+  if (n_out) *n_out = 0;
+  if (frames_done) *frames_done = 0;
+  CU(cudaStreamSynchronize(v->stream)); /* setters queued on the main stream come first */
+
+  uint64_t written = 0; /* in units */
+  uint32_t submitted = 0, delivered = 0;
+  int rc_final = ADDER_OK;
+  /* Frame f uses ring slot f % kRing.  Its kernel waits for its H2D copy (ev_in) and for the D2H
+   * copy that last used the slot (ev_out); its D2H copy is issued once the host knows the count. */
+  auto deliver = [&](uint32_t f) -> int {
+    const int s = f % kRing;
+    CU(cudaEventSynchronize(v->ev_k[s]));
+    const uint32_t* off = v->h_chunk_off[s];
+    const uint64_t total = off[v->n_chunks];
+    const uint64_t need = raw ? total * unit : total;
+    if (written + need > out_cap)
+      return fail(ADDER_ERR_CAPACITY, "output holds %zu %s; frame %u needs %llu more than fit", out_cap, raw ? "bytes" : "records", f,
+                  (unsigned long long)(written + need - out_cap));
+    if (total) {
+      const void* src = raw ? (const void*)v->d_raw[s] : (const void*)v->d_events[s];
+      CU(cudaMemcpyAsync((uint8_t*)out + written * (raw ? 1 : unit), src, total * unit, cudaMemcpyDeviceToHost, v->stream_out));
     }
-    while (rc_final == ADDER_OK && delivered < submitted) {
-      if (int rc = deliver(delivered)) {
+    CU(cudaEventRecord(v->ev_out[s], v->stream_out));
+    if (frame_counts) frame_counts[f] = total;
+    if (chunk_counts) offsets_to_counts(off, v->n_chunks, chunk_counts + (size_t)f * v->n_chunks);
+    written += need;
+    return ADDER_OK;
+  };
+
+  for (uint32_t f = 0; f < n_frames; f++) {
+    const int s = f % kRing;
+    if (f >= (uint32_t)kRing) { /* the slot's previous tenant must be delivered before it is reused */
+      if (int rc = deliver(f - kRing)) {
         rc_final = rc;
         break;
       }
       delivered++;
     }
-    CU(cudaStreamSynchronize(v->stream_out));
-    CU(cudaStreamSynchronize(v->stream));
-    v->last_slot = -1;
-    if (n_events) *n_events = written;
-    if (frames_done) *frames_done = delivered;
-    if (int rc = collect_errors(v, v->stream)) return rc;
-    return rc_final;
+    CU(cudaStreamWaitEvent(v->stream_in, v->ev_k[s], 0)); /* previous kernel on this slot has read its frame */
+    CU(cudaMemcpyAsync(rgb_in(v) ? v->d_rgb[s] : v->d_frame[s], frames + (size_t)f * frame_stride, in_bytes, cudaMemcpyHostToDevice,
+                       v->stream_in));
+    CU(cudaEventRecord(v->ev_in[s], v->stream_in));
+    CU(cudaStreamWaitEvent(v->stream, v->ev_in[s], 0));
+    CU(cudaStreamWaitEvent(v->stream, v->ev_out[s], 0));
+    if (rgb_in(v))
+      if (int rc = launch_gray(v, v->stream, v->d_rgb[s], v->d_frame[s])) return rc;
+    if (int rc = launch_frame(v, v->stream, v->d_frame[s], time_spanned, v->d_events[s], v->events_capacity, v->d_chunk_off[s]))
+      return rc;
+    if (raw)
+      if (int rc = launch_raw_encode(v, v->stream, v->d_events[s], v->d_chunk_off[s] + v->n_chunks, v->events_capacity, v->d_raw[s]))
+        return rc;
+    CU(cudaMemcpyAsync(v->h_chunk_off[s], v->d_chunk_off[s], ((size_t)v->n_chunks + 1) * sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost, v->stream));
+    CU(cudaEventRecord(v->ev_k[s], v->stream));
+    submitted++;
+  }
+  while (rc_final == ADDER_OK && delivered < submitted) {
+    if (int rc = deliver(delivered)) {
+      rc_final = rc;
+      break;
+    }
+    delivered++;
+  }
+  CU(cudaStreamSynchronize(v->stream_out));
+  CU(cudaStreamSynchronize(v->stream));
+  v->last_slot = -1;
+  if (n_out) *n_out = written;
+  if (frames_done) *frames_done = delivered;
+  if (int rc = collect_errors(v, v->stream)) return rc;
+  return rc_final;
+}
+
+}  // namespace
+
+int adder_b200_video_integrate_frames_host(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
+                                           uint32_t n_frames, float time_spanned, adder_event_t* events_out,
+                                           size_t events_cap, uint64_t* frame_counts, uint32_t* chunk_counts,
+                                           uint64_t* n_events, uint32_t* frames_done) {
+  return guarded([&]() -> int {
+    return frames_host_impl(v, frames, frame_stride, n_frames, time_spanned, events_out, events_cap, false, frame_counts,
+                            chunk_counts, n_events, frames_done);
   });
+}
+
+int adder_b200_video_integrate_frames_host_raw(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
+                                               uint32_t n_frames, float time_spanned, uint8_t* bytes_out, size_t bytes_cap,
+                                               uint64_t* frame_counts, uint32_t* chunk_counts, uint64_t* n_bytes,
+                                               uint32_t* frames_done) {
+  return guarded([&]() -> int {
+    return frames_host_impl(v, frames, frame_stride, n_frames, time_spanned, bytes_out, bytes_cap, true, frame_counts,
+                            chunk_counts, n_bytes, frames_done);
+  });
+}
+
+int adder_b200_video_raw_event_size(const adder_b200_video* v) { return v ? (int)raw_event_size(v) : -ADDER_ERR_BAD_PARAMS; }
+
+int adder_b200_video_raw_encode_device(adder_b200_video* v, const adder_event_t* d_events, const uint32_t* d_n_events,
+                                       uint64_t n_events_max, uint8_t* d_out) {
+  if (!v || !d_n_events || (n_events_max && (!d_events || !d_out))) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if ((reinterpret_cast<uintptr_t>(d_out) & 3u) != 0) return fail(ADDER_ERR_BAD_PARAMS, "d_out must be 4-byte aligned");
+  if (int rc = set_device(v)) return rc;
+  return launch_raw_encode(v, v->stream, d_events, d_n_events, n_events_max, d_out);
+}
+
+static uint8_t* put_be16(uint8_t* p, uint16_t x) {
+  p[0] = (uint8_t)(x >> 8);
+  p[1] = (uint8_t)x;
+  return p + 2;
+}
+static uint8_t* put_be32(uint8_t* p, uint32_t x) {
+  p[0] = (uint8_t)(x >> 24);
+  p[1] = (uint8_t)(x >> 16);
+  p[2] = (uint8_t)(x >> 8);
+  p[3] = (uint8_t)x;
+  return p + 4;
+}
+
+int adder_b200_video_raw_header(const adder_b200_video* v, uint8_t version, uint32_t source_camera, uint32_t adu_interval,
+                                uint8_t* out, size_t cap, size_t* n_bytes) {
+  if (!v || !out || !n_bytes) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (version > 3) return fail(ADDER_ERR_BAD_PARAMS, "codec version must be 0..=3 (CodecError::BadFile, encoder.rs:228)");
+  const size_t need = 25u + 4u * version;
+  if (cap < need) return fail(ADDER_ERR_CAPACITY, "header needs %zu bytes", need);
+  uint8_t* p = out;
+  memcpy(p, "adder", 5); /* MAGIC_RAW, header.rs:5 */
+  p += 5;
+  *p++ = version;
+  *p++ = 'b';
+  p = put_be16(p, v->w);
+  p = put_be16(p, v->h);
+  p = put_be32(p, v->tps);
+  p = put_be32(p, v->ref_time);
+  p = put_be32(p, v->delta_t_max);
+  *p++ = (uint8_t)raw_event_size(v);
+  *p++ = v->c;
+  if (version >= 1) p = put_be32(p, source_camera);
+  if (version >= 2) p = put_be32(p, (uint32_t)v->time_mode);
+  if (version >= 3) p = put_be32(p, adu_interval);
+  *n_bytes = (size_t)(p - out);
+  return ADDER_OK;
+}
+
+int adder_b200_raw_eof(uint8_t* out, size_t cap, size_t* n_bytes) {
+  if (!out || !n_bytes) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (cap < ADDER_RAW_EOF_BYTES) return fail(ADDER_ERR_CAPACITY, "the EOF event needs 11 bytes");
+  static const uint8_t eof[11] = {0xFF, 0xFF, 0xFF, 0xFF, 1, 0, 0, 0, 0, 0, 0}; /* x = y = 0xFFFF, c = Some(0), d = 0, t = 0 */
+  memcpy(out, eof, 11);
+  *n_bytes = 11;
+  return ADDER_OK;
 }
 
 int adder_b200_video_running_intensities(adder_b200_video* v, uint8_t* out) {
@@ -818,10 +979,16 @@ int adder_b200_video_integrate_frames_device(adder_b200_video* v, const uint8_t*
   return guarded([&]() -> int {
     if (!v || (!d_frames && n_frames) || (!d_events && events_stride)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
     if (int rc = set_device(v)) return rc;
-    if (frame_stride == 0) frame_stride = v->P;
+    if (frame_stride == 0) frame_stride = in_frame_bytes(v);
+    if (rgb_in(v) && !v->d_gray) CU(cudaMalloc(&v->d_gray, v->P));
     for (uint32_t f = 0; f < n_frames; f++) {
       uint32_t* off = d_chunk_offsets ? d_chunk_offsets + (size_t)f * (v->n_chunks + 1) : nullptr;
-      if (int rc = launch_frame(v, v->stream, d_frames + (size_t)f * frame_stride, time_spanned,
+      const uint8_t* d_in = d_frames + (size_t)f * frame_stride;
+      if (rgb_in(v)) { /* one scratch frame: the conversions and the integrate kernels alternate on the stream */
+        if (int rc = launch_gray(v, v->stream, d_in, v->d_gray)) return rc;
+        d_in = v->d_gray;
+      }
+      if (int rc = launch_frame(v, v->stream, d_in, time_spanned,
                                 d_events + (size_t)f * events_stride, events_stride, off))
         return rc;
     }

@@ -1,0 +1,87 @@
+/*
+ * raw_kernel.cuh — event records -> raw .adder wire records on the device.
+ *
+ * What the reference does serially after the parallel section, one event at a time:
+ *   Video::integrate_matrix   adder-codec-rs/src/transcoder/source/video.rs:736-740   (encoder.ingest_event per event)
+ *   RawOutput::ingest_event   adder-codec-core/src/codec/raw/stream.rs:100-120        (bincode fixint big-endian)
+ * A single-channel plane writes EventSingle {x:u16, y:u16, d:u8, t:u32} = 9 bytes, any other plane
+ * Event {x, y, c: Some(u8) -> tag 1 + value, d, t} = 11 bytes (codec/header.rs:77-81).
+ *
+ * One thread serialises one record into shared memory; the CTA then stores its 256 records
+ * (2304 or 2816 bytes, a whole number of 32-bit words) with coalesced word stores.  The event count
+ * is read from device memory (the integrate kernel's last chunk offset), so the launch needs no
+ * host round trip.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace adder {
+
+constexpr uint32_t kRawThreads = 256;
+
+__global__ void __launch_bounds__(kRawThreads) raw_encode_kernel(const uint32_t* __restrict__ ev_words, const uint32_t* __restrict__ n_events_ptr,
+                                                                 unsigned long long n_events_max, uint32_t esize /* 9 or 11 */,
+                                                                 uint8_t* __restrict__ out) {
+  __shared__ __align__(16) uint8_t s_bytes[kRawThreads * 11];
+  const unsigned long long n = min((unsigned long long)*n_events_ptr, n_events_max);
+  for (unsigned long long base = (unsigned long long)blockIdx.x * kRawThreads; base < n; base += (unsigned long long)gridDim.x * kRawThreads) {
+    const unsigned long long i = base + threadIdx.x;
+    if (i < n) {
+      const uint32_t w0 = ev_words[i * 3ull], w1 = ev_words[i * 3ull + 1ull], t = ev_words[i * 3ull + 2ull];
+      const uint32_t x = w0 & 0xFFFFu, y = w0 >> 16, c = w1 & 0xFFu, d = (w1 >> 8) & 0xFFu;
+      uint8_t* p = s_bytes + threadIdx.x * esize;
+      p[0] = (uint8_t)(x >> 8);
+      p[1] = (uint8_t)x;
+      p[2] = (uint8_t)(y >> 8);
+      p[3] = (uint8_t)y;
+      if (esize == 11u) {
+        p[4] = 1; /* Option tag: Some */
+        p[5] = (uint8_t)c;
+        p += 2;
+      }
+      p[4] = (uint8_t)d;
+      p[5] = (uint8_t)(t >> 24);
+      p[6] = (uint8_t)(t >> 16);
+      p[7] = (uint8_t)(t >> 8);
+      p[8] = (uint8_t)t;
+    }
+    __syncthreads();
+    const uint32_t cnt = (uint32_t)min((unsigned long long)kRawThreads, n - base);
+    const uint32_t nbytes = cnt * esize;
+    uint8_t* dst = out + base * esize; /* base is a multiple of 256, so dst is word aligned when out is */
+    const uint32_t nwords = nbytes >> 2;
+    for (uint32_t j = threadIdx.x; j < nwords; j += kRawThreads) reinterpret_cast<uint32_t*>(dst)[j] = reinterpret_cast<const uint32_t*>(s_bytes)[j];
+    for (uint32_t j = (nwords << 2) + threadIdx.x; j < nbytes; j += kRawThreads) dst[j] = s_bytes[j];
+    __syncthreads();
+  }
+}
+
+/*
+ * handle_color (adder-codec-rs/src/utils/cv.rs:215-232), the pre-step of Framed::consume for a gray
+ * transcode of a colour source (framed.rs:129): gray = (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in
+ * f64, left to right, every product and sum rounded on its own (no FMA), truncating and saturating.
+ * Four pixels per thread: three 32-bit loads in, one 32-bit store out.
+ */
+__device__ __forceinline__ uint32_t gray_of(uint32_t c0, uint32_t c1, uint32_t c2) {
+  const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)c0, 0.114), __dmul_rn((double)c1, 0.587)), __dmul_rn((double)c2, 0.299));
+  const uint32_t u = __double2uint_rz(s);
+  return u > 255u ? 255u : u;
+}
+__global__ void __launch_bounds__(256) rgb_to_gray_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray, uint32_t n_px) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; /* group of four pixels */
+  const uint32_t i = q * 4u;
+  if (i + 4u <= n_px && ((reinterpret_cast<uintptr_t>(rgb) | reinterpret_cast<uintptr_t>(gray)) & 3u) == 0) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(rgb) + q * 3u;
+    const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2); /* bytes r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3 */
+    const uint32_t g0 = gray_of(a & 0xFFu, (a >> 8) & 0xFFu, (a >> 16) & 0xFFu);
+    const uint32_t g1 = gray_of(a >> 24, b & 0xFFu, (b >> 8) & 0xFFu);
+    const uint32_t g2 = gray_of((b >> 16) & 0xFFu, b >> 24, c & 0xFFu);
+    const uint32_t g3 = gray_of((c >> 8) & 0xFFu, (c >> 16) & 0xFFu, c >> 24);
+    reinterpret_cast<uint32_t*>(gray)[q] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+  } else {
+    for (uint32_t j = i; j < n_px && j < i + 4u; j++) gray[j] = (uint8_t)gray_of(rgb[3u * j], rgb[3u * j + 1u], rgb[3u * j + 2u]);
+  }
+}
+
+}  // namespace adder

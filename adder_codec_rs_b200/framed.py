@@ -33,7 +33,9 @@ class NoData(SourceError):
 
 
 def handle_color(frame: np.ndarray, color: bool) -> np.ndarray:
-    """utils/cv.rs:215-232: gray = (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in f64, truncating."""
+    """utils/cv.rs:215-232: gray = (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in f64, truncating.
+    Host-side statement of the formula for callers that want the gray frame without a Video; `Framed`
+    itself runs the conversion on the device (adder_b200_video_set_source_channels)."""
     if color:
         return frame
     f = frame.astype(np.float64)
@@ -51,7 +53,8 @@ class Framed:
         self.source_fps = float(source_fps)
         self.color_input = bool(color_input)
         self.frame_count = frame_count if frame_count is not None else (len(frames) if hasattr(frames, "__len__") else None)
-        self.input_frame = np.zeros((height, width, 3 if color_input else 1), dtype=np.uint8)
+        self._input_frame = np.zeros((height, width, 3 if color_input else 1), dtype=np.uint8)
+        self._input_on_device = False
         self.video = B.Video(width, height, 3 if color_input else 1, B.MODE_FRAME_PERFECT, device, max_depth)
 
     # ---- Framed's own builder methods ----
@@ -75,6 +78,14 @@ class Framed:
 
     def get_ref_time(self) -> int:
         return self.video.info().ref_time
+
+    @property
+    def input_frame(self) -> np.ndarray:
+        """framed.rs:129: the frame after handle_color (fetched from the device when it was made there)."""
+        if self._input_on_device:
+            self._input_frame = self.video.input_frame()
+            self._input_on_device = False
+        return self._input_frame
 
     def get_last_input_frame(self) -> np.ndarray:
         return self.input_frame
@@ -120,12 +131,13 @@ class Framed:
         frame = np.asarray(frame, dtype=np.uint8)
         if frame.ndim == 2:
             frame = frame[..., None]
-        if frame.shape[-1] == 3:
-            self.input_frame = handle_color(frame, self.color_input)
-        else:
-            self.input_frame = frame
+        # handle_color (framed.rs:129): a colour frame for a gray transcode is folded on the device
+        want_src = 3 if (frame.shape[-1] == 3 and not self.color_input) else self.video.c
+        if want_src != self.video.src_c:
+            self.video.set_source_channels(want_src)
+        self._input_frame, self._input_on_device = frame, want_src != self.video.c
         ref_time = self.video.info().ref_time
-        events, counts = self.video.integrate_matrix(self.input_frame, float(ref_time))
+        events, counts = self.video.integrate_matrix(frame, float(ref_time))
         bounds = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
         return [events[bounds[i]:bounds[i + 1]] for i in range(len(counts))]
 
@@ -142,3 +154,26 @@ class Framed:
         """framed.rs:180-185"""
         i = self.video.info()
         return i.tps / i.ref_time * (i.width * i.height * i.channels) * 8.0
+
+
+class RawAdderWriter:
+    """The file side of `Encoder::new_raw` + `RawOutput` (codec/encoder.rs:170-229, raw/stream.rs:79-120):
+    header at construction, event bytes as they come from `Video.integrate_frames_host_raw`, the 11-byte
+    EOF event on close.  The bytes themselves are produced on the device; this only lays them out."""
+
+    def __init__(self, fileobj, video: B.Video, version: int = 3, source_camera: int = 0, adu_interval: int = 0):
+        self.f = fileobj
+        self.event_size = video.raw_event_size
+        self.header = video.raw_header(version, source_camera, adu_interval)
+        self.f.write(self.header)
+        self.n_events = 0
+
+    def write_body(self, body) -> None:
+        b = memoryview(np.ascontiguousarray(body)).cast("B")
+        assert len(b) % self.event_size == 0
+        self.f.write(b)
+        self.n_events += len(b) // self.event_size
+
+    def close(self) -> None:
+        self.f.write(B.raw_eof())
+        self.f.flush()

@@ -229,6 +229,43 @@ int adder_b200_video_integrate_frames_host(adder_b200_video* v, const uint8_t* f
                                            size_t events_cap, uint64_t* frame_counts, uint32_t* chunk_counts,
                                            uint64_t* n_events, uint32_t* frames_done);
 
+/* ---- colour source, gray transcode (the step before the path: framed.rs:129 handle_color) -----
+ * Framed::new(.., color_input = false, ..) builds a one-channel Video but its decoder still yields
+ * three-channel frames, which handle_color (utils/cv.rs:215-232) folds to gray on the CPU.  With
+ * source_channels = 3 on a one-channel video every frame handed to integrate_matrix /
+ * integrate_frames_host / integrate_frames_host_raw / integrate_frames_device is H*W*3 bytes and the
+ * same conversion runs on the device in front of the integrate kernel.  source_channels = 0 or the
+ * video's own channel count turns it off (default). */
+int adder_b200_video_set_source_channels(adder_b200_video* v, uint8_t source_channels);
+/* The gray frame the last integrate call worked on (Framed.input_frame, framed.rs:129, :163-169): H*W bytes to `out` [host]. */
+int adder_b200_video_input_frame(adder_b200_video* v, uint8_t* out);
+
+/* ---- raw .adder output (the step after the path: video.rs:736-740 feeding RawOutput) ---------
+ * Wire format: bincode fixint big-endian (encoder.rs:64-66). */
+#define ADDER_RAW_HEADER_MAX 37u
+#define ADDER_RAW_EOF_BYTES 11u
+/* EventStreamHeader + extensions for this video's plane and time parameters (codec/header.rs:14-85,
+ * encoder.rs:170-229).  version 0..3 (LATEST_CODEC_VERSION = 3, codec/mod.rs:74) -> 25/29/33/37 bytes;
+ * source_camera = SourceCamera variant index (FramedU8 = 0, lib.rs:35-47).  Host memory only. */
+int adder_b200_video_raw_header(const adder_b200_video* v, uint8_t version, uint32_t source_camera, uint32_t adu_interval,
+                                uint8_t* out, size_t cap, size_t* n_bytes);
+/* RawOutput::into_writer's EOF event (raw/stream.rs:79-92): always the 11-byte form. */
+int adder_b200_raw_eof(uint8_t* out, size_t cap, size_t* n_bytes);
+/* Bytes per event on the wire for this plane: 9 (one channel) or 11 (header.rs:77-81). */
+int adder_b200_video_raw_event_size(const adder_b200_video* v);
+/* RawOutput::ingest_event (raw/stream.rs:100-120) for events already in HBM, queued on the handle's
+ * stream: the first min(*d_n_events, n_events_max) records of d_events -> d_out (4-byte aligned,
+ * event_size bytes each).  d_n_events is a device word, e.g. the last entry of a frame's chunk offsets. */
+int adder_b200_video_raw_encode_device(adder_b200_video* v, const adder_event_t* d_events, const uint32_t* d_n_events,
+                                       uint64_t n_events_max, uint8_t* d_out);
+/* adder_b200_video_integrate_frames_host, delivering the raw stream body instead of records: what
+ * Framed::consume + the raw encoder produce for n_frames frames, copies and kernels overlapped.
+ * bytes_out receives event_size bytes per event, all frames back to back (no header, no EOF). */
+int adder_b200_video_integrate_frames_host_raw(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
+                                               uint32_t n_frames, float time_spanned, uint8_t* bytes_out, size_t bytes_cap,
+                                               uint64_t* frame_counts, uint32_t* chunk_counts, uint64_t* n_bytes,
+                                               uint32_t* frames_done);
+
 /* Back to the state of a fresh Video::new (video.rs:350-438) with the current parameters kept:
  * what adder-viz does on EOF by rebuilding the source (adder.rs:151-166). */
 int adder_b200_video_reset_state(adder_b200_video* v);

@@ -762,3 +762,69 @@ int oracle_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ---- raw .adder wire format ------------------------------------------------------------------- */
+
+static uint8_t* put_u16(uint8_t* p, uint16_t v) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; return p + 2; }
+static uint8_t* put_u32(uint8_t* p, uint32_t v) {
+  p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
+  return p + 4;
+}
+
+size_t oracle_raw_header(uint8_t* out, int compressed, uint8_t version, uint16_t width, uint16_t height, uint32_t tps,
+                         uint32_t ref_interval, uint32_t delta_t_max, uint8_t channels, uint32_t source_camera,
+                         uint32_t time_mode, uint32_t adu_interval) {
+  static const uint8_t magic_raw[5] = {97, 100, 100, 101, 114}; /* header.rs:5 'adder' */
+  static const uint8_t magic_cmp[5] = {97, 100, 100, 101, 99};  /* header.rs:6 'addec' */
+  if (version > 3) return 0; /* encoder.rs:228 BadFile */
+  uint8_t* p = out;
+  memcpy(p, compressed ? magic_cmp : magic_raw, 5); /* [u8;5]: no length prefix */
+  p += 5;
+  *p++ = version;
+  *p++ = 98; /* 'b' header.rs:68 */
+  p = put_u16(p, width);
+  p = put_u16(p, height);
+  p = put_u32(p, tps);
+  p = put_u32(p, ref_interval);
+  p = put_u32(p, delta_t_max);
+  *p++ = channels == 1 ? 9 : 11; /* header.rs:77-81 */
+  *p++ = channels;
+  /* extension V0 is an empty struct: no bytes (encoder.rs:193-197) */
+  if (version >= 1) p = put_u32(p, source_camera); /* enum as u32 variant index, :199-207 */
+  if (version >= 2) p = put_u32(p, time_mode);     /* :209-217 */
+  if (version >= 3) p = put_u32(p, adu_interval);  /* :219-227 */
+  return (size_t)(p - out);
+}
+
+size_t oracle_raw_encode(const adder_event_t* ev, size_t n, uint8_t channels, uint8_t* out) {
+  uint8_t* p = out;
+  for (size_t i = 0; i < n; i++) {
+    p = put_u16(p, ev[i].x);
+    p = put_u16(p, ev[i].y);
+    if (channels != 1) { /* Option<u8>: tag 1 then the value (raw/stream.rs:115-117) */
+      *p++ = 1;
+      *p++ = ev[i].c;
+    }
+    *p++ = ev[i].d;
+    p = put_u32(p, ev[i].t);
+  }
+  return (size_t)(p - out);
+}
+
+size_t oracle_raw_eof(uint8_t* out) {
+  static const uint8_t eof[11] = {0xFF, 0xFF, 0xFF, 0xFF, 1, 0, 0, 0, 0, 0, 0}; /* x = y = EOF_PX_ADDRESS, c = Some(0), d = 0, t = 0 */
+  memcpy(out, eof, 11);
+  return 11;
+}
+
+/* ---- handle_color (utils/cv.rs:215-232) ------------------------------------------------------- */
+void oracle_handle_color(const uint8_t* rgb, size_t n_px, uint8_t* out) {
+  for (size_t i = 0; i < n_px; i++) {
+    volatile double a = (double)rgb[3 * i] * 0.114;
+    volatile double b = (double)rgb[3 * i + 1] * 0.587;
+    volatile double c = (double)rgb[3 * i + 2] * 0.299;
+    volatile double s = a + b;
+    s = s + c;
+    out[i] = s >= 255.0 ? 255 : (s > 0.0 ? (uint8_t)s : 0); /* `as u8`: truncating, saturating */
+  }
+}

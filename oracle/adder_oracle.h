@@ -138,6 +138,23 @@ const oracle_px* oracle_video_px(const oracle_video* v, size_t index);
 
 int oracle_max_threads(void);
 
+/* handle_color, adder-codec-rs/src/utils/cv.rs:215-232: (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in f64,
+ * evaluated left to right, truncating and saturating.  rgb: n_px * 3 bytes, out: n_px bytes. */
+void oracle_handle_color(const uint8_t* rgb, size_t n_px, uint8_t* out);
+
+/* ---- raw .adder wire format ---------------------------------
+ * bincode 1.3 fixint big-endian, adder-codec-core/src/codec/encoder.rs:64-66, raw/stream.rs:34-36. */
+/* EventStreamHeader + extensions V0..V3: codec/header.rs:14-85, encoder.rs:170-229.
+ * Returns the bytes written: 25 (v0), 29 (v1), 33 (v2), 37 (v3); 0 for an unknown version. */
+size_t oracle_raw_header(uint8_t* out, int compressed, uint8_t version, uint16_t width, uint16_t height, uint32_t tps,
+                         uint32_t ref_interval, uint32_t delta_t_max, uint8_t channels, uint32_t source_camera,
+                         uint32_t time_mode, uint32_t adu_interval);
+/* RawOutput::ingest_event for n events, raw/stream.rs:100-120: EventSingle (9 bytes) when the plane
+ * has one channel, Event with c = Some (11 bytes) otherwise.  Returns the bytes written. */
+size_t oracle_raw_encode(const adder_event_t* ev, size_t n, uint8_t channels, uint8_t* out);
+/* RawOutput::into_writer's EOF event, raw/stream.rs:79-92: always the 11-byte form. */
+size_t oracle_raw_eof(uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,14 @@ def lib() -> C.CDLL:
     L.oracle_px_set_d_for_continuous.restype = i32
     L.oracle_px_set_d_for_continuous.argtypes = [C.POINTER(Px), f32, u32, C.POINTER(Event)]
     L.oracle_px_integrate.argtypes = [C.POINTER(Px), f32, f32, i32, u32, u32, u8, u8, i32]
+    L.oracle_handle_color.restype = None
+    L.oracle_handle_color.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.oracle_raw_header.restype = C.c_size_t
+    L.oracle_raw_header.argtypes = [C.c_void_p, i32, u8, C.c_uint16, C.c_uint16, u32, u32, u32, u8, u32, u32, u32]
+    L.oracle_raw_encode.restype = C.c_size_t
+    L.oracle_raw_encode.argtypes = [C.c_void_p, C.c_size_t, u8, C.c_void_p]
+    L.oracle_raw_eof.restype = C.c_size_t
+    L.oracle_raw_eof.argtypes = [C.c_void_p]
     L.oracle_get_frame_value_u8.restype = u8
     L.oracle_get_frame_value_u8.argtypes = [u8, u32, C.c_double, f32, u32, i32, u32, u32]
     L.oracle_log2_raw.restype = f32
@@ -307,3 +315,35 @@ def crf_parameters(crf, w, h) -> CrfParameters:
 
 def max_threads() -> int:
     return lib().oracle_max_threads()
+
+
+def raw_header(width, height, channels, tps, ref_interval, delta_t_max, version=3, source_camera=0, time_mode=TIME_ABSOLUTE_T,
+               adu_interval=0, compressed=False) -> bytes:
+    """EventStreamHeader + extensions (codec/header.rs, encoder.rs:170-229)."""
+    buf = (C.c_uint8 * 64)()
+    n = lib().oracle_raw_header(buf, int(compressed), version, width, height, tps, ref_interval, delta_t_max, channels,
+                                source_camera, time_mode, adu_interval)
+    return bytes(buf[:n])
+
+
+def raw_encode(events: np.ndarray, channels: int) -> bytes:
+    """RawOutput::ingest_event over an event array (raw/stream.rs:100-120)."""
+    events = np.ascontiguousarray(events)
+    out = np.empty(len(events) * 11 + 1, dtype=np.uint8)
+    n = lib().oracle_raw_encode(events.ctypes.data, len(events), channels, out.ctypes.data)
+    return out[:n].tobytes()
+
+
+def raw_eof() -> bytes:
+    buf = (C.c_uint8 * 11)()
+    lib().oracle_raw_eof(buf)
+    return bytes(buf)
+
+
+def handle_color(frame: np.ndarray) -> np.ndarray:
+    """(H, W, 3) u8 -> (H, W, 1) u8 gray, utils/cv.rs:215-232."""
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    assert frame.shape[-1] == 3
+    out = np.empty(frame.shape[:-1] + (1,), dtype=np.uint8)
+    lib().oracle_handle_color(frame.ctypes.data, out.size, out.ctypes.data)
+    return out

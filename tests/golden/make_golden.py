@@ -74,5 +74,22 @@ def main():
     print("frames", frames.shape, "events", len(rec))
 
 
+
+
+def digest():
+    """lake_adder_digest.json: size and SHA-256 of the reference's raw .adder fixture, so that a test
+    can re-serialise the golden events (header + 9-byte records + 11-byte EOF) and compare the whole
+    file without reading /root/reference."""
+    import hashlib
+    import json
+
+    raw = open(os.path.join(REF, "lake_scaled_hd_out.adder"), "rb").read()
+    json.dump({"file": "adder-codec-rs/tests/samples/lake_scaled_hd_out.adder", "size": len(raw),
+               "sha256": hashlib.sha256(raw).hexdigest()}, open(os.path.join(HERE, "lake_adder_digest.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    if len(sys.argv) > 1 and sys.argv[1] == "digest":
+        digest()
+    else:
+        sys.exit(main())

@@ -252,3 +252,123 @@ def test_many_events_per_pixel_use_the_dead_level_park():
             most = max(most, np.bincount(eo["y"].astype(np.int64) * case.w + eo["x"]).max())
     assert most >= 6, most
     _assert_state_equal(gv, ov, case.w * case.h, step=7)
+
+
+@pytest.mark.parametrize("name", ["cfg2_rgb_noise_crf3", "cfg3_jitter_c5", "ragged_37x13x3_chunk4", "cfg5_static_normal"])
+def test_raw_stream_body_equals_the_oracle_encoder(name):
+    """integrate_frames_host_raw: the wire bytes RawOutput would write for the same events
+    (9-byte records for one channel, 11-byte for colour), and the header for this video."""
+    case = cases.CASES_BY_NAME[name]
+    gv, ov = _pair(case)
+    frames = case.frames()
+    want = b""
+    exp_fc = []
+    for f in range(case.n_frames):
+        eo, _ = ov.integrate_matrix(frames[f], case.time)
+        want += O.raw_encode(eo, case.c)
+        exp_fc.append(len(eo))
+    pinned = A.pinned_empty(frames.shape, np.uint8)
+    pinned[...] = frames
+    out = A.pinned_empty((len(want) + 64,), np.uint8)
+    body, fc, _ = gv.integrate_frames_host_raw(np.asarray(pinned), case.time, np.asarray(out))
+    assert gv.raw_event_size == (9 if case.c == 1 else 11)
+    assert body.tobytes() == want
+    assert np.array_equal(fc, np.array(exp_fc, dtype=np.uint64))
+    i = gv.info()
+    assert gv.raw_header() == O.raw_header(case.w, case.h, case.c, i.tps, i.ref_time, i.delta_t_max, version=3, time_mode=i.time_mode)
+    assert gv.raw_header(version=1) == O.raw_header(case.w, case.h, case.c, i.tps, i.ref_time, i.delta_t_max, version=1)
+    assert A.raw_eof() == O.raw_eof()
+
+
+def test_raw_encode_device_resident_events():
+    """Events left in HBM by the device-resident form, serialised in HBM, count read from the chunk offsets."""
+    case = cases.Case("mid_noise_gray", 320, 200, 1, synth.NOISE, 6, crf=3)
+    gv, ov = _pair(case)
+    P = case.w * case.h * case.c
+    frames = case.frames()
+    d_frames = gv.device_alloc(P)
+    stride = P * 3
+    d_events = gv.device_alloc(stride * 12)
+    d_off = gv.device_alloc((gv.n_chunks + 1) * 4)
+    d_raw = gv.device_alloc(stride * 9)
+    for f in range(case.n_frames):
+        d_frames.from_host(frames[f])
+        gv.integrate_frames_device(d_frames.ptr, P, 1, case.time, d_events.ptr, stride, d_off.ptr)
+        gv.raw_encode_device(d_events.ptr, d_off.ptr + gv.n_chunks * 4, stride, d_raw.ptr)
+        gv.sync()
+        eo, _ = ov.integrate_matrix(frames[f], case.time)
+        assert d_raw.to_host(nbytes=len(eo) * 9).tobytes() == O.raw_encode(eo, 1), f"frame {f}"
+
+
+def test_colour_source_gray_transcode_on_device():
+    """set_source_channels(3): handle_color (utils/cv.rs:215-232) on the device in front of the integrate
+    kernel, through all three forms, against the oracle's handle_color + transcode."""
+    w, h, nf = 52, 21, 12  # odd sizes: the 4-pixel groups of the conversion kernel end ragged
+    rgb = synth.frames(synth.NOISE, 11, 0, nf, w, h, 3)
+    rgb[1] = 255
+    rgb[2] = 0
+    gv = A.Video(w, h, 1)
+    ov = O.Video(w, h, 1, O.MODE_FRAME_PERFECT)
+    for v in (gv, ov):
+        v.update_crf(2)
+    gv.set_source_channels(3)
+    exp = []
+    for f in range(nf):
+        gray = O.handle_color(rgb[f])
+        eo, co = ov.integrate_matrix(gray, 255.0)
+        exp.append(eo)
+        if f < 4:  # single-frame host form
+            eg, cg = gv.integrate_matrix(rgb[f], 255.0)
+            assert eg.tobytes() == eo.tobytes() and np.array_equal(cg, co), f"frame {f}"
+            assert np.array_equal(gv.input_frame(), gray)
+    # batched host form
+    pinned = A.pinned_empty((4, h, w, 3), np.uint8)
+    pinned[...] = rgb[4:8]
+    out = A.pinned_empty((sum(len(e) for e in exp[4:8]) + 8,), A.EVENT_DTYPE)
+    ev, _, _ = gv.integrate_frames_host(np.asarray(pinned), 255.0, np.asarray(out))
+    assert ev.tobytes() == np.concatenate(exp[4:8]).tobytes()
+    # device-resident form
+    d_rgb = gv.device_alloc(4 * h * w * 3)
+    d_rgb.from_host(rgb[8:12])
+    stride = w * h * 3
+    d_events = gv.device_alloc(4 * stride * 12)
+    d_off = gv.device_alloc(4 * (gv.n_chunks + 1) * 4)
+    gv.integrate_frames_device(d_rgb.ptr, 0, 4, 255.0, d_events.ptr, stride, d_off.ptr)
+    gv.sync()
+    offs = d_off.to_host(np.uint32).reshape(4, -1)
+    for k in range(4):
+        n = int(offs[k, -1])
+        assert n == len(exp[8 + k])
+        assert d_events.to_host(A.EVENT_DTYPE, nbytes=n * 12, offset=k * stride * 12).tobytes() == exp[8 + k].tobytes()
+    assert np.array_equal(gv.input_frame(), O.handle_color(rgb[11]))
+    assert np.array_equal(gv.running_intensities(), ov.running_intensities())
+
+
+def test_raw_adder_file_layout(tmp_path):
+    """Header + body + EOF written through RawAdderWriter parse back to the oracle's events
+    (adder-info derives the event count as (eof_pos - 1 - header_size) / event_size, adder-info/src/main.rs:42)."""
+    import struct
+
+    from adder_codec_rs_b200.framed import RawAdderWriter
+
+    case = cases.CASES_BY_NAME["cfg3_jitter_c5"]
+    gv, ov = _pair(case)
+    frames = case.frames()
+    exp = np.concatenate([ov.integrate_matrix(frames[f], case.time)[0] for f in range(case.n_frames)])
+    pinned = A.pinned_empty(frames.shape, np.uint8)
+    pinned[...] = frames
+    out = A.pinned_empty((len(exp) * 9 + 64,), np.uint8)
+    path = tmp_path / "out.adder"
+    with open(path, "wb") as fh:
+        wr = RawAdderWriter(fh, gv)
+        body, _, _ = gv.integrate_frames_host_raw(np.asarray(pinned), case.time, np.asarray(out))
+        wr.write_body(body)
+        wr.close()
+    raw = open(path, "rb").read()
+    assert raw[:5] == b"adder" and raw[5] == 3 and len(raw) == 37 + 9 * len(exp) + 11
+    w, h, tps, ref, dtm = struct.unpack(">HHIII", raw[7:23])
+    assert (w, h, ref, dtm, raw[23], raw[24]) == (case.w, case.h, case.ref, case.dtm, 9, 1)
+    rec = np.frombuffer(raw[37:-11], dtype=np.dtype([("x", ">u2"), ("y", ">u2"), ("d", "u1"), ("t", ">u4")]))
+    assert np.array_equal(rec["x"], exp["x"]) and np.array_equal(rec["y"], exp["y"])
+    assert np.array_equal(rec["d"], exp["d"]) and np.array_equal(rec["t"], exp["t"])
+    assert raw[-11:] == O.raw_eof() and wr.n_events == len(exp)
