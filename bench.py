@@ -284,13 +284,36 @@ def run_ours(args):
     barrier()
     assert tot == events_per_step * e2e_steps
 
+    # the same step delivering the raw .adder body (11-byte wire records for RGB) instead of 12-byte records:
+    # what Framed::consume + Encoder<RawOutput>::ingest_event produce.  One timed step.
+    esize = v.raw_event_size
+    del host_events
+    host_bytes = np.asarray(A.pinned_empty((max_sub_events * esize,), np.uint8))
+
+    def step_host_raw():
+        v.reset_state()
+        v.update_crf(CRF)
+        total = 0
+        for f0 in range(0, NF, sub):
+            body, fc, cc = v.integrate_frames_host_raw(hf[f0:f0 + sub], float(REF), host_bytes)
+            total += len(body)
+        return total
+
+    step_host_raw()
+    barrier()
+    t0 = time.perf_counter()
+    raw_bytes = step_host_raw()
+    raw_s = time.perf_counter() - t0
+    barrier()
+    assert raw_bytes == events_per_step * esize
+
     # ---- reduce over ranks -------------------------------------------------------------------
     if dist is not None:
         import torch
 
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s, raw_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = t[0].item(), t[1].item()
+        ms, e2e_s, raw_s = t[0].item(), t[1].item(), t[2].item()
         s = torch.tensor([float(alg_bytes_step), float(events_per_step), float(launches)], dtype=torch.float64, device="cuda")
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         alg_bytes_all, events_all, launches = s[0].item(), s[1].item(), int(s[2].item())
@@ -315,11 +338,13 @@ def run_ours(args):
                        "events_per_step": events_all, "events_per_px_frame": events_all / px_step},
             "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": P * NF, "d2h_bytes_per_step": int(events_per_step * 12 + (n_chunks + 1) * 4 * NF),
                     "steps": e2e_steps, "api": "adder_b200_video_integrate_frames_host, pinned host frames in, all events out to pinned host memory"},
+            "e2e_raw": {"value": px_step / raw_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": P * NF, "d2h_bytes_per_step": int(raw_bytes + (n_chunks + 1) * 4 * NF),
+                        "steps": 1, "api": "adder_b200_video_integrate_frames_host_raw: the raw .adder stream body (wire records serialised on the device) to pinned host memory"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                         "kernel": "integrate_frame_kernel<false>", "algorithmic_bytes_per_launch": alg_bytes_step / NF,
+                         "kernel": "integrate_frame_kernel<8,false>", "algorithmic_bytes_per_launch": alg_bytes_step / NF,
                          "algorithmic_bytes_per_px_frame": alg_bytes_step / (P * NF),
                          "node_loads_per_px_frame": cnt["node_loads"] / (P * NF), "node_stores_per_px_frame": cnt["node_stores"] / (P * NF),
                          "note": "time = CUDA events around the whole timed region on the launching stream (300 integrate launches + 2 reset kernels per step)"},
