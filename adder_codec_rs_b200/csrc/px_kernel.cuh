@@ -36,6 +36,14 @@
 #include "px_machine.cuh"
 #include "state_layout.h"
 
+/* build-time switches of the kernel (A/B builds: tools/gpu_ab.sh) */
+#ifndef ADDER_WO_PIPE
+#define ADDER_WO_PIPE 1 /* write-out: the read of record e+1 overlaps the store of record e */
+#endif
+#ifndef ADDER_DEEP_PF
+#define ADDER_DEEP_PF 2 /* px_step entry: pull levels 2..length-1 towards L1 (1) or L2 (2); 0 = off */
+#endif
+
 namespace adder {
 
 struct FrameArgs {
@@ -86,6 +94,19 @@ struct GlobalNodes {
   }
   /* level 1 is fetched with the root, before the length is known: it counts as algorithmic traffic
    * only when the state machine needed it; a level requested ahead and then dropped does not count */
+  /* every level the walk will visit, requested at once (no register, no scoreboard) */
+  __device__ __forceinline__ void prefetch_levels(uint32_t len) {
+#if ADDER_DEEP_PF
+    const uint4* q = p + 2ull * stride;
+    for (uint32_t k = 2; k < len; k++, q += stride) {
+#if ADDER_DEEP_PF == 1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+#else
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+#endif
+    }
+#endif
+  }
   __device__ __forceinline__ void used_preloaded() { n_loads++; }
   __device__ __forceinline__ void unused_load() { n_loads--; }
 };
@@ -521,6 +542,28 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           }
           const uint32_t w0 = x | ((y + a.row0) << 16);
           EventPark<S> park{const_cast<uint32_t*>(pslot_t) + q, const_cast<uint8_t*>(pslot_d) + q, a.nodes + i, a.spill1 + i, a.level_stride, TILE, a.px.depth, nev, 0u};
+#if ADDER_WO_PIPE
+          /* records beyond the shared-memory slot come back from global memory: the read of record
+           * e+1 is in flight while record e is stored */
+          uint32_t dd, tt;
+          park.get(0u, dd, tt);
+#pragma unroll 1
+          for (uint32_t e = 0; e < nev; e++) {
+            uint32_t dn = 0, tn = 0;
+            if (e + 1u < nev) park.get(e + 1u, dn, tn);
+            const unsigned long long rec = (unsigned long long)first + e;
+            if (rec < a.ev_cap) {
+              uint32_t* dst = a.ev_words + rec * 3ull;
+              dst[0] = w0;
+              dst[1] = c | (dd << 8);
+              dst[2] = tt;
+            } else {
+              capbits = ADDER_DEVERR_CAPACITY;
+            }
+            dd = dn;
+            tt = tn;
+          }
+#else
 #pragma unroll 1
           for (uint32_t e = 0; e < nev; e++) {
             uint32_t dd, tt;
@@ -535,6 +578,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
               capbits = ADDER_DEVERR_CAPACITY;
             }
           }
+#endif
         }
       }
       if (capbits) atomicOr(a.err, capbits);

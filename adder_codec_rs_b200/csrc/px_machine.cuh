@@ -267,6 +267,7 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
   uint32_t base = HDR_BASE(h.y), cth = HDR_CTHRESH(h.y), cnt = HDR_COUNTER(h.y);
   uint32_t len = HDR_LENGTH(h.y);
   uint32_t popped = HDR_POPPED(h.y);
+  mem.prefetch_levels(len);
   bool root_new = false; /* the root's best event after this frame is not the one of the last frame */
 
   /* ---- video.rs:1338-1358: the pixel changed by more than c_thresh -> pop_best_events -------- */

@@ -24,6 +24,7 @@ struct HostNodes {
   adder::Node load(uint32_t k) const { return p[(size_t)k * stride]; }
   void store(uint32_t k, const adder::Node& n) const { p[(size_t)k * stride] = n; }
   void used_preloaded() const {}
+  void prefetch_levels(uint32_t) const {}
   void unused_load() const {}
 };
 struct VecSink {
