@@ -41,6 +41,7 @@ SYMBOLS = [
     "adder_b200_video_raw_header", "adder_b200_raw_eof", "adder_b200_video_raw_event_size",
     "adder_b200_video_raw_encode_device", "adder_b200_video_integrate_frames_host_raw",
     "adder_b200_video_set_source_channels", "adder_b200_video_input_frame",
+    "adder_b200_video_update_detect_features", "adder_b200_video_new_features", "adder_b200_video_feature_mask",
 ]
 
 
@@ -153,6 +154,9 @@ def lib() -> C.CDLL:
         "adder_b200_video_integrate_frames_host_raw": (i32, [vp, vp, sz, u32, f32, vp, sz, vp, vp, P(u64), P(u32)]),
         "adder_b200_video_set_source_channels": (i32, [vp, u8]),
         "adder_b200_video_input_frame": (i32, [vp, vp]),
+        "adder_b200_video_update_detect_features": (i32, [vp, i32, i32]),
+        "adder_b200_video_new_features": (i32, [vp, vp, sz, P(u32)]),
+        "adder_b200_video_feature_mask": (i32, [vp, vp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -317,6 +321,24 @@ class Video:
         """The (gray) frame the last integrate call worked on (Framed.input_frame, framed.rs:129)."""
         out = np.empty((self.h, self.w, self.c), dtype=np.uint8)
         _check(self.L.adder_b200_video_input_frame(self.v, out.ctypes.data))
+        return out
+
+    def update_detect_features(self, detect_features: bool, feature_rate_adjustment: bool = False):
+        """Video::update_detect_features, video.rs:825-837 (drawing / clustering flags are GUI-only)."""
+        _check(self.L.adder_b200_video_update_detect_features(self.v, int(detect_features), int(feature_rate_adjustment)))
+
+    def new_features(self) -> np.ndarray:
+        """[x, y] of the features newly found by the last integrated frame, sorted (the reference keeps a HashSet)."""
+        n = C.c_uint32()
+        _check(self.L.adder_b200_video_new_features(self.v, None, 0, C.byref(n)))
+        out = np.empty((n.value, 2), dtype=np.uint16)
+        if n.value:
+            _check(self.L.adder_b200_video_new_features(self.v, out.ctypes.data, n.value, C.byref(n)))
+        return out[np.lexsort((out[:, 0], out[:, 1]))] if len(out) else out
+
+    def feature_mask(self) -> np.ndarray:
+        out = np.empty((self.h, self.w), dtype=np.uint8)
+        _check(self.L.adder_b200_video_feature_mask(self.v, out.ctypes.data))
         return out
 
     def set_row_offset(self, row0):

@@ -18,6 +18,7 @@
 
 #include "../../include/adder_b200.h"
 #include "px_kernel.cuh"
+#include "feature_kernel.cuh"
 #include "raw_kernel.cuh"
 #include "synth.cuh"
 
@@ -123,6 +124,13 @@ struct adder_b200_video {
   uint8_t* d_rgb[kRing] = {nullptr, nullptr, nullptr}; /* three-channel staging of the host forms (gray transcode of a colour source) */
   uint8_t* d_gray = nullptr;                           /* the same for the device-resident form */
   const uint8_t* d_last_input = nullptr;               /* the (gray) frame the last integrate call worked on */
+  /* feature detection (video.rs:202-210) */
+  bool feature_detection = false, feature_rate_adjustment = false;
+  uint8_t* d_feat_mask = nullptr;  /* (H,W) */
+  uint32_t* d_new_xy = nullptr;    /* x | y<<16 of the last frame's new features */
+  uint32_t* d_n_new = nullptr;
+  uint32_t* d_feat_off = nullptr;  /* chunk offsets for frames whose caller did not ask for them */
+  uint32_t new_cap = 0;
   adder_event_t* d_events[kRing] = {nullptr, nullptr, nullptr};
   uint8_t* d_raw[kRing] = {nullptr, nullptr, nullptr}; /* wire-format copies of d_events (raw host form only) */
   uint32_t* d_chunk_off[kRing] = {nullptr, nullptr, nullptr};
@@ -301,6 +309,21 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   a.running = v->d_running;
   a.ev_words = reinterpret_cast<uint32_t*>(d_events);
   a.ev_cap = cap;
+  if (v->feature_detection) {
+    if (v->row0 != 0) return fail(ADDER_ERR_UNSUPPORTED, "feature detection on a row band: the FAST neighbourhood would cross bands");
+    if (!v->d_feat_mask) {
+      const size_t hw = (size_t)v->w * v->h;
+      v->new_cap = (uint32_t)std::min<size_t>(hw, 1u << 24);
+      CU(cudaMalloc(&v->d_feat_mask, hw));
+      CU(cudaMemsetAsync(v->d_feat_mask, 0, hw, stream));
+      CU(cudaMalloc(&v->d_new_xy, (size_t)v->new_cap * sizeof(uint32_t)));
+      CU(cudaMalloc(&v->d_n_new, sizeof(uint32_t)));
+    }
+    if (!d_chunk_off) { /* the feature pass walks the stream chunk by chunk */
+      if (!v->d_feat_off) CU(cudaMalloc(&v->d_feat_off, ((size_t)v->h + 1) * sizeof(uint32_t))); /* n_chunks <= h */
+      d_chunk_off = v->d_feat_off;
+    }
+  }
   a.chunk_off = d_chunk_off;
   a.tile_status = v->d_status;
   a.ticket = v->d_ticket;
@@ -353,6 +376,22 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   v->ticket_base += v->n_tiles_r + v->grid; /* every CTA draws one ticket past the end */
   v->launches++;
   CU(cudaGetLastError());
+  if (!v->feature_detection && v->d_n_new) CU(cudaMemsetAsync(v->d_n_new, 0, sizeof(uint32_t), stream)); /* this frame found none */
+  if (v->feature_detection) { /* video.rs:744 handle_features */
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v->device));
+    CU(cudaMemsetAsync(v->d_n_new, 0, sizeof(uint32_t), stream));
+    adder::feature_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_events), d_chunk_off, v->n_chunks, v->chunk_rows,
+                                                      v->row0, v->d_running, v->w, v->h, v->c, v->d_feat_mask, v->d_new_xy, v->d_n_new,
+                                                      v->new_cap);
+    v->launches++;
+    if (v->feature_rate_adjustment && v->crf.feature_c_radius > 0) { /* :1089-1104 */
+      adder::feature_reset_kernel<<<sms * 4, 256, 0, stream>>>(v->d_hdr, v->d_new_xy, v->d_n_new, v->new_cap, v->w, v->h, v->c,
+                                                              (int)v->crf.feature_c_radius, std::min<uint32_t>(v->crf.c_thresh_baseline, 2u));
+      v->launches++;
+    }
+    CU(cudaGetLastError());
+  }
   return ADDER_OK;
 }
 
@@ -515,6 +554,10 @@ void adder_b200_video_destroy(adder_b200_video* v) {
   cudaFree(v->d_counters);
   cudaFree(v->d_exact_lut);
   cudaFree(v->d_gray);
+  cudaFree(v->d_feat_mask);
+  cudaFree(v->d_new_xy);
+  cudaFree(v->d_n_new);
+  cudaFree(v->d_feat_off);
   if (v->h_err) cudaFreeHost(v->h_err);
   if (v->h_total) cudaFreeHost(v->h_total);
   for (int s = 0; s < kRing; s++) {
@@ -645,6 +688,49 @@ int adder_b200_video_set_in_interval_count(adder_b200_video* v, uint32_t n) {
   return ADDER_OK;
 }
 
+int adder_b200_video_update_detect_features(adder_b200_video* v, int detect_features, int feature_rate_adjustment) {
+  if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  v->feature_detection = detect_features != 0;
+  v->feature_rate_adjustment = feature_rate_adjustment != 0;
+  return ADDER_OK;
+}
+
+int adder_b200_video_new_features(adder_b200_video* v, uint16_t* xy_out, size_t cap, uint32_t* n) {
+  if (!v || !n || (cap && !xy_out)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  *n = 0;
+  if (!v->d_n_new) return ADDER_OK; /* detection never ran */
+  if (int rc = set_device(v)) return rc;
+  uint32_t cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, v->d_n_new, sizeof(cnt), cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  if (cnt > v->new_cap) return fail(ADDER_ERR_CAPACITY, "more new features (%u) than the device list holds (%u)", cnt, v->new_cap);
+  *n = cnt;
+  const uint32_t take = (uint32_t)std::min<size_t>(cnt, cap);
+  if (take) {
+    std::vector<uint32_t> tmp(take);
+    CU(cudaMemcpyAsync(tmp.data(), v->d_new_xy, (size_t)take * sizeof(uint32_t), cudaMemcpyDeviceToHost, v->stream));
+    CU(cudaStreamSynchronize(v->stream));
+    for (uint32_t k = 0; k < take; k++) {
+      xy_out[2 * k] = (uint16_t)(tmp[k] & 0xFFFFu);
+      xy_out[2 * k + 1] = (uint16_t)(tmp[k] >> 16);
+    }
+  }
+  return ADDER_OK;
+}
+
+int adder_b200_video_feature_mask(adder_b200_video* v, uint8_t* out) {
+  if (!v || !out) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (int rc = set_device(v)) return rc;
+  const size_t hw = (size_t)v->w * v->h;
+  if (!v->d_feat_mask) {
+    memset(out, 0, hw);
+    return ADDER_OK;
+  }
+  CU(cudaMemcpyAsync(out, v->d_feat_mask, hw, cudaMemcpyDeviceToHost, v->stream));
+  CU(cudaStreamSynchronize(v->stream));
+  return ADDER_OK;
+}
+
 int adder_b200_video_set_source_channels(adder_b200_video* v, uint8_t source_channels) {
   if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
   if (source_channels != 0 && source_channels != v->c && !(source_channels == 3 && v->c == 1))
@@ -720,6 +806,7 @@ int adder_b200_video_reset_state(adder_b200_video* v) {
   v->running_t = 0.0f;
   v->in_interval_count = 1;
   v->display_force = true;
+  if (v->d_feat_mask) CU(cudaMemsetAsync(v->d_feat_mask, 0, (size_t)v->w * v->h, v->stream));
   return ADDER_OK;
 }
 

@@ -229,6 +229,20 @@ int adder_b200_video_integrate_frames_host(adder_b200_video* v, const uint8_t* f
                                            size_t events_cap, uint64_t* frame_counts, uint32_t* chunk_counts,
                                            uint64_t* n_events, uint32_t* frames_done);
 
+/* ---- feature detection: handle_features inside integrate_matrix (video.rs:744, :883-1113) -----
+ * Video::update_detect_features, video.rs:825-837 (show_features and feature_cluster only draw on the
+ * GUI frame and are not part of this library).  While on, every integrate call ends with is_feature
+ * (utils/cv.rs:22-212, FAST 9_16 on channel 0 of running_intensities) for the pixels that fired, the
+ * update of the feature sets, and — with feature_rate_adjustment and a non-zero feature_c_radius in the
+ * CRF parameters — c_thresh = min(c_thresh_baseline, 2) around every newly found feature.
+ * Not available on a row band (set_row_offset != 0): the 7x7 neighbourhood would cross GPUs. */
+int adder_b200_video_update_detect_features(adder_b200_video* v, int detect_features, int feature_rate_adjustment);
+/* The features newly inserted by the last integrated frame (the reference's `new_features`, video.rs:919-923):
+ * up to `cap` [x, y] pairs to xy_out [host], unordered; *n = how many there were. */
+int adder_b200_video_new_features(adder_b200_video* v, uint16_t* xy_out, size_t cap, uint32_t* n);
+/* VideoState.features as a mask: H*W bytes, 1 where (x, y) is in its chunk's feature set [host]. */
+int adder_b200_video_feature_mask(adder_b200_video* v, uint8_t* out);
+
 /* ---- colour source, gray transcode (the step before the path: framed.rs:129 handle_color) -----
  * Framed::new(.., color_input = false, ..) builds a one-channel Video but its decoder still yields
  * three-channel frames, which handle_color (utils/cv.rs:215-232) folds to gray on the CPU.  With

@@ -535,6 +535,11 @@ struct oracle_video {
   oracle_evec* chunks; /* big_buffer: one Vec<Event> per chunk */
   uint64_t live_entry, live_exit;
   uint32_t max_live, max_px_events;
+  /* feature detection, VideoState.{feature_detection, feature_rate_adjustment, features} video.rs:202-210 */
+  int feature_detection, feature_rate_adjustment;
+  uint8_t* feature_mask;   /* (H,W): coordinate is in its chunk's HashSet<Coord> (state.features) */
+  uint16_t* new_features;  /* [x,y] pairs newly inserted by the last frame */
+  size_t n_new_features, cap_new_features;
 };
 
 static uint32_t n_chunks_of(uint32_t h, uint32_t chunk_rows) { return (h + chunk_rows - 1) / chunk_rows; }
@@ -567,6 +572,7 @@ oracle_video* oracle_video_new(uint16_t w, uint16_t h, uint8_t c, int pixel_tree
   size_t n = (size_t)w * h * c;
   v->px = (oracle_px*)malloc(n * sizeof(oracle_px));
   v->running = (uint8_t*)calloc(n, 1);
+  v->feature_mask = (uint8_t*)calloc((size_t)w * h, 1);
   v->matrix_f32 = (float*)malloc(n * sizeof(float));
   size_t i = 0;
   for (uint32_t y = 0; y < h; y++)
@@ -583,6 +589,8 @@ void oracle_video_delete(oracle_video* v) {
   for (size_t i = 0; i < n; i++) oracle_px_free(&v->px[i]);
   free(v->px);
   free(v->running);
+  free(v->feature_mask);
+  free(v->new_features);
   free(v->matrix_f32);
   for (uint32_t i = 0; i < v->n_chunks; i++) free(v->chunks[i].data);
   free(v->chunks);
@@ -671,6 +679,129 @@ static void set_initial_d(oracle_video* v, const uint8_t* frame) {
   }
 }
 
+/* ---- feature detection: the one cross-pixel step of integrate_matrix ------------------------- */
+
+/* is_feature, adder-codec-rs/src/utils/cv.rs:22-212: asynchronous FAST 9_16 on channel 0 of the image */
+int oracle_is_feature(const uint8_t* img, uint16_t w, uint16_t h, uint8_t channels, uint16_t cx, uint16_t cy, uint8_t cc) {
+  static const int CIRCLE3[16][2] = {{0, 3}, {1, 3}, {2, 2}, {3, 1}, {3, 0}, {3, -1}, {2, -2}, {1, -3},
+                                     {0, -3}, {-1, -3}, {-2, -2}, {-3, -1}, {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}}; /* :26-31 */
+  const int INTENSITY_THRESHOLD = 30, STREAK_SIZE = 9;                                                          /* :22, :33 */
+  /* Coord::is_border(w, h, 3), lib.rs:353-358; c must be 0 (None counts as 0: c_usize) */
+  if (cx < 3 || (int)cx >= (int)w - 3 || cy < 3 || (int)cy >= (int)h - 3 || cc != 0) return 0; /* :69-71 */
+  const long c = channels, width = (long)w * c, y = cy, x = cx;
+  const int candidate = img[y * width + x * c];
+#define PX(k) ((int)img[(y + CIRCLE3[(k)][1]) * width + (x + CIRCLE3[(k)][0]) * c])
+#define TAB(v) ((v) - candidate < -INTENSITY_THRESHOLD ? 1 : ((v) - candidate > INTENSITY_THRESHOLD ? 2 : 0)) /* THRESHOLD_TABLE :35-50 */
+  int d = TAB(PX(0)) | TAB(PX(8)); /* :92-96 */
+  if (d == 0) return 0;
+  d &= TAB(PX(2)) | TAB(PX(10));
+  d &= TAB(PX(4)) | TAB(PX(12));
+  d &= TAB(PX(6)) | TAB(PX(14));
+  if (d == 0) return 0; /* :117-119 */
+  d &= TAB(PX(1)) | TAB(PX(9));
+  d &= TAB(PX(3)) | TAB(PX(11));
+  d &= TAB(PX(5)) | TAB(PX(13));
+  d &= TAB(PX(7)) | TAB(PX(15));
+  if (d & 1) { /* dark streak :142-172 */
+    const int vt = candidate - INTENSITY_THRESHOLD;
+    int count = 0;
+    for (int k = 0; k < 16; k++) {
+      if (PX(k) < vt) {
+        if (++count == STREAK_SIZE) return 1;
+      } else {
+        count = 0;
+      }
+    }
+    for (int k = 16; k < 25; k++) {
+      if (PX(k - 16) < vt) {
+        if (++count == STREAK_SIZE) return 1;
+      } else {
+        count = 0;
+        if (k == 17) return 0; /* :167-169: returns for the whole function, the bright test is not reached */
+      }
+    }
+  }
+  if (d & 2) { /* bright streak :174-205 */
+    const int vt = candidate + INTENSITY_THRESHOLD;
+    int count = 0;
+    for (int k = 0; k < 16; k++) {
+      if (PX(k) > vt) {
+        if (++count == STREAK_SIZE) return 1;
+      } else {
+        count = 0;
+      }
+    }
+    for (int k = 16; k < 25; k++) {
+      if (PX(k - 16) > vt) {
+        if (++count == STREAK_SIZE) return 1;
+      } else {
+        count = 0;
+        if (k == 17) return 0;
+      }
+    }
+  }
+#undef PX
+#undef TAB
+  return 0;
+}
+
+static int coord_eq(const adder_event_t* a, const adder_event_t* b) { return a->x == b->x && a->y == b->y && a->c == b->c; }
+
+/* Video::handle_features, video.rs:883-1113, without logging, drawing and clustering (display only) */
+static void handle_features(oracle_video* v) {
+  v->n_new_features = 0;
+  if (!v->feature_detection) return; /* :885-887 */
+  for (uint32_t ci = 0; ci < v->n_chunks; ci++) {
+    const oracle_evec* ev = &v->chunks[ci];
+    for (size_t j = 0; j < ev->len; j++) { /* events.iter().circular_tuple_windows() :898 */
+      const adder_event_t* e1 = &ev->data[j];
+      const adder_event_t* e2 = &ev->data[j + 1 < ev->len ? j + 1 : 0];
+      if ((e1->c == ADDER_C_NONE || e1->c == 0) && !coord_eq(e1, e2) && e1->d != ADDER_D_EMPTY) { /* :899-903 */
+        const size_t p = (size_t)e1->y * v->w + e1->x;
+        if (oracle_is_feature(v->running, v->w, v->h, v->c, e1->x, e1->y, 0)) {
+          if (!v->feature_mask[p]) { /* feature_set.insert(..) returned true :908-910 */
+            v->feature_mask[p] = 1;
+            if (v->n_new_features == v->cap_new_features) {
+              v->cap_new_features = v->cap_new_features ? v->cap_new_features * 2 : 64;
+              v->new_features = (uint16_t*)realloc(v->new_features, v->cap_new_features * 2 * sizeof(uint16_t));
+            }
+            v->new_features[2 * v->n_new_features] = e1->x;
+            v->new_features[2 * v->n_new_features + 1] = e1->y;
+            v->n_new_features++;
+          }
+        } else {
+          v->feature_mask[p] = 0; /* feature_set.remove :912 */
+        }
+      }
+    }
+  }
+  /* :1077-1104: c_thresh of every pixel within the radius of a new feature */
+  if (v->feature_rate_adjustment && v->crf.feature_c_radius > 0) {
+    const int radius = (int)v->crf.feature_c_radius;
+    const uint8_t value = v->crf.c_thresh_baseline < 2 ? v->crf.c_thresh_baseline : 2;
+    for (size_t k = 0; k < v->n_new_features; k++) {
+      const int fx = v->new_features[2 * k], fy = v->new_features[2 * k + 1];
+      const int r0 = fy - radius > 0 ? fy - radius : 0, r1 = fy + radius < (int)v->h - 1 ? fy + radius : (int)v->h - 1;
+      const int c0 = fx - radius > 0 ? fx - radius : 0, c1 = fx + radius < (int)v->w - 1 ? fx + radius : (int)v->w - 1;
+      for (int row = r0; row <= r1; row++)
+        for (int col = c0; col <= c1; col++)
+          for (int ch = 0; ch < v->c; ch++) v->px[((size_t)row * v->w + col) * v->c + ch].c_thresh = value;
+    }
+  }
+}
+
+/* Video::update_detect_features, video.rs:825-837 (show_features and feature_cluster only affect drawing) */
+void oracle_video_update_detect_features(oracle_video* v, int detect_features, int feature_rate_adjustment) {
+  v->feature_detection = detect_features;
+  v->feature_rate_adjustment = feature_rate_adjustment;
+}
+size_t oracle_video_new_features(const oracle_video* v, uint16_t* xy_out, size_t cap) {
+  const size_t n = v->n_new_features < cap ? v->n_new_features : cap;
+  if (n) memcpy(xy_out, v->new_features, n * 2 * sizeof(uint16_t));
+  return v->n_new_features;
+}
+const uint8_t* oracle_video_feature_mask(const oracle_video* v) { return v->feature_mask; }
+
 /* Video::integrate_matrix, video.rs:651-778 (up to and including the parallel section) */
 size_t oracle_video_integrate_matrix(oracle_video* v, const uint8_t* frame, float time_spanned, int n_threads) {
   if (v->in_interval_count == 0) set_initial_d(v, frame);
@@ -724,6 +855,7 @@ size_t oracle_video_integrate_matrix(oracle_video* v, const uint8_t* frame, floa
   v->live_exit = live_exit;
   v->max_live = max_live;
   v->max_px_events = max_px_events;
+  handle_features(v); /* video.rs:744 (after the parallel section and the encoder loop) */
   size_t total = 0;
   for (uint32_t ci = 0; ci < v->n_chunks; ci++) total += v->chunks[ci].len;
   return total;

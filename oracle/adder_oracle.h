@@ -138,6 +138,16 @@ const oracle_px* oracle_video_px(const oracle_video* v, size_t index);
 
 int oracle_max_threads(void);
 
+/* ---- feature detection inside integrate_matrix ---------------------------
+ * is_feature, utils/cv.rs:22-212 (FAST 9_16 on channel 0; parity UNPINNED by reference tests — none exist;
+ * tests/test_features_cpu.py compares it with OpenCV's FAST, of which the reference says it is a port). */
+int oracle_is_feature(const uint8_t* img, uint16_t w, uint16_t h, uint8_t channels, uint16_t x, uint16_t y, uint8_t c);
+/* Video::update_detect_features, video.rs:825-837; handle_features (:883-1113) then runs at the end of every
+ * integrate_matrix: feature sets per chunk, newly found features, c_thresh reset around them (:1077-1104). */
+void oracle_video_update_detect_features(oracle_video* v, int detect_features, int feature_rate_adjustment);
+size_t oracle_video_new_features(const oracle_video* v, uint16_t* xy_out, size_t cap);
+const uint8_t* oracle_video_feature_mask(const oracle_video* v);
+
 /* handle_color, adder-codec-rs/src/utils/cv.rs:215-232: (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in f64,
  * evaluated left to right, truncating and saturating.  rgb: n_px * 3 bytes, out: n_px bytes. */
 void oracle_handle_color(const uint8_t* rgb, size_t n_px, uint8_t* out);

@@ -119,6 +119,14 @@ def lib() -> C.CDLL:
     L.oracle_px_set_d_for_continuous.restype = i32
     L.oracle_px_set_d_for_continuous.argtypes = [C.POINTER(Px), f32, u32, C.POINTER(Event)]
     L.oracle_px_integrate.argtypes = [C.POINTER(Px), f32, f32, i32, u32, u32, u8, u8, i32]
+    L.oracle_is_feature.restype = i32
+    L.oracle_is_feature.argtypes = [C.c_void_p, u16, u16, u8, u16, u16, u8]
+    L.oracle_video_update_detect_features.restype = None
+    L.oracle_video_update_detect_features.argtypes = [vp, i32, i32]
+    L.oracle_video_new_features.restype = C.c_size_t
+    L.oracle_video_new_features.argtypes = [vp, C.c_void_p, C.c_size_t]
+    L.oracle_video_feature_mask.restype = C.POINTER(C.c_uint8)
+    L.oracle_video_feature_mask.argtypes = [vp]
     L.oracle_handle_color.restype = None
     L.oracle_handle_color.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     L.oracle_raw_header.restype = C.c_size_t
@@ -292,6 +300,21 @@ class Video:
         """Same work, events stay in the per-chunk vectors (the timed CPU-baseline form)."""
         return self._L.oracle_video_integrate_matrix(self._v, frame.ctypes.data, time_spanned, n_threads)
 
+    def update_detect_features(self, detect_features: bool, feature_rate_adjustment: bool = False):
+        """video.rs:825-837"""
+        self._L.oracle_video_update_detect_features(self._v, int(detect_features), int(feature_rate_adjustment))
+
+    def new_features(self) -> np.ndarray:
+        """[x, y] of the features newly inserted by the last integrate_matrix, sorted (the reference keeps a HashSet)."""
+        n = self._L.oracle_video_new_features(self._v, None, 0)
+        out = np.empty((n, 2), dtype=np.uint16)
+        if n:
+            self._L.oracle_video_new_features(self._v, out.ctypes.data, n)
+        return out[np.lexsort((out[:, 0], out[:, 1]))] if n else out
+
+    def feature_mask(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self._L.oracle_video_feature_mask(self._v), shape=(self.h * self.w,)).reshape(self.h, self.w).copy()
+
     def running_intensities(self) -> np.ndarray:
         p = self._L.oracle_video_running_intensities(self._v)
         n = self.w * self.h * self.c
@@ -346,4 +369,16 @@ def handle_color(frame: np.ndarray) -> np.ndarray:
     assert frame.shape[-1] == 3
     out = np.empty(frame.shape[:-1] + (1,), dtype=np.uint8)
     lib().oracle_handle_color(frame.ctypes.data, out.size, out.ctypes.data)
+    return out
+
+
+def is_feature_map(img: np.ndarray) -> np.ndarray:
+    """oracle_is_feature at every pixel of an (H, W, C) u8 image -> (H, W) bool."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, c = img.shape
+    L = lib()
+    out = np.zeros((h, w), dtype=bool)
+    for y in range(h):
+        for x in range(w):
+            out[y, x] = bool(L.oracle_is_feature(img.ctypes.data, w, h, c, x, y, 0))
     return out

@@ -42,3 +42,21 @@ def frame(kind: int, seed: int, f: int, w: int, h: int, c: int) -> np.ndarray:
 
 def frames(kind: int, seed: int, f0: int, n: int, w: int, h: int, c: int) -> np.ndarray:
     return np.stack([frame(kind, seed, f0 + k, w, h, c) for k in range(n)])
+
+
+def moving_blocks(seed: int, n: int, w: int, h: int, c: int) -> np.ndarray:
+    """(n, H, W, C) u8: a dim textured background with bright and dark rectangles that drift a pixel per frame —
+    corners come and go, which is what the feature pass of the transcoder reacts to."""
+    rng = np.random.default_rng(seed)
+    bg = rng.integers(60, 90, (h, w, c)).astype(np.int32)
+    rects = [(int(rng.integers(0, w - 12)), int(rng.integers(0, h - 10)), int(rng.integers(6, 12)), int(rng.integers(5, 10)),
+              int(rng.choice([-55, 70, 120])), int(rng.choice([-1, 1])), int(rng.choice([-1, 0, 1]))) for _ in range(max(3, w * h // 900))]
+    out = np.empty((n, h, w, c), dtype=np.uint8)
+    for f in range(n):
+        img = bg.copy()
+        for (x0, y0, rw, rh, dv, vx, vy) in rects:
+            x = (x0 + vx * f) % (w - rw)
+            y = (y0 + vy * f) % (h - rh)
+            img[y:y + rh, x:x + rw] += dv
+        out[f] = np.clip(img + rng.integers(-2, 3, (h, w, c)), 0, 255).astype(np.uint8)
+    return out

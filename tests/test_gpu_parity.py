@@ -372,3 +372,44 @@ def test_raw_adder_file_layout(tmp_path):
     assert np.array_equal(rec["x"], exp["x"]) and np.array_equal(rec["y"], exp["y"])
     assert np.array_equal(rec["d"], exp["d"]) and np.array_equal(rec["t"], exp["t"])
     assert raw[-11:] == O.raw_eof() and wr.n_events == len(exp)
+
+
+@pytest.mark.parametrize("c,adjust,chunk_rows", [(1, True, 1), (3, True, 1), (1, False, 5), (1, True, 64)])
+def test_feature_detection_pass_matches_the_oracle(c, adjust, chunk_rows):
+    """handle_features (video.rs:883-1113) at the end of integrate_matrix: feature sets, newly found features
+    and — with rate adjustment — the c_thresh reset around them, which changes the following frames' events."""
+    w, h, nf = 96, 64, 40
+    frames = synth.moving_blocks(3, nf, w, h, c)
+    gv = A.Video(w, h, c)
+    ov = O.Video(w, h, c, O.MODE_FRAME_PERFECT)
+    n_new = 0
+    for v in (gv, ov):
+        if chunk_rows != 1:
+            v.chunk_rows(chunk_rows)
+        v.update_crf(6)  # baseline 7, max 13, feature radius = 64/25 = 2
+        v.update_detect_features(True, adjust)
+    for f in range(nf):
+        eg, cg = gv.integrate_matrix(frames[f], 255.0)
+        eo, co = ov.integrate_matrix(frames[f], 255.0)
+        assert eg.tobytes() == eo.tobytes(), f"frame {f}"
+        assert np.array_equal(cg, co)
+        assert np.array_equal(gv.new_features(), ov.new_features()), f"frame {f}: new features differ"
+        assert np.array_equal(gv.feature_mask(), ov.feature_mask()), f"frame {f}: feature sets differ"
+        n_new += len(ov.new_features())
+    assert n_new > 20, n_new
+    _assert_state_equal(gv, ov, w * h * c, step=3)
+    # switching detection off stops the pass; the sets stay as they are
+    gv.update_detect_features(False)
+    ov.update_detect_features(False)
+    eg, _ = gv.integrate_matrix(frames[0], 255.0)
+    eo, _ = ov.integrate_matrix(frames[0], 255.0)
+    assert eg.tobytes() == eo.tobytes() and len(gv.new_features()) == 0 == len(ov.new_features())
+
+
+def test_feature_detection_is_refused_on_a_row_band():
+    gv = A.Video(32, 16, 1)
+    gv.set_row_offset(16)
+    gv.update_detect_features(True)
+    with pytest.raises(A.AdderError) as e:
+        gv.integrate_matrix(np.zeros((16, 32, 1), np.uint8), 255.0)
+    assert e.value.code == B.ERR_UNSUPPORTED
