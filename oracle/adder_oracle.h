@@ -148,6 +148,22 @@ void oracle_video_update_detect_features(oracle_video* v, int detect_features, i
 size_t oracle_video_new_features(const oracle_video* v, uint16_t* xy_out, size_t cap);
 const uint8_t* oracle_video_feature_mask(const oracle_video* v);
 
+/* ---- INSTANTANEOUS framer, events -> u8 frames (framer_oracle.c) ----------- */
+typedef struct oracle_framer oracle_framer;
+/* FramerBuilder::new(plane, chunk_rows).codec_version(v, time_mode).time_parameters(tps, ref, dtm, output_fps)
+ * .mode(INSTANTANEOUS).view_mode(..).source(U8, source_camera).buffer_limit(..).finish::<u8>(), driver.rs:36-147, :300-399 */
+oracle_framer* oracle_framer_new(uint16_t w, uint16_t h, uint8_t c, uint32_t chunk_rows, uint8_t codec_version, int time_mode,
+                                 uint32_t tps, uint32_t ref_interval, uint32_t delta_t_max, float output_fps, int view_mode,
+                                 uint32_t source_camera, int64_t buffer_limit);
+void oracle_framer_delete(oracle_framer* f);
+int oracle_framer_ingest_event(oracle_framer* f, adder_event_t e);                       /* driver.rs:437-562 */
+int oracle_framer_ingest_events_events(oracle_framer* f, const adder_event_t* ev, const uint32_t* chunk_counts, uint32_t n_counts); /* :564-626 */
+int oracle_framer_write_multi_frame_bytes(oracle_framer* f, uint8_t* out, size_t cap, size_t* n_bytes); /* :971-982 */
+int oracle_framer_flush_frame_buffer(oracle_framer* f);                                 /* :633-680 */
+int oracle_framer_bad(const oracle_framer* f);
+int64_t oracle_framer_frames_written(const oracle_framer* f);
+uint32_t oracle_framer_tpf(const oracle_framer* f);
+
 /* handle_color, adder-codec-rs/src/utils/cv.rs:215-232: (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in f64,
  * evaluated left to right, truncating and saturating.  rgb: n_px * 3 bytes, out: n_px bytes. */
 void oracle_handle_color(const uint8_t* rgb, size_t n_px, uint8_t* out);

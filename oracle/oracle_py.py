@@ -86,7 +86,7 @@ class CrfParameters(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed recipe (oracle/Makefile)."""
-    src = [os.path.join(_HERE, f) for f in ("adder_oracle.c", "adder_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("adder_oracle.c", "framer_oracle.c", "adder_oracle.h", "Makefile")]
     stale = not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
@@ -127,6 +127,24 @@ def lib() -> C.CDLL:
     L.oracle_video_new_features.argtypes = [vp, C.c_void_p, C.c_size_t]
     L.oracle_video_feature_mask.restype = C.POINTER(C.c_uint8)
     L.oracle_video_feature_mask.argtypes = [vp]
+    i64 = C.c_int64
+    L.oracle_framer_new.restype = vp
+    L.oracle_framer_new.argtypes = [u16, u16, u8, u32, u8, i32, u32, u32, u32, f32, i32, u32, i64]
+    L.oracle_framer_delete.argtypes = [vp]
+    L.oracle_framer_ingest_event.restype = i32
+    L.oracle_framer_ingest_event.argtypes = [vp, Event]
+    L.oracle_framer_ingest_events_events.restype = i32
+    L.oracle_framer_ingest_events_events.argtypes = [vp, C.c_void_p, C.c_void_p, u32]
+    L.oracle_framer_write_multi_frame_bytes.restype = i32
+    L.oracle_framer_write_multi_frame_bytes.argtypes = [vp, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.oracle_framer_flush_frame_buffer.restype = i32
+    L.oracle_framer_flush_frame_buffer.argtypes = [vp]
+    L.oracle_framer_bad.restype = i32
+    L.oracle_framer_bad.argtypes = [vp]
+    L.oracle_framer_frames_written.restype = i64
+    L.oracle_framer_frames_written.argtypes = [vp]
+    L.oracle_framer_tpf.restype = u32
+    L.oracle_framer_tpf.argtypes = [vp]
     L.oracle_handle_color.restype = None
     L.oracle_handle_color.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     L.oracle_raw_header.restype = C.c_size_t
@@ -382,3 +400,55 @@ def is_feature_map(img: np.ndarray) -> np.ndarray:
         for x in range(w):
             out[y, x] = bool(L.oracle_is_feature(img.ctypes.data, w, h, c, x, y, 0))
     return out
+
+
+class Framer:
+    """FrameSequence<u8>, FramerMode::INSTANTANEOUS (framer/driver.rs), built like the reference's FramerBuilder chain."""
+
+    def __init__(self, width, height, channels, chunk_rows, codec_version, time_mode, tps, ref_interval, delta_t_max,
+                 output_fps=None, view_mode=VIEW_INTENSITY, source_camera=0, buffer_limit=None):
+        self._L = lib()
+        self.w, self.h, self.c = width, height, channels
+        self._f = self._L.oracle_framer_new(width, height, channels, chunk_rows, codec_version, time_mode, tps, ref_interval,
+                                            delta_t_max, 0.0 if output_fps is None else output_fps, view_mode, source_camera,
+                                            -1 if buffer_limit is None else buffer_limit)
+        assert self._f
+
+    def __del__(self):
+        try:
+            self._L.oracle_framer_delete(self._f)
+        except Exception:
+            pass
+
+    @property
+    def tpf(self):
+        return self._L.oracle_framer_tpf(self._f)
+
+    @property
+    def frames_written(self):
+        return self._L.oracle_framer_frames_written(self._f)
+
+    @property
+    def bad(self):
+        return bool(self._L.oracle_framer_bad(self._f))
+
+    def ingest_event(self, x, y, c, d, t) -> bool:
+        return bool(self._L.oracle_framer_ingest_event(self._f, Event(x, y, c, d, 0, t)))
+
+    def ingest_events_events(self, events: np.ndarray, chunk_counts: np.ndarray) -> bool:
+        events = np.ascontiguousarray(events)
+        cc = np.ascontiguousarray(chunk_counts, dtype=np.uint32)
+        return bool(self._L.oracle_framer_ingest_events_events(self._f, events.ctypes.data, cc.ctypes.data, len(cc)))
+
+    def write_multi_frame_bytes(self, max_frames=1024) -> np.ndarray:
+        """Pops every filled frame; returns them as (n, H, W, C) u8."""
+        fb = self.w * self.h * self.c
+        out = np.empty(max_frames * fb, dtype=np.uint8)
+        nb = C.c_size_t()
+        n = self._L.oracle_framer_write_multi_frame_bytes(self._f, out.ctypes.data, out.size, C.byref(nb))
+        if n < 0:
+            raise RuntimeError("write_multi_frame_bytes: reference error path (bad fill count / no frame) or buffer too small")
+        return out[: nb.value].reshape(n, self.h, self.w, self.c).copy()
+
+    def flush_frame_buffer(self) -> bool:
+        return bool(self._L.oracle_framer_flush_frame_buffer(self._f))

@@ -88,8 +88,37 @@ def digest():
                "sha256": hashlib.sha256(raw).hexdigest()}, open(os.path.join(HERE, "lake_adder_digest.json"), "w"), indent=1)
 
 
+def framer_goldens():
+    """framer_sample3.npz: the reference's golden pairs for the INSTANTANEOUS framer
+    (tests/integration_tests.rs:818-962): sample_3_{ordered,unordered}.adder (v0 header, 10x5x1, 9-byte events) and the
+    frames both must reconstruct, sample_3.gray (405 frames).  lake_scaled_out.npy: the 11 frames the `dark` test
+    (adder_simulproc.rs:238-263) expects from the lake events already held in lake_events.npz."""
+    out = {}
+    for name in ("ordered", "unordered"):
+        raw = open(os.path.join(REF, f"sample_3_{name}.adder"), "rb").read()
+        assert raw[:5] == b"adder" and raw[5] == 0
+        w, h, tps, ref, dtm = struct.unpack(">HHIII", raw[7:23])
+        assert (w, h, tps, ref, dtm, raw[23], raw[24]) == (10, 5, 300000, 5000, 3000000, 9, 1)
+        body = raw[25:]
+        n = len(body) // 9
+        rec = np.frombuffer(body[: n * 9], dtype=np.dtype([("x", ">u2"), ("y", ">u2"), ("d", "u1"), ("t", ">u4")]))
+        out[f"{name}_x"], out[f"{name}_y"] = rec["x"].astype(np.uint16), rec["y"].astype(np.uint16)
+        out[f"{name}_d"], out[f"{name}_t"] = rec["d"].astype(np.uint8), rec["t"].astype(np.uint32)
+        out[f"{name}_tail"] = np.frombuffer(body[n * 9:], dtype=np.uint8)
+    gray = np.frombuffer(open(os.path.join(REF, "sample_3.gray"), "rb").read(), dtype=np.uint8)
+    assert gray.size == 405 * 50
+    out["gray"] = gray.reshape(405, 5, 10, 1)
+    np.savez_compressed(os.path.join(HERE, "framer_sample3.npz"), **out)
+    lake = np.frombuffer(open(os.path.join(REF, "lake_scaled_out"), "rb").read(), dtype=np.uint8)
+    assert lake.size == 11 * 50 * 200
+    np.save(os.path.join(HERE, "lake_scaled_out.npy"), lake.reshape(11, 50, 200, 1))
+    print("sample_3 events", len(out["ordered_x"]), len(out["unordered_x"]), "tail bytes", len(out["ordered_tail"]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "digest":
         digest()
+    elif len(sys.argv) > 1 and sys.argv[1] == "framer":
+        framer_goldens()
     else:
         sys.exit(main())
