@@ -42,6 +42,9 @@ SYMBOLS = [
     "adder_b200_video_raw_encode_device", "adder_b200_video_integrate_frames_host_raw",
     "adder_b200_video_set_source_channels", "adder_b200_video_input_frame",
     "adder_b200_video_update_detect_features", "adder_b200_video_new_features", "adder_b200_video_feature_mask",
+    "adder_b200_framer_create", "adder_b200_framer_destroy", "adder_b200_framer_ingest_events_device",
+    "adder_b200_framer_ingest_events_host", "adder_b200_framer_write_multi_frame_bytes",
+    "adder_b200_framer_flush_frame_buffer", "adder_b200_framer_state",
 ]
 
 
@@ -157,6 +160,13 @@ def lib() -> C.CDLL:
         "adder_b200_video_update_detect_features": (i32, [vp, i32, i32]),
         "adder_b200_video_new_features": (i32, [vp, vp, sz, P(u32)]),
         "adder_b200_video_feature_mask": (i32, [vp, vp]),
+        "adder_b200_framer_create": (i32, [u16, u16, u8, u32, u8, i32, u32, u32, u32, f32, i32, u32, C.c_int64, u32, i32, P(vp)]),
+        "adder_b200_framer_destroy": (None, [vp]),
+        "adder_b200_framer_ingest_events_device": (i32, [vp, vp, vp, P(i32)]),
+        "adder_b200_framer_ingest_events_host": (i32, [vp, vp, vp, P(i32)]),
+        "adder_b200_framer_write_multi_frame_bytes": (i32, [vp, vp, u32, P(u32)]),
+        "adder_b200_framer_flush_frame_buffer": (i32, [vp, P(i32)]),
+        "adder_b200_framer_state": (i32, [vp, P(C.c_int64), P(u32)]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -476,3 +486,80 @@ class Video:
         ms = C.c_float()
         _check(self.L.adder_b200_video_timer_stop(self.v, C.byref(ms)))
         return ms.value
+
+
+class Framer:
+    """Mirrors the reference's FrameSequence<u8> in FramerMode::INSTANTANEOUS (framer/driver.rs) as built by
+    FramerBuilder::new(plane, chunk_rows).codec_version(..).time_parameters(..).mode(INSTANTANEOUS).view_mode(..)
+    .source(U8, source_camera).buffer_limit(..).finish()."""
+
+    def __init__(self, width, height, channels, chunk_rows, codec_version, time_mode, tps, ref_interval, delta_t_max,
+                 output_fps=None, view_mode=VIEW_INTENSITY, source_camera=0, buffer_limit=None, ring_frames=0, device=0):
+        self.L = lib()
+        self.w, self.h, self.c, self.chunk_rows = width, height, channels, chunk_rows
+        self.n_chunks = (height + chunk_rows - 1) // chunk_rows
+        self.f = C.c_void_p()
+        _check(self.L.adder_b200_framer_create(width, height, channels, chunk_rows, codec_version, time_mode, tps, ref_interval,
+                                               delta_t_max, 0.0 if output_fps is None else output_fps, view_mode, source_camera,
+                                               -1 if buffer_limit is None else buffer_limit, ring_frames, device, C.byref(self.f)))
+
+    def close(self):
+        if getattr(self, "f", None):
+            self.L.adder_b200_framer_destroy(self.f)
+            self.f = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _state(self):
+        fw, tpf = C.c_int64(), C.c_uint32()
+        _check(self.L.adder_b200_framer_state(self.f, C.byref(fw), C.byref(tpf)))
+        return fw.value, tpf.value
+
+    @property
+    def frames_written(self):
+        return self._state()[0]
+
+    @property
+    def tpf(self):
+        return self._state()[1]
+
+    def ingest_events_events(self, events: np.ndarray, chunk_counts: np.ndarray) -> bool:
+        """Vec<Vec<Event>> as the concatenated records + per-chunk lengths (host memory)."""
+        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        cc = np.ascontiguousarray(chunk_counts, dtype=np.uint32)
+        assert len(cc) == self.n_chunks and int(cc.sum()) == len(events)
+        ready = C.c_int()
+        _check(self.L.adder_b200_framer_ingest_events_host(self.f, events.ctypes.data if len(events) else None, cc.ctypes.data, C.byref(ready)))
+        return bool(ready.value)
+
+    def ingest_events_device(self, d_events, d_chunk_offsets) -> bool:
+        """The transcoder's device-resident output (records + n_chunks+1 offsets in HBM)."""
+        ready = C.c_int()
+        _check(self.L.adder_b200_framer_ingest_events_device(self.f, d_events, d_chunk_offsets, C.byref(ready)))
+        return bool(ready.value)
+
+    def ingest_event(self, x, y, c, d, t) -> bool:
+        """Framer::ingest_event: one event (driver.rs:437-562)."""
+        ev = np.zeros(1, dtype=EVENT_DTYPE)
+        ev[0] = (x, y, c, d, 0, t)
+        cc = np.zeros(self.n_chunks, dtype=np.uint32)
+        if y // self.chunk_rows < self.n_chunks:
+            cc[y // self.chunk_rows] = 1
+        else:
+            ev = ev[:0]
+        return self.ingest_events_events(ev, cc)
+
+    def write_multi_frame_bytes(self, max_frames=1024) -> np.ndarray:
+        out = np.empty((max_frames, self.h, self.w, self.c), dtype=np.uint8)
+        n = C.c_uint32()
+        _check(self.L.adder_b200_framer_write_multi_frame_bytes(self.f, out.ctypes.data, max_frames, C.byref(n)))
+        return out[: n.value].copy()
+
+    def flush_frame_buffer(self) -> bool:
+        ready = C.c_int()
+        _check(self.L.adder_b200_framer_flush_frame_buffer(self.f, C.byref(ready)))
+        return bool(ready.value)

@@ -19,6 +19,7 @@
 #include "../../include/adder_b200.h"
 #include "px_kernel.cuh"
 #include "feature_kernel.cuh"
+#include "framer_kernel.cuh"
 #include "raw_kernel.cuh"
 #include "synth.cuh"
 
@@ -1195,6 +1196,283 @@ int adder_b200_synth_frames(adder_b200_video* v, uint8_t* d_frames, size_t frame
     v->launches++;
   }
   CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
+}  /* extern "C" */
+
+/* ================================ framer (include/adder_b200.h, framer section) ================================ */
+
+struct adder_b200_framer {
+  uint16_t w = 0, h = 0;
+  uint8_t c = 0;
+  int device = 0;
+  uint32_t chunk_rows = 1, n_chunks = 0;
+  int64_t frames_written = 0;
+  uint32_t tpf = 0, tps = 0, ref_interval = 0, source_dtm = 0, source_camera = 0, ring_frames = 0;
+  uint8_t codec_version = 3;
+  int view_mode = 0, time_mode = 0;
+  int64_t buffer_limit = -1;
+  float practical_d_max = 0.0f;
+  uint64_t frame_px = 0;
+  cudaStream_t stream = nullptr;
+  unsigned long long* d_running_ts = nullptr;
+  long long* d_last_filled = nullptr;
+  uint8_t* d_last_intensity = nullptr;
+  uint8_t *d_ring_val = nullptr, *d_ring_some = nullptr;
+  long long *d_offset_max = nullptr, *d_forced = nullptr;
+  uint8_t *d_tracker = nullptr, *d_status = nullptr;
+  uint32_t *d_result = nullptr, *d_err = nullptr, *d_off_stage = nullptr;
+  adder_event_t* d_ev_stage = nullptr;
+  uint64_t ev_stage_cap = 0;
+  uint8_t* d_out_stage = nullptr;
+  uint32_t out_stage_frames = 0;
+  uint32_t* h_result = nullptr; /* pinned: [0..2] predicates, [3] error word */
+};
+
+namespace {
+
+int framer_set_device(const adder_b200_framer* f) {
+  CU(cudaSetDevice(f->device));
+  return ADDER_OK;
+}
+
+/* status of the front frame -> tracker update (mode) -> predicates on the host */
+int framer_refresh(adder_b200_framer* f, int mode, const uint32_t* d_chunk_off) {
+  const uint64_t chunk_px = (uint64_t)f->chunk_rows * f->w * f->c;
+  adder::framer_chunk_status_kernel<<<f->n_chunks, 256, 0, f->stream>>>(f->d_ring_some, f->ring_frames, f->frame_px, chunk_px, f->d_forced,
+                                                                        f->frames_written, f->d_status);
+  adder::framer_tracker_kernel<<<1, 256, 0, f->stream>>>(f->d_tracker, f->d_status, d_chunk_off, f->n_chunks, mode, f->d_offset_max,
+                                                         f->frames_written, f->buffer_limit, f->d_result);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(f->h_result, f->d_result, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaMemcpyAsync(f->h_result + 3, f->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  if (f->h_result[3]) {
+    CU(cudaMemsetAsync(f->d_err, 0, sizeof(uint32_t), f->stream));
+    return fail(ADDER_ERR_CAPACITY, "an event reaches more than %u output frames ahead of the last one written (create the framer with a larger ring_frames)",
+                f->ring_frames);
+  }
+  return ADDER_OK;
+}
+
+int framer_ingest(adder_b200_framer* f, const adder_event_t* d_events, const uint32_t* d_chunk_off, int* frame_ready) {
+  adder::FramerArgs a{};
+  a.ev_words = reinterpret_cast<const uint32_t*>(d_events);
+  a.chunk_off = d_chunk_off;
+  a.n_chunks = f->n_chunks;
+  a.chunk_rows = f->chunk_rows;
+  a.W = f->w;
+  a.H = f->h;
+  a.C = f->c;
+  a.frames_written = f->frames_written;
+  a.tpf = f->tpf;
+  a.ref_interval = f->ref_interval;
+  a.source_dtm = f->source_dtm;
+  a.codec_version = f->codec_version;
+  a.framed_source = f->source_camera <= 5u ? 1u : 0u; /* FramedU8..FramedF64, lib.rs:35-47 */
+  a.view_mode = (uint32_t)f->view_mode;
+  a.absolute_t = f->time_mode == ADDER_TIME_ABSOLUTE_T ? 1u : 0u;
+  a.practical_d_max = f->practical_d_max;
+  a.buffer_limit = f->buffer_limit;
+  a.running_ts = f->d_running_ts;
+  a.last_filled = f->d_last_filled;
+  a.last_intensity = f->d_last_intensity;
+  a.ring_val = f->d_ring_val;
+  a.ring_some = f->d_ring_some;
+  a.ring_frames = f->ring_frames;
+  a.frame_px = f->frame_px;
+  a.offset_max = f->d_offset_max;
+  a.forced_frame = f->d_forced;
+  a.err = f->d_err;
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device));
+  adder::framer_ingest_kernel<<<sms * 8, 256, 0, f->stream>>>(a);
+  CU(cudaGetLastError());
+  if (int rc = framer_refresh(f, 0, d_chunk_off)) return rc;
+  if (frame_ready) *frame_ready = (int)f->h_result[0];
+  return ADDER_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int adder_b200_framer_create(uint16_t width, uint16_t height, uint8_t channels, uint32_t chunk_rows, uint8_t codec_version, int time_mode,
+                             uint32_t tps, uint32_t ref_interval, uint32_t delta_t_max, float output_fps, int view_mode,
+                             uint32_t source_camera, int64_t buffer_limit, uint32_t ring_frames, int device, adder_b200_framer** out) {
+  return guarded([&]() -> int {
+    if (!out) return fail(ADDER_ERR_BAD_PARAMS, "out is NULL");
+    *out = nullptr;
+    if (!width || !height || !channels || !chunk_rows || !ref_interval) return fail(ADDER_ERR_BAD_PARAMS, "plane, chunk_rows and ref_interval must be non-zero");
+    if (view_mode < 0 || view_mode > ADDER_VIEW_SAE || time_mode < 0 || time_mode > ADDER_TIME_MIXED) return fail(ADDER_ERR_BAD_PARAMS, "unknown mode");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(ADDER_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(ADDER_ERR_BAD_PARAMS, "device %d out of range", device);
+    adder_b200_framer* f = new adder_b200_framer();
+    f->w = width;
+    f->h = height;
+    f->c = channels;
+    f->device = device;
+    f->chunk_rows = chunk_rows;
+    f->n_chunks = (height + chunk_rows - 1) / chunk_rows;
+    f->tpf = output_fps > 0.0f ? (uint32_t)((float)tps / output_fps) : ref_interval; /* driver.rs:355-359 */
+    if (f->tpf == 0) {
+      delete f;
+      return fail(ADDER_ERR_BAD_PARAMS, "ticks per output frame would be 0");
+    }
+    f->tps = tps;
+    f->ref_interval = ref_interval;
+    f->source_dtm = delta_t_max;
+    f->codec_version = codec_version;
+    f->source_camera = source_camera;
+    f->view_mode = view_mode;
+    f->time_mode = time_mode;
+    f->buffer_limit = buffer_limit;
+    f->practical_d_max = log2_raw(255.0f * (float)(delta_t_max / ref_interval)); /* driver.rs:1020-1021, u8::max_f32() = 255 */
+    f->frame_px = (uint64_t)width * height * channels;
+    /* a lagging pixel can hold the front frame back by delta_t_max while its neighbours run delta_t_max ahead */
+    f->ring_frames = ring_frames ? ring_frames : 4u * (delta_t_max / f->tpf) + 64u;
+    auto build = [&]() -> int {
+      CU(cudaSetDevice(device));
+      CU(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+      const uint64_t P = f->frame_px;
+      CU(cudaMalloc(&f->d_running_ts, P * sizeof(unsigned long long)));
+      CU(cudaMalloc(&f->d_last_filled, P * sizeof(long long)));
+      CU(cudaMalloc(&f->d_last_intensity, P));
+      CU(cudaMalloc(&f->d_ring_val, P * f->ring_frames));
+      CU(cudaMalloc(&f->d_ring_some, P * f->ring_frames));
+      CU(cudaMalloc(&f->d_offset_max, f->n_chunks * sizeof(long long)));
+      CU(cudaMalloc(&f->d_forced, f->n_chunks * sizeof(long long)));
+      CU(cudaMalloc(&f->d_tracker, f->n_chunks));
+      CU(cudaMalloc(&f->d_status, f->n_chunks));
+      CU(cudaMalloc(&f->d_result, 4 * sizeof(uint32_t)));
+      CU(cudaMalloc(&f->d_err, sizeof(uint32_t)));
+      CU(cudaMalloc(&f->d_off_stage, ((size_t)f->n_chunks + 1) * sizeof(uint32_t)));
+      CU(cudaHostAlloc(&f->h_result, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+      CU(cudaMemsetAsync(f->d_running_ts, 0, P * sizeof(unsigned long long), f->stream));
+      CU(cudaMemsetAsync(f->d_last_intensity, 0, P, f->stream));
+      CU(cudaMemsetAsync(f->d_ring_val, 0, P * f->ring_frames, f->stream));
+      CU(cudaMemsetAsync(f->d_ring_some, 0, P * f->ring_frames, f->stream));
+      CU(cudaMemsetAsync(f->d_tracker, 0, f->n_chunks, f->stream));
+      CU(cudaMemsetAsync(f->d_err, 0, sizeof(uint32_t), f->stream));
+      const uint64_t nn = std::max<uint64_t>(P, f->n_chunks);
+      adder::framer_init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, f->stream>>>(f->d_last_filled, P, f->d_offset_max, f->d_forced, f->n_chunks);
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(f->stream));
+      return ADDER_OK;
+    };
+    if (int rc = build()) {
+      adder_b200_framer_destroy(f);
+      return rc;
+    }
+    *out = f;
+    return ADDER_OK;
+  });
+}
+
+void adder_b200_framer_destroy(adder_b200_framer* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  cudaFree(f->d_running_ts);
+  cudaFree(f->d_last_filled);
+  cudaFree(f->d_last_intensity);
+  cudaFree(f->d_ring_val);
+  cudaFree(f->d_ring_some);
+  cudaFree(f->d_offset_max);
+  cudaFree(f->d_forced);
+  cudaFree(f->d_tracker);
+  cudaFree(f->d_status);
+  cudaFree(f->d_result);
+  cudaFree(f->d_err);
+  cudaFree(f->d_off_stage);
+  cudaFree(f->d_ev_stage);
+  cudaFree(f->d_out_stage);
+  if (f->h_result) cudaFreeHost(f->h_result);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+int adder_b200_framer_ingest_events_device(adder_b200_framer* f, const adder_event_t* d_events, const uint32_t* d_chunk_offsets, int* frame_ready) {
+  return guarded([&]() -> int {
+    if (!f || !d_chunk_offsets) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (int rc = framer_set_device(f)) return rc;
+    return framer_ingest(f, d_events, d_chunk_offsets, frame_ready);
+  });
+}
+
+int adder_b200_framer_ingest_events_host(adder_b200_framer* f, const adder_event_t* events, const uint32_t* chunk_counts, int* frame_ready) {
+  return guarded([&]() -> int {
+    if (!f || !chunk_counts) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (int rc = framer_set_device(f)) return rc;
+    std::vector<uint32_t> off(f->n_chunks + 1u, 0u);
+    for (uint32_t k = 0; k < f->n_chunks; k++) off[k + 1] = off[k] + chunk_counts[k];
+    const uint64_t total = off[f->n_chunks];
+    if (total && !events) return fail(ADDER_ERR_BAD_PARAMS, "events is NULL");
+    if (total > f->ev_stage_cap) {
+      if (f->d_ev_stage) CU(cudaFree(f->d_ev_stage));
+      f->d_ev_stage = nullptr;
+      f->ev_stage_cap = std::max<uint64_t>(total, 4096);
+      CU(cudaMalloc(&f->d_ev_stage, f->ev_stage_cap * sizeof(adder_event_t)));
+    }
+    CU(cudaMemcpyAsync(f->d_off_stage, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, f->stream));
+    if (total) CU(cudaMemcpyAsync(f->d_ev_stage, events, total * sizeof(adder_event_t), cudaMemcpyHostToDevice, f->stream));
+    CU(cudaStreamSynchronize(f->stream)); /* `off` and the caller's buffers may go away */
+    return framer_ingest(f, f->d_ev_stage, f->d_off_stage, frame_ready);
+  });
+}
+
+int adder_b200_framer_write_multi_frame_bytes(adder_b200_framer* f, uint8_t* frames_out, uint32_t max_frames, uint32_t* n_frames) {
+  return guarded([&]() -> int {
+    if (!f || !n_frames || (max_frames && !frames_out)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    *n_frames = 0;
+    if (int rc = framer_set_device(f)) return rc;
+    if (!f->d_out_stage) {
+      f->out_stage_frames = 4;
+      CU(cudaMalloc(&f->d_out_stage, f->frame_px * f->out_stage_frames));
+    }
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device));
+    /* while self.is_frame_filled(0)? { write_frame_bytes } — one frame per pass: the status of the next front frame is only
+     * known once the previous one has been popped */
+    if (int rc = framer_refresh(f, 3, f->d_off_stage)) return rc;
+    while (f->h_result[1] && *n_frames < max_frames) {
+      adder::framer_pop_kernel<<<sms * 4, 256, 0, f->stream>>>(f->d_ring_val, f->d_ring_some, f->ring_frames, f->frame_px, f->frames_written, 1u,
+                                                             f->d_out_stage);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(frames_out + (size_t)*n_frames * f->frame_px, f->d_out_stage, f->frame_px, cudaMemcpyDeviceToHost, f->stream));
+      f->frames_written += 1; /* driver.rs:959 */
+      *n_frames += 1;
+      if (int rc = framer_refresh(f, 1, f->d_off_stage)) return rc; /* pop_next_frame_for_chunk :923-924 */
+    }
+    return ADDER_OK;
+  });
+}
+
+int adder_b200_framer_flush_frame_buffer(adder_b200_framer* f, int* frame_ready) {
+  return guarded([&]() -> int {
+    if (!f) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+    if (int rc = framer_set_device(f)) return rc;
+    if (int rc = framer_refresh(f, 3, f->d_off_stage)) return rc; /* query: does any chunk hold more than one frame? */
+    if (f->h_result[2]) {
+      int sms = 0;
+      CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device));
+      adder::framer_flush_kernel<<<sms * 4, 256, 0, f->stream>>>(f->d_ring_val, f->d_ring_some, f->ring_frames, f->frame_px, f->frames_written,
+                                                               f->d_last_intensity, f->d_last_filled);
+      CU(cudaGetLastError());
+    }
+    if (int rc = framer_refresh(f, 2, f->d_off_stage)) return rc;
+    if (frame_ready) *frame_ready = (int)f->h_result[0];
+    return ADDER_OK;
+  });
+}
+
+int adder_b200_framer_state(const adder_b200_framer* f, int64_t* frames_written, uint32_t* tpf) {
+  if (!f) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  if (frames_written) *frames_written = f->frames_written;
+  if (tpf) *tpf = f->tpf;
   return ADDER_OK;
 }
 

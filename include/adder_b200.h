@@ -280,6 +280,37 @@ int adder_b200_video_integrate_frames_host_raw(adder_b200_video* v, const uint8_
                                                uint64_t* frame_counts, uint32_t* chunk_counts, uint64_t* n_bytes,
                                                uint32_t* frames_done);
 
+/* ---- INSTANTANEOUS framer: events -> u8 frames (framer/driver.rs; what SimulProcessor runs downstream of
+ * Framed::consume, utils/simulproc.rs:166-218) -------------------------------------------------------------
+ * FramerBuilder::new(plane, chunk_rows).codec_version(v, time_mode).time_parameters(tps, ref, dtm, output_fps)
+ * .mode(INSTANTANEOUS).view_mode(view).source(U8, source_camera).buffer_limit(limit).finish::<u8>()
+ * (driver.rs:36-147, :300-399).  output_fps <= 0 means None (ticks per frame = ref_interval); buffer_limit < 0 means
+ * None.  ring_frames = output frames that can be pending at once (0 = 4 * delta_t_max / tpf + 64; two bytes per pixel-channel each); an event that reaches
+ * further ahead than that is reported as ADDER_ERR_CAPACITY (the reference grows its VecDeque without bound). */
+typedef struct adder_b200_framer adder_b200_framer;
+int adder_b200_framer_create(uint16_t width, uint16_t height, uint8_t channels, uint32_t chunk_rows, uint8_t codec_version,
+                             int time_mode, uint32_t tps, uint32_t ref_interval, uint32_t delta_t_max, float output_fps,
+                             int view_mode, uint32_t source_camera, int64_t buffer_limit, uint32_t ring_frames, int device,
+                             adder_b200_framer** out);
+void adder_b200_framer_destroy(adder_b200_framer* f);
+/* Framer::ingest_events_events (driver.rs:564-626): one Vec<Event> per chunk, given as the records in chunk order
+ * plus n_chunks+1 exclusive offsets — the form adder_b200_video_integrate_frames_device leaves in HBM.  Within one
+ * call a pixel-channel's events must be contiguous (true of the transcoder's stream).  *frame_ready receives
+ * is_frame_0_filled() (driver.rs:851-866). */
+int adder_b200_framer_ingest_events_device(adder_b200_framer* f, const adder_event_t* d_events, const uint32_t* d_chunk_offsets,
+                                           int* frame_ready);
+/* The same from host memory: `events` holds sum(chunk_counts) records, chunk after chunk. */
+int adder_b200_framer_ingest_events_host(adder_b200_framer* f, const adder_event_t* events, const uint32_t* chunk_counts,
+                                         int* frame_ready);
+/* FrameSequence::write_multi_frame_bytes (driver.rs:971-982): pops every frame whose chunks are all filled
+ * (None pixels read as 0), H*W*C bytes each, to frames_out [host]; *n_frames = how many.  With max_frames too
+ * small the remaining filled frames stay queued for the next call. */
+int adder_b200_framer_write_multi_frame_bytes(adder_b200_framer* f, uint8_t* frames_out, uint32_t max_frames, uint32_t* n_frames);
+/* Framer::flush_frame_buffer (driver.rs:633-680). */
+int adder_b200_framer_flush_frame_buffer(adder_b200_framer* f, int* frame_ready);
+/* FrameSequenceState.frames_written and .tpf (driver.rs:232-238). */
+int adder_b200_framer_state(const adder_b200_framer* f, int64_t* frames_written, uint32_t* tpf);
+
 /* Back to the state of a fresh Video::new (video.rs:350-438) with the current parameters kept:
  * what adder-viz does on EOF by rebuilding the source (adder.rs:151-166). */
 int adder_b200_video_reset_state(adder_b200_video* v);
