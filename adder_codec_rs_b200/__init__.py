@@ -29,4 +29,5 @@ from .binding import (  # noqa: F401
     pinned_empty,
     raw_eof,
 )
-from .framed import Framed  # noqa: F401
+from .framed import Framed, RawAdderWriter  # noqa: F401
+from .simulproc import SimulProcessor  # noqa: F401

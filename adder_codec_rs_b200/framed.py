@@ -122,20 +122,25 @@ class Framed:
         return self
 
     # ---- Source, framed.rs:124-186 ----
-    def consume(self) -> List[np.ndarray]:
-        """One input frame -> Vec<Vec<Event>>: a list of n_chunks event arrays (framed.rs:127-157)."""
+    def next_frame(self) -> np.ndarray:
+        """The decode half of consume() (framed.rs:128), with handle_color (:129) routed to the device: returns the
+        frame exactly as the library wants it (three channels when a colour source feeds a gray transcode)."""
         try:
             frame = next(self._it)
         except StopIteration:
             raise NoData("end of input") from None
-        frame = np.asarray(frame, dtype=np.uint8)
+        frame = np.ascontiguousarray(frame, dtype=np.uint8)
         if frame.ndim == 2:
             frame = frame[..., None]
-        # handle_color (framed.rs:129): a colour frame for a gray transcode is folded on the device
         want_src = 3 if (frame.shape[-1] == 3 and not self.color_input) else self.video.c
         if want_src != self.video.src_c:
             self.video.set_source_channels(want_src)
         self._input_frame, self._input_on_device = frame, want_src != self.video.c
+        return frame
+
+    def consume(self) -> List[np.ndarray]:
+        """One input frame -> Vec<Vec<Event>>: a list of n_chunks event arrays (framed.rs:127-157)."""
+        frame = self.next_frame()
         ref_time = self.video.info().ref_time
         events, counts = self.video.integrate_matrix(frame, float(ref_time))
         bounds = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])

@@ -117,3 +117,32 @@ def test_ring_overflow_is_reported():
     with pytest.raises(A.AdderError) as e:
         fr.ingest_event(1, 1, 0xFF, 5, 50000)  # reaches 50 frames ahead
     assert e.value.code == A.binding.ERR_CAPACITY
+
+
+def test_simulproc_mirror_writes_the_oracle_pipeline_frames_and_stream(tmp_path):
+    """Framed -> SimulProcessor.run: reconstructed frames file and raw .adder file against the oracle transcoder + framer
+    + raw encoder driven the same way (colour source, gray transcode, so handle_color is in the loop too)."""
+    import io
+
+    w, h, nf = 48, 20, 45
+    rgb = synth.moving_blocks(9, nf, w, h, 3)
+    src = A.Framed(list(rgb), w, h, color_input=False, source_fps=24.0)
+    src = src.crf(2).auto_time_parameters(255, 255 * 8, None).write_out(A.TIME_ABSOLUTE_T, A.MULTI_COLLAPSE)
+    frames_io, raw_io = io.BytesIO(), io.BytesIO()
+    sp = A.SimulProcessor(src, 255, frames_io, raw_output=raw_io, ring_frames=200)
+    assert sp.run() == nf
+    # the oracle, step by step
+    ov = O.Video(w, h, 1, O.MODE_FRAME_PERFECT)
+    ov.update_crf(2)
+    assert ov.time_parameters(int(255 * 24), 255, 255 * 8, None)
+    ov.write_out(O.TIME_ABSOLUTE_T, O.MULTI_COLLAPSE)
+    of = O.Framer(w, h, 1, 1, 3, O.TIME_ABSOLUTE_T, int(255 * 24), 255, 255 * 8, output_fps=24.0)
+    want_frames, want_raw = b"", O.raw_header(w, h, 1, int(255 * 24), 255, 255 * 8, version=3, time_mode=O.TIME_ABSOLUTE_T)
+    for f in range(nf):
+        eo, co = ov.integrate_matrix(O.handle_color(rgb[f]), 255.0)
+        want_raw += O.raw_encode(eo, 1)
+        if of.ingest_events_events(eo, co):
+            want_frames += of.write_multi_frame_bytes().tobytes()
+    want_raw += O.raw_eof()
+    assert raw_io.getvalue() == want_raw
+    assert frames_io.getvalue() == want_frames and len(want_frames) >= w * h * 3
