@@ -110,7 +110,8 @@ struct adder_b200_video {
 
   uint2* d_hdr = nullptr;
   uint4* d_nodes = nullptr;
-  uint2* d_spill1 = nullptr;
+  uint2* d_park_arena = nullptr; /* [grid][3 park buffers][arena_slots][tile px]: events beyond the shared-memory slots */
+  uint32_t arena_slots = 0;
   uint8_t* d_running = nullptr;
   unsigned long long* d_status = nullptr;
   uint32_t* d_ticket = nullptr;
@@ -178,6 +179,17 @@ int ensure_depth(adder_b200_video* v, uint32_t need) {
   v->d_nodes = nn;
   const bool first = v->depth == 0;
   v->depth = need;
+  { /* a pixel emits at most depth + 2 events in one frame (1 + max(L, 2) + 1): the arena takes what the slots do not */
+    const uint32_t slots = need + 2u - adder::park_slots(v->R);
+    if (v->d_park_arena) {
+      CU(cudaStreamSynchronize(v->stream));
+      CU(cudaFree(v->d_park_arena));
+      v->d_park_arena = nullptr;
+    }
+    const size_t cta_slots = std::max<uint32_t>(v->grid, 1u);
+    CU(cudaMalloc(&v->d_park_arena, cta_slots * adder::kParkBufs * slots * adder::tile_px(v->R) * sizeof(uint2)));
+    v->arena_slots = slots;
+  }
   if (first) {
     adder::init_state_kernel<<<(v->P + 255) / 256, 256, 0, v->stream>>>(v->d_hdr, v->d_nodes, v->d_running, v->P);
     v->launches++;
@@ -305,7 +317,8 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   a.frame = d_frame;
   a.hdr = v->d_hdr;
   a.nodes = v->d_nodes;
-  a.spill1 = v->d_spill1;
+  a.park_arena = v->d_park_arena;
+  a.arena_slots = v->arena_slots;
   a.level_stride = v->Ppad;
   a.running = v->d_running;
   a.ev_words = reinterpret_cast<uint32_t*>(d_events);
@@ -505,7 +518,6 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       CU(cudaEventCreate(&v->ev_t1));
       CU(cudaMalloc(&v->d_hdr, (size_t)v->Ppad * sizeof(uint2)));
       CU(cudaMalloc(&v->d_running, (size_t)v->Ppad));
-      CU(cudaMalloc(&v->d_spill1, (size_t)v->Ppad * sizeof(uint2)));
       CU(cudaMalloc(&v->d_status, (size_t)v->n_tiles * sizeof(unsigned long long)));
       CU(cudaMalloc(&v->d_ticket, sizeof(uint32_t)));
       CU(cudaMalloc(&v->d_err, sizeof(uint32_t)));
@@ -547,7 +559,7 @@ void adder_b200_video_destroy(adder_b200_video* v) {
   cudaFree(v->d_hdr);
   cudaFree(v->d_nodes);
   cudaFree(v->d_running);
-  cudaFree(v->d_spill1);
+  cudaFree(v->d_park_arena);
   cudaFree(v->d_status);
   cudaFree(v->d_ticket);
   cudaFree(v->d_err);

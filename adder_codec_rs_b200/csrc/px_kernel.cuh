@@ -51,7 +51,8 @@ struct FrameArgs {
   const uint8_t* frame; /* P bytes, raster (y,x,c) */
   uint2* hdr;
   uint4* nodes;
-  uint2* spill1;                   /* P entries: a pixel's second event of the frame, when the park has one slot */
+  uint2* park_arena;               /* events beyond the shared-memory slots: [CTA][park buffer][slot][pixel-in-tile] */
+  uint32_t arena_slots;            /* slots per pixel in the arena (allocated node depth + 2 - S covers the worst case) */
   unsigned long long level_stride; /* uint4 elements between levels */
   uint8_t* running;
   uint32_t* ev_words;        /* output records as 3 u32 words each */
@@ -113,30 +114,25 @@ struct GlobalNodes {
 
 /*
  * Where a pixel parks its events until the tile's output offset is known.  The first S go to
- * shared memory ([slot][pixel-in-tile]).  With S = 1 (the large tile) a second event goes to the
- * pixel's entry of a global spill array.  Events beyond that (a deep pop_best in Normal mode, rare)
- * park event #e >= 2 in the pixel's OWN node column at level e: that level is dead by then —
- * pop_best produces event #e at node k >= e, i.e. after level e has been consumed, and after a
- * pop_best only levels 0 and 1 are written again this frame (length becomes 1, at most 2) — so no
- * extra memory is needed and no live state is touched.  Needs e < depth.
+ * shared memory ([slot][pixel-in-tile]); a pixel that emits more (a changed pixel pops its whole
+ * stack: rare on noise, bursts of 3-6 on slowly varying scenes) parks event #e >= S in the CTA's own
+ * arena in global memory, [park buffer][e - S][pixel-in-tile]: written and read back by the same
+ * thread two pipeline iterations apart, coalesced across a warp, never shared between CTAs and never
+ * part of the pixel state (so nothing of a frame is left in state memory once its tile has been computed).
  */
 template <uint32_t S>
 struct EventPark {
-  uint32_t* t;  /* &slot_t[pixel-in-tile] */
-  uint8_t* d;   /* &slot_d[pixel-in-tile] */
-  uint4* col;   /* &nodes[i] */
-  uint2* spill; /* &spill1[i] (S == 1 only) */
-  unsigned long long stride;
-  uint32_t tile_px, depth;
+  uint32_t* t; /* &slot_t[pixel-in-tile] */
+  uint8_t* d;  /* &slot_d[pixel-in-tile] */
+  uint2* ovf;  /* &arena[cta][buffer][0][pixel-in-tile] */
+  uint32_t tile_px, ovf_slots;
   uint32_t n, overflow;
   __device__ __forceinline__ void push(uint32_t dd, uint32_t tt) {
     if (n < S) {
       t[n * tile_px] = tt;
       d[n * tile_px] = (uint8_t)dd;
-    } else if (S == 1u && n == 1u) {
-      *spill = make_uint2(tt, dd);
-    } else if (n < depth) {
-      col[(unsigned long long)n * stride] = make_uint4(tt, dd, 0u, 0u);
+    } else if (n - S < ovf_slots) {
+      ovf[(n - S) * tile_px] = make_uint2(tt, dd);
     } else {
       overflow = 1;
       return;
@@ -147,12 +143,8 @@ struct EventPark {
     if (e < S) {
       tt = t[e * tile_px];
       dd = d[e * tile_px];
-    } else if (S == 1u && e == 1u) {
-      const uint2 v = *spill;
-      tt = v.x;
-      dd = v.y;
     } else {
-      const uint4 v = col[(unsigned long long)e * stride];
+      const uint2 v = ovf[(e - S) * tile_px];
       tt = v.x;
       dd = v.y;
     }
@@ -298,6 +290,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const bool duty = warp < 2u;
+  uint2* const arena = a.park_arena + (unsigned long long)blockIdx.x * kParkBufs * a.arena_slots * TILE; /* this CTA's */
   const uint32_t my_rows = duty ? (uint32_t)R - ADDER_DUTY_LESS : (uint32_t)R;
   const bool frame_aligned = (reinterpret_cast<uintptr_t>(a.frame) & 15u) == 0;
   /* this warp's row of round r, and the tile-relative index of this thread's pixel in it */
@@ -380,7 +373,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         uint32_t nev = 0;
         if (i < a.P) {
           GlobalNodes mem{a.nodes + i, a.level_stride, 1u, 0u};
-          EventPark<S> park{slot_t + q, slot_d + q, a.nodes + i, a.spill1 + i, a.level_stride, TILE, a.px.depth, 0u, 0u};
+          EventPark<S> park{slot_t + q, slot_d + q, arena + (unsigned long long)b * a.arena_slots * TILE + q, TILE, a.arena_slots, 0u, 0u};
           PxHeader h{__uint_as_float(hraw.x), hraw.y};
           const Node n0{__uint_as_float(n0raw.x), __uint_as_float(n0raw.y), __uint_as_float(n0raw.z), n0raw.w};
           const Node n1{__uint_as_float(n1raw.x), __uint_as_float(n1raw.y), __uint_as_float(n1raw.z), n1raw.w};
@@ -541,7 +534,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             c = rem - x * a.C;
           }
           const uint32_t w0 = x | ((y + a.row0) << 16);
-          EventPark<S> park{const_cast<uint32_t*>(pslot_t) + q, const_cast<uint8_t*>(pslot_d) + q, a.nodes + i, a.spill1 + i, a.level_stride, TILE, a.px.depth, nev, 0u};
+          EventPark<S> park{const_cast<uint32_t*>(pslot_t) + q, const_cast<uint8_t*>(pslot_d) + q, arena + (unsigned long long)pb * a.arena_slots * TILE + q, TILE, a.arena_slots, nev, 0u};
 #if ADDER_WO_PIPE
           /* records beyond the shared-memory slot come back from global memory: the read of record
            * e+1 is in flight while record e is stored */
