@@ -86,6 +86,8 @@ uint32_t f32_as_u32(float x) { /* Rust `as u32` */
 }
 
 constexpr int kRing = 3; /* host-form pipeline depth */
+constexpr uint32_t kMaxFramesPerLaunch = adder::kMaxLaunchFrames; /* frames one integrate launch may span */
+constexpr uint32_t kRtSlots = 8;              /* launches whose running_t tables may be in flight before one is reused */
 
 }  // namespace
 
@@ -103,6 +105,11 @@ struct adder_b200_video {
   uint32_t P = 0, n_tiles = 0;   /* n_tiles: tiles of the smallest shape (upper bound, sizes the status array) */
   uint32_t R = 1, n_tiles_r = 0; /* sub-tiles per tile and the number of tiles that goes with it */
   uint32_t grid = 0;             /* persistent CTAs per launch */
+  uint32_t status_ring = 1;      /* frames of status words (power of two) */
+  uint64_t status_words = 0;     /* status_ring * tiles */
+  float* d_running_t[kRtSlots] = {}; /* running_t per frame of a launch (kMaxFramesPerLaunch + 1 floats each) */
+  float* d_rt_cur = nullptr;
+  uint32_t rt_slot = 0;
   bool display_force = true;     /* next frame recomputes every display byte (PxParams::display == 2) */
   uint8_t* d_exact_lut = nullptr; /* [257] display bytes of exactly integral intensities, for lut_ref */
   uint32_t lut_ref = 0;
@@ -295,26 +302,51 @@ uint32_t choose_r(uint32_t P) {
 }
 
 /* Queue one frame on `stream`.  d_frame: P dense bytes on the device. */
-int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_frame, float time_spanned,
-                 adder_event_t* d_events, uint64_t cap, uint32_t* d_chunk_off) {
+/* Queue n_frames consecutive frames (d_frame + f * frame_stride) as ONE launch: frame f's events go to
+ * d_events + f * cap, its chunk offsets to d_chunk_off + f * (n_chunks + 1).  Tickets run frame-major over the
+ * launch; a tile waits for the same tile of the previous frame through the status words, so the tail of one
+ * frame overlaps the head of the next (profiles/r01k_timeline.txt: a third of a single-frame launch is drain). */
+int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_frame, size_t frame_stride, uint32_t n_frames,
+                  float time_spanned, adder_event_t* d_events, uint64_t cap, uint32_t* d_chunk_off) {
   if (v->tree_mode != ADDER_MODE_FRAME_PERFECT)
     return fail(ADDER_ERR_UNSUPPORTED, "Mode::Continuous is not on the framed path (framed.rs:67 always builds FramePerfect)");
+  if (n_frames == 0) return ADDER_OK;
+  if (n_frames > 1 && (v->feature_detection || n_frames > kMaxFramesPerLaunch || (uint64_t)n_frames * v->n_tiles_r >= (1ull << 31)))
+    return fail(ADDER_ERR_INTERNAL, "launch_frames: batch not split by the caller");
   if (int rc = ensure_depth(v, derive_depth(v))) return rc;
 
   if (v->in_interval_count == 0) { /* video.rs:656-658 */
     adder::set_initial_d_kernel<<<(v->P + 255) / 256, 256, 0, stream>>>(v->d_hdr, v->d_nodes, d_frame, v->P);
     v->launches++;
   }
-  v->in_interval_count += 1; /* :662 */
+  v->in_interval_count += n_frames; /* :662, once per frame */
 
-  if (v->epoch == 0x3FFFFFFFu) { /* epoch wrap: forget all status words */
-    CU(cudaMemsetAsync(v->d_status, 0, (size_t)v->n_tiles * sizeof(unsigned long long), stream));
+  if ((uint64_t)v->epoch + n_frames >= 0x3FFFFFF0ull) { /* epoch wrap: forget all status words */
+    CU(cudaMemsetAsync(v->d_status, 0, v->status_words * sizeof(unsigned long long), stream));
     v->epoch = 0;
   }
-  v->epoch += 1;
+  const uint32_t epoch0 = v->epoch + 1u; /* frame f of this launch carries epoch0 + f */
+  v->epoch += n_frames;
+
+  /* running_t before / after every frame of the launch: the same f32 add per frame as event_pixel_tree.rs:337 */
+  {
+    std::vector<float> rt(n_frames + 1u);
+    rt[0] = v->running_t;
+    for (uint32_t f = 0; f < n_frames; f++) rt[f + 1] = rt[f] + time_spanned;
+    float* d_rt = v->d_running_t[v->rt_slot];
+    v->rt_slot = (v->rt_slot + 1u) % kRtSlots;
+    CU(cudaMemcpyAsync(d_rt, rt.data(), rt.size() * sizeof(float), cudaMemcpyHostToDevice, stream)); /* pageable source: staged before the call returns */
+    v->running_t = rt[n_frames];
+    v->d_rt_cur = d_rt;
+  }
 
   adder::FrameArgs a{};
   a.frame = d_frame;
+  a.frame_stride = frame_stride;
+  a.n_frames = n_frames;
+  a.status_ring = v->status_ring;
+  a.running_t = v->d_rt_cur;
+  a.tiles_magic = adder::ref_magic_of(v->n_tiles_r);
   a.hdr = v->d_hdr;
   a.nodes = v->d_nodes;
   a.park_arena = v->d_park_arena;
@@ -344,7 +376,7 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   a.err = v->d_err;
   a.total_events = v->d_total;
   a.ticket_base = v->ticket_base;
-  a.epoch = v->epoch;
+  a.epoch = epoch0;
   a.P = v->P;
   a.n_tiles = v->n_tiles_r;
   a.C = v->c;
@@ -359,9 +391,8 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   adder::PxParams& p = a.px;
   p.depth = v->depth;
   p.time = time_spanned;
-  p.running_t_prev = v->running_t;
-  v->running_t = v->running_t + time_spanned; /* event_pixel_tree.rs:337, the same f32 add for every pixel */
-  p.running_t = v->running_t;
+  p.running_t_prev = 0.0f; /* per frame, from a.running_t[] */
+  p.running_t = 0.0f;
   p.dtm_f = (float)v->delta_t_max;
   p.ref = v->ref_time;
   p.dtm = v->delta_t_max;
@@ -385,9 +416,9 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
   p.exact_lut = v->d_exact_lut;
   p.practical_d_max = log2_raw(255.0f * (float)(v->delta_t_max / v->ref_time)); /* :668-670 */
 
-  v->d_last_input = d_frame;
+  v->d_last_input = d_frame + (size_t)(n_frames - 1u) * frame_stride;
   launch_variant(v, a, stream);
-  v->ticket_base += v->n_tiles_r + v->grid; /* every CTA draws one ticket past the end */
+  v->ticket_base += n_frames * v->n_tiles_r + v->grid; /* every CTA draws one ticket past the end */
   v->launches++;
   CU(cudaGetLastError());
   if (!v->feature_detection && v->d_n_new) CU(cudaMemsetAsync(v->d_n_new, 0, sizeof(uint32_t), stream)); /* this frame found none */
@@ -407,6 +438,11 @@ int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fram
     CU(cudaGetLastError());
   }
   return ADDER_OK;
+}
+
+int launch_frame(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_frame, float time_spanned, adder_event_t* d_events,
+                 uint64_t cap, uint32_t* d_chunk_off) {
+  return launch_frames(v, stream, d_frame, v->P, 1u, time_spanned, d_events, cap, d_chunk_off);
 }
 
 bool rgb_in(const adder_b200_video* v) { return v->src_c == 3 && v->c == 1; }
@@ -518,13 +554,12 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       CU(cudaEventCreate(&v->ev_t1));
       CU(cudaMalloc(&v->d_hdr, (size_t)v->Ppad * sizeof(uint2)));
       CU(cudaMalloc(&v->d_running, (size_t)v->Ppad));
-      CU(cudaMalloc(&v->d_status, (size_t)v->n_tiles * sizeof(unsigned long long)));
+      /* allocated after choose_grid(): see below */
       CU(cudaMalloc(&v->d_ticket, sizeof(uint32_t)));
       CU(cudaMalloc(&v->d_err, sizeof(uint32_t)));
       CU(cudaMalloc(&v->d_total, sizeof(unsigned long long)));
       CU(cudaHostAlloc(&v->h_err, sizeof(uint32_t), cudaHostAllocDefault));
       CU(cudaHostAlloc(&v->h_total, sizeof(unsigned long long), cudaHostAllocDefault));
-      CU(cudaMemsetAsync(v->d_status, 0, (size_t)v->n_tiles * sizeof(unsigned long long), v->stream));
       CU(cudaMemsetAsync(v->d_ticket, 0, sizeof(uint32_t), v->stream));
       CU(cudaMemsetAsync(v->d_err, 0, sizeof(uint32_t), v->stream));
       CU(cudaMemsetAsync(v->d_total, 0, sizeof(unsigned long long), v->stream));
@@ -533,6 +568,17 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       if (int rc = set_smem_attr<4>()) return rc;
       if (int rc = set_smem_attr<8>()) return rc;
       if (int rc = choose_grid(v)) return rc;
+      { /* Status words for as many frames as can be in flight at once: a CTA holds at most three tickets, so the
+         * tickets being worked on span at most 3 * grid / tiles frames; + 3 for the frame being read by look-backs,
+         * the one before it (dependencies) and rounding. */
+        uint32_t need = (3u * v->grid + v->n_tiles_r - 1u) / v->n_tiles_r + 3u, ring = 1u;
+        while (ring < need) ring <<= 1;
+        v->status_ring = ring;
+        v->status_words = (uint64_t)ring * v->n_tiles_r;
+        CU(cudaMalloc(&v->d_status, v->status_words * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(v->d_status, 0, v->status_words * sizeof(unsigned long long), v->stream));
+        for (uint32_t k = 0; k < kRtSlots; k++) CU(cudaMalloc(&v->d_running_t[k], (kMaxFramesPerLaunch + 1u) * sizeof(float)));
+      }
       CU(cudaMalloc(&v->d_exact_lut, 257));
       CU(cudaMalloc(&v->d_counters, 4 * sizeof(unsigned long long)));
       CU(cudaMemsetAsync(v->d_counters, 0, 4 * sizeof(unsigned long long), v->stream));
@@ -560,6 +606,7 @@ void adder_b200_video_destroy(adder_b200_video* v) {
   cudaFree(v->d_nodes);
   cudaFree(v->d_running);
   cudaFree(v->d_park_arena);
+  for (uint32_t k = 0; k < kRtSlots; k++) cudaFree(v->d_running_t[k]);
   cudaFree(v->d_status);
   cudaFree(v->d_ticket);
   cudaFree(v->d_err);
@@ -1081,16 +1128,25 @@ int adder_b200_video_integrate_frames_device(adder_b200_video* v, const uint8_t*
     if (int rc = set_device(v)) return rc;
     if (frame_stride == 0) frame_stride = in_frame_bytes(v);
     if (rgb_in(v) && !v->d_gray) CU(cudaMalloc(&v->d_gray, v->P));
-    for (uint32_t f = 0; f < n_frames; f++) {
+    /* One launch per run of frames when nothing has to happen between frames: no colour conversion into the single
+     * scratch frame, no feature pass, no set_initial_d for the first frame. */
+    const bool per_frame = rgb_in(v) || v->feature_detection;
+    uint32_t f = 0;
+    while (f < n_frames) {
       uint32_t* off = d_chunk_offsets ? d_chunk_offsets + (size_t)f * (v->n_chunks + 1) : nullptr;
       const uint8_t* d_in = d_frames + (size_t)f * frame_stride;
+      uint32_t batch = 1;
       if (rgb_in(v)) { /* one scratch frame: the conversions and the integrate kernels alternate on the stream */
         if (int rc = launch_gray(v, v->stream, d_in, v->d_gray)) return rc;
         d_in = v->d_gray;
+      } else if (!per_frame && v->in_interval_count != 0) {
+        const uint64_t by_tickets = ((1ull << 31) - 1u) / std::max<uint32_t>(v->n_tiles_r, 1u);
+        batch = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(n_frames - f, kMaxFramesPerLaunch), std::max<uint64_t>(by_tickets, 1u));
       }
-      if (int rc = launch_frame(v, v->stream, d_in, time_spanned,
-                                d_events + (size_t)f * events_stride, events_stride, off))
+      if (int rc = launch_frames(v, v->stream, d_in, frame_stride, batch, time_spanned, d_events + (size_t)f * events_stride,
+                                 events_stride, off))
         return rc;
+      f += batch;
     }
     return ADDER_OK;
   });

@@ -47,17 +47,22 @@
 namespace adder {
 
 struct FrameArgs {
-  PxParams px;
-  const uint8_t* frame; /* P bytes, raster (y,x,c) */
+  PxParams px;          /* running_t_prev / running_t / display change per frame: see running_t[] */
+  const uint8_t* frame; /* n_frames frames of P bytes, raster (y,x,c), frame_stride bytes apart */
+  unsigned long long frame_stride;
+  uint32_t n_frames;       /* consecutive frames in this launch: ticket k = frame k / n_tiles, tile k % n_tiles */
+  uint32_t status_ring;    /* frames of status words kept (a power of two) */
+  const float* running_t;  /* n_frames + 1 entries: PixelArena.running_t before frame f and after it (event_pixel_tree.rs:337) */
+  unsigned long long tiles_magic; /* ceil(2^64 / n_tiles), 0 for n_tiles == 1 */
   uint2* hdr;
   uint4* nodes;
   uint2* park_arena;               /* events beyond the shared-memory slots: [CTA][park buffer][slot][pixel-in-tile] */
   uint32_t arena_slots;            /* slots per pixel in the arena (allocated node depth + 2 - S covers the worst case) */
   unsigned long long level_stride; /* uint4 elements between levels */
   uint8_t* running;
-  uint32_t* ev_words;        /* output records as 3 u32 words each */
-  unsigned long long ev_cap; /* records */
-  uint32_t* chunk_off;       /* n_chunks+1 exclusive offsets, or null */
+  uint32_t* ev_words;        /* output records as 3 u32 words each; frame f's start at f * ev_cap records */
+  unsigned long long ev_cap; /* records per frame */
+  uint32_t* chunk_off;       /* n_chunks+1 exclusive offsets per frame, or null */
   unsigned long long* tile_status;
   uint32_t* ticket;
   uint32_t* err;
@@ -81,7 +86,7 @@ struct GlobalNodes {
   uint32_t n_loads, n_stores; /* only read by the counting variant of the kernel */
   __device__ __forceinline__ Node load(uint32_t k) {
     n_loads++;
-    const uint4 v = p[(unsigned long long)k * stride];
+    const uint4 v = __ldcg(p + (unsigned long long)k * stride); /* state is read where it is coherent between SMs: L2 */
     Node n;
     n.integ = __uint_as_float(v.x);
     n.dt = __uint_as_float(v.y);
@@ -151,8 +156,20 @@ struct EventPark {
   }
 };
 
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
-  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+/* A tile's status word is published by ONE thread after it has passed the CTA's rendezvous behind the tile's
+ * state machines: the release at gpu scope is cumulative over what that thread has observed through the
+ * mbarrier, i.e. over every warp's state stores of the tile (the pattern of CUTLASS's Semaphore::release).
+ * The next frame's tile over the same pixels acquires it before its first state load. */
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v, bool release) {
+  if (release)
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  else /* a single-frame launch has no reader of the pixel state inside the launch: the count alone matters */
+    *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+__device__ __forceinline__ unsigned long long ld_status_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
   return *reinterpret_cast<const volatile unsigned long long*>(p);
@@ -207,6 +224,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   } while (!ok);
 }
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kMaxLaunchFrames = 512; /* frames one launch may span (FrameArgs::n_frames) */
 
 /* pull the line holding *p towards L2 (no register, no scoreboard) */
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -222,7 +240,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
  * predecessors back to the first one that already knows its own prefix.  128 predecessors per L2
  * round trip (lane l looks at j-l, j-32-l, j-64-l, j-96-l).
  */
-__device__ __forceinline__ uint32_t look_back(const FrameArgs& a, uint32_t tile, uint32_t lane) {
+__device__ __forceinline__ uint32_t look_back(const unsigned long long* status, uint32_t epoch, uint32_t tile, uint32_t lane) {
   uint32_t excl = 0;
   int j = (int)tile - 1;
   for (;;) {
@@ -236,9 +254,9 @@ __device__ __forceinline__ uint32_t look_back(const FrameArgs& a, uint32_t tile,
         unsigned long long s;
         uint32_t shi;
         do {
-          s = ld_status(&a.tile_status[idx]);
+          s = ld_status(&status[idx]);
           shi = (uint32_t)(s >> 32);
-        } while ((shi >> 2) != a.epoch || (shi & 3u) == 0u);
+        } while ((shi >> 2) != epoch || (shi & 3u) == 0u);
         flag[w] = shi & 3u;
         val[w] = (uint32_t)s;
       }
@@ -287,12 +305,17 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   __shared__ uint32_t s_wtot[kParkBufs][ROWS];
   __shared__ __align__(8) unsigned long long s_bar_a, s_bar_b;
   __shared__ uint8_t s_lut[260];
+  __shared__ float s_running_t[kMaxLaunchFrames + 1]; /* a.running_t[], read once per tile */
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const bool duty = warp < 2u;
   uint2* const arena = a.park_arena + (unsigned long long)blockIdx.x * kParkBufs * a.arena_slots * TILE; /* this CTA's */
   const uint32_t my_rows = duty ? (uint32_t)R - ADDER_DUTY_LESS : (uint32_t)R;
-  const bool frame_aligned = (reinterpret_cast<uintptr_t>(a.frame) & 15u) == 0;
+  const bool frame_aligned = ((reinterpret_cast<uintptr_t>(a.frame) | a.frame_stride) & 15u) == 0;
+  const uint32_t n_total = a.n_frames * a.n_tiles; /* tickets of this launch */
+  /* ticket -> frame (tile = ticket - frame * n_tiles); the frame's row of status words */
+  auto frame_of = [&](uint32_t k) { return a.tiles_magic ? mulhi_u32_u64(k, a.tiles_magic) : k; };
+  auto status_row = [&](uint32_t fi) { return a.tile_status + (unsigned long long)(fi & (a.status_ring - 1u)) * a.n_tiles; };
   /* this warp's row of round r, and the tile-relative index of this thread's pixel in it */
   auto row_of = [&](uint32_t r) { return r + 1u < (uint32_t)R ? 8u * r + warp : 8u * ((uint32_t)R - 1u) + warp - 2u * ADDER_DUTY_LESS; };
 
@@ -301,11 +324,12 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   if (tid == 0) {
     const uint32_t t0 = atomicAdd(a.ticket, 1u) - a.ticket_base;
     s_ticket[0] = t0;
-    s_ticket[1] = t0 < a.n_tiles ? atomicAdd(a.ticket, 1u) - a.ticket_base : kNone;
+    s_ticket[1] = t0 < n_total ? atomicAdd(a.ticket, 1u) - a.ticket_base : kNone;
     mbar_init(&s_bar_a, kWarps);
     mbar_init(&s_bar_b, 2u);
   }
   for (uint32_t j = tid; j < 257u; j += kThreads) s_lut[j] = a.px.exact_lut[j];
+  for (uint32_t j = tid; j <= a.n_frames; j += kThreads) s_running_t[j] = a.running_t[j];
   PxParams px = a.px; /* the display table is read from shared memory */
   px.exact_lut = s_lut;
   __syncthreads();
@@ -314,15 +338,17 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
 
   /* samples of tile t -> this warp's staging area fb (asynchronously when whole and aligned) */
   auto fetch_frame = [&](uint32_t t, uint32_t fb) {
-    const uint32_t start = t * TILE;
+    const uint32_t fi = frame_of(t);
+    const uint32_t start = (t - fi * a.n_tiles) * TILE;
+    const uint8_t* src = a.frame + (unsigned long long)fi * a.frame_stride;
     uint8_t* dst = s_frame + fb * (kThreads * R) + warp * (R * 32u);
     if (start + TILE <= a.P && frame_aligned) {
-      if (lane < 2u * my_rows) cp_async16(dst + lane * 16u, a.frame + start + 32u * row_of(lane >> 1) + (lane & 1u) * 16u);
+      if (lane < 2u * my_rows) cp_async16(dst + lane * 16u, src + start + 32u * row_of(lane >> 1) + (lane & 1u) * 16u);
     } else {
 #pragma unroll 1
       for (uint32_t r = 0; r < my_rows; r++) {
         const uint32_t i = start + 32u * row_of(r) + lane;
-        if (i < a.P) dst[r * 32u + lane] = a.frame[i];
+        if (i < a.P) dst[r * 32u + lane] = src[i];
       }
     }
   };
@@ -332,27 +358,48 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   uint4 n0_next = make_uint4(0u, 0u, 0u, 0u), n1_next = n0_next;
   auto fetch_px = [&](uint32_t i) {
     if (i < a.P) {
-      h_next = a.hdr[i];
-      n0_next = a.nodes[i];
-      n1_next = a.nodes[a.level_stride + i];
+      h_next = __ldcg(a.hdr + i);
+      n0_next = __ldcg(a.nodes + i);
+      n1_next = __ldcg(a.nodes + a.level_stride + i);
     }
   };
-  if (t_cur < a.n_tiles) {
+  /* First state load of tile t.  A launch spans n_frames frames; the tail of one frame overlaps the head of the
+   * next, so the pixels' state of the previous frame must be known to be in place: the same tile of frame f-1
+   * (held by another CTA, or this CTA's own previous tile) must have published its status.  Called after this
+   * warp has arrived at the rendezvous of the current iteration, so a CTA can wait for its own publication.
+   * Frame 0 of a launch follows the previous launch in stream order. */
+  auto fetch_tile_head = [&](uint32_t t) {
+    const uint32_t fi = frame_of(t), tl = t - fi * a.n_tiles;
+    if (fi != 0u) {
+      const unsigned long long* dep = status_row(fi - 1u) + tl;
+      const uint32_t want = a.epoch + fi - 1u;
+      uint32_t shi;
+      do {
+        shi = (uint32_t)(ld_status_acquire(dep) >> 32);
+      } while ((shi >> 2) != want || (shi & 3u) == 0u);
+    }
+    if (my_rows) fetch_px(tl * TILE + 32u * row_of(0u) + lane);
+  };
+  if (t_cur < n_total) {
     fetch_frame(t_cur, 0u);
-    if (my_rows) fetch_px(t_cur * TILE + 32u * row_of(0u) + lane);
+    fetch_tile_head(t_cur);
   }
 
-  while (t_cur < a.n_tiles || t_m1 < a.n_tiles || t_m2 < a.n_tiles) {
-    const bool have_tile = t_cur < a.n_tiles;
+  while (t_cur < n_total || t_m1 < n_total || t_m2 < n_total) {
+    const bool have_tile = t_cur < n_total;
     /* ticket of iteration n+2, requested now and needed after the state machines (drawn only while
      * the previous one was a tile: every CTA draws exactly one ticket past the end, which is what the
      * host advances ticket_base by) */
     uint32_t t_next2 = kNone;
-    if (tid == 0 && s_ticket[(n + 1u) & 1u] < a.n_tiles) t_next2 = atomicAdd(a.ticket, 1u) - a.ticket_base;
+    if (tid == 0 && s_ticket[(n + 1u) & 1u] < n_total) t_next2 = atomicAdd(a.ticket, 1u) - a.ticket_base;
 
     /* ---- stage 1: the state machines of tile n --------------------------------------------------- */
     if (have_tile) {
-      const uint32_t tile_start = t_cur * TILE;
+      const uint32_t fi_cur = frame_of(t_cur);
+      const uint32_t tile_start = (t_cur - fi_cur * a.n_tiles) * TILE;
+      px.running_t_prev = s_running_t[fi_cur];
+      px.running_t = s_running_t[fi_cur + 1u];
+      px.display = fi_cur == 0u ? a.px.display : (a.px.display ? 1u : 0u); /* only the launch's first frame can be a forced one */
       uint32_t* const slot_t = s_slot_t + b * (S * TILE);
       uint8_t* const slot_d = s_slot_d + b * (S * TILE);
       uint16_t* const info = s_info + b * TILE;
@@ -425,7 +472,6 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
     if (lane == 0) mbar_arrive(&s_bar_a); /* this warp's rows of tile n are parked, their totals stored */
     if (duty) {
       mbar_wait(&s_bar_a, n & 1u); /* every row total of tile n is in shared memory */
-      const unsigned long long tag = (unsigned long long)a.epoch << 2;
       if (warp == 0) {
         if (have_tile) {
           /* exclusive scan of the row totals, in pixel order; publish the aggregate */
@@ -454,20 +500,25 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           if (lane == 0) {
             /* tile 0 knows its prefix (0) at once; the others publish their aggregate now and their
              * inclusive prefix after their look-back, one iteration later */
-            st_status(&a.tile_status[t_cur], ((tag | (t_cur == 0u ? kFlagPrefix : kFlagAggregate)) << 32) | tot);
+            const uint32_t fi = frame_of(t_cur), tl = t_cur - fi * a.n_tiles;
+            const unsigned long long tag = (unsigned long long)(a.epoch + fi) << 2;
+            st_status(status_row(fi) + tl, ((tag | (tl == 0u ? kFlagPrefix : kFlagAggregate)) << 32) | tot, a.n_frames > 1u);
             s_tot[b] = tot;
             if (kCount) atomicAdd(&a.counters[3], (unsigned long long)tot);
           }
         }
         if (lane == 0) s_ticket[n & 1u] = t_next2; /* slot (n+2) & 1 */
-      } else if (t_m1 < a.n_tiles) {
-        const uint32_t excl = t_m1 != 0u ? look_back(a, t_m1, lane) : 0u;
+      } else if (t_m1 < n_total) {
+        const uint32_t fi = frame_of(t_m1), tl = t_m1 - fi * a.n_tiles;
+        unsigned long long* const row = status_row(fi);
+        const uint32_t excl = tl != 0u ? look_back(row, a.epoch + fi, tl, lane) : 0u;
         if (lane == 0) {
           const uint32_t incl_all = excl + s_tot[b == 0u ? 2u : b - 1u];
-          if (t_m1 != 0u) st_status(&a.tile_status[t_m1], ((tag | kFlagPrefix) << 32) | incl_all);
+          const unsigned long long tag = (unsigned long long)(a.epoch + fi) << 2;
+          if (tl != 0u) st_status(row + tl, ((tag | kFlagPrefix) << 32) | incl_all, a.n_frames > 1u); /* a dependent may acquire this value instead of the aggregate */
           s_prefix[(n + 1u) & 1u] = excl; /* slot (n-1) & 1 */
-          if (t_m1 == a.n_tiles - 1u) {
-            if (a.chunk_off) a.chunk_off[a.n_chunks] = incl_all;
+          if (tl == a.n_tiles - 1u) {
+            if (a.chunk_off) a.chunk_off[(unsigned long long)fi * (a.n_chunks + 1u) + a.n_chunks] = incl_all;
             if (a.total_events) atomicAdd(a.total_events, (unsigned long long)incl_all);
           }
         }
@@ -478,9 +529,9 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
 
     /* ---- what iteration n+1 will need: its samples and its first row ------------------------------ */
     const uint32_t t_next = s_ticket[(n + 1u) & 1u];
-    if (t_next < a.n_tiles) {
+    if (t_next < n_total) {
       fetch_frame(t_next, (n + 1u) & 1u);
-      const uint32_t i = t_next * TILE + 32u * row_of(0u) + lane;
+      const uint32_t i = (t_next - frame_of(t_next) * a.n_tiles) * TILE + 32u * row_of(0u) + lane;
       if (my_rows && i < a.P) { /* towards L2 now, into registers after the write-out */
         if ((lane & 15u) == 0u) prefetch_l2(a.hdr + i);
         if ((lane & 7u) == 0u) {
@@ -491,15 +542,18 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
     }
 
     /* ---- stage 3: write-out of tile n-2, every thread stores its own pixels' records ------------- */
-    if (t_m2 < a.n_tiles) {
+    if (t_m2 < n_total) {
       const uint32_t pb = b == 2u ? 0u : b + 1u; /* (n-2) % 3 */
       const uint32_t prefix = s_prefix[n & 1u];  /* slot (n-2) & 1 */
-      const uint32_t pstart = t_m2 * TILE;
+      const uint32_t pfi = frame_of(t_m2);
+      const uint32_t pstart = (t_m2 - pfi * a.n_tiles) * TILE;
+      uint32_t* const ev_out = a.ev_words + (unsigned long long)pfi * a.ev_cap * 3ull;
+      uint32_t* const chunk_out = a.chunk_off ? a.chunk_off + (unsigned long long)pfi * (a.n_chunks + 1u) : nullptr;
       const uint32_t* const pslot_t = s_slot_t + pb * (S * TILE);
       const uint8_t* const pslot_d = s_slot_d + pb * (S * TILE);
       const uint16_t* const pinfo = s_info + pb * TILE;
       uint32_t capbits = 0;
-      if (a.chunk_off) { /* lengths of the reference's Vec<Vec<Event>>, video.rs:677-734 */
+      if (chunk_out) { /* lengths of the reference's Vec<Vec<Event>>, video.rs:677-734 */
         if (a.chunk_px >= TILE) { /* at most one chunk starts inside this tile */
           const uint32_t t_end = pstart + TILE - 1u < a.P - 1u ? pstart + TILE - 1u : a.P - 1u;
           const uint32_t ch = a.chunk_magic ? mulhi_u32_u64(t_end, a.chunk_magic) : t_end; /* chunk of the tile's last pixel */
@@ -507,13 +561,13 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           if (cb >= pstart) {
             const uint32_t qq = cb - pstart, row = qq >> 5;
             const uint32_t owner = row < 8u * ((uint32_t)R - 1u) ? (row & 7u) : row - 8u * ((uint32_t)R - 1u) + 2u * ADDER_DUTY_LESS;
-            if (owner * 32u + (qq & 31u) == tid) a.chunk_off[ch] = prefix + s_wtot[pb][row] + (pinfo[qq] & 1023u);
+            if (owner * 32u + (qq & 31u) == tid) chunk_out[ch] = prefix + s_wtot[pb][row] + (pinfo[qq] & 1023u);
           }
         } else {
 #pragma unroll 1
           for (uint32_t r = 0; r < my_rows; r++) {
             const uint32_t row = row_of(r), q = 32u * row + lane, i = pstart + q;
-            if (i < a.P && i % a.chunk_px == 0u) a.chunk_off[i / a.chunk_px] = prefix + s_wtot[pb][row] + (pinfo[q] & 1023u);
+            if (i < a.P && i % a.chunk_px == 0u) chunk_out[i / a.chunk_px] = prefix + s_wtot[pb][row] + (pinfo[q] & 1023u);
           }
         }
       }
@@ -546,7 +600,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             if (e + 1u < nev) park.get(e + 1u, dn, tn);
             const unsigned long long rec = (unsigned long long)first + e;
             if (rec < a.ev_cap) {
-              uint32_t* dst = a.ev_words + rec * 3ull;
+              uint32_t* dst = ev_out + rec * 3ull;
               dst[0] = w0;
               dst[1] = c | (dd << 8);
               dst[2] = tt;
@@ -563,7 +617,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             park.get(e, dd, tt);
             const unsigned long long rec = (unsigned long long)first + e;
             if (rec < a.ev_cap) {
-              uint32_t* dst = a.ev_words + rec * 3ull;
+              uint32_t* dst = ev_out + rec * 3ull;
               dst[0] = w0;
               dst[1] = c | (dd << 8);
               dst[2] = tt;
@@ -577,7 +631,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
       if (capbits) atomicOr(a.err, capbits);
     }
 
-    if (t_next < a.n_tiles && my_rows) fetch_px(t_next * TILE + 32u * row_of(0u) + lane);
+    if (t_next < n_total) fetch_tile_head(t_next);
     t_m2 = t_m1;
     t_m1 = t_cur;
     t_cur = t_next;

@@ -4,7 +4,8 @@
 Workload (BASELINE.json configs[1]): 1920x1080 RGB 8-bit synthetic uniform noise, 300 frames,
 crf 3 (c_thresh baseline 2 / max 7 / velocity 7), ref_time 255, delta_t_max 7650, FramePerfect,
 PixelMultiMode::Collapse, TimeMode::AbsoluteT, chunk_rows 1, fresh pixel state at the start of every
-step.  One step = the whole 300-frame sequence through the hot path (one kernel launch per frame).
+step.  One step = the whole 300-frame sequence through the hot path (adder_b200_video_integrate_frames_device:
+one persistent kernel launch for the 300 frames, the tail of each frame overlapping the head of the next).
 At N GPUs the frame is N row bands of 1080 rows (weak scaling: each rank permanently owns one band's
 state); there is no data-path collective — rank-order concatenation of the bands'
 event streams is the reference's raster order.
@@ -343,11 +344,11 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                         "kernel": "integrate_frame_kernel<8,false>", "algorithmic_bytes_per_launch": alg_bytes_step / NF,
+                         "traffic": ((traffic or {}).get("dram_bytes_per_frame") or 0) * NF or None, "peak_source": peak_src,
+                         "kernel": "integrate_frame_kernel<8,false>", "frames_per_launch": NF, "algorithmic_bytes_per_launch": alg_bytes_step,
                          "algorithmic_bytes_per_px_frame": alg_bytes_step / (P * NF),
                          "node_loads_per_px_frame": cnt["node_loads"] / (P * NF), "node_stores_per_px_frame": cnt["node_stores"] / (P * NF),
-                         "note": "time = CUDA events around the whole timed region on the launching stream (300 integrate launches + 2 reset kernels per step)"},
+                         "note": "one integrate launch spans the step's 300 frames; time = CUDA events around the whole timed region on the launching stream (that launch + 2 reset kernels per step); traffic = ncu dram bytes per frame of a 16-frame launch x 300"},
         }
         # ---- CPU baseline on this box's host cores (bounded sample) -------------------------
         if world == 1 and not args.no_cpu:

@@ -18,6 +18,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 is_bench_workload = "--other" not in sys.argv  # pass --other for captures of workloads that are not bench.py's
+frames_per_launch = int(sys.argv[sys.argv.index("--frames-per-launch") + 1]) if "--frames-per-launch" in sys.argv else 16
 G, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(PR, exist_ok=True)
 
@@ -84,6 +85,7 @@ if os.path.exists(rep):
         iT = hdr.index("gpu__time_duration.sum")
     if is_bench_workload:
       json.dump({"tag": tag, "kernel": rows[2][iN], "dram_bytes_per_launch": sum(traffic) / len(traffic),
+                 "frames_per_launch": frames_per_launch, "dram_bytes_per_frame": sum(traffic) / len(traffic) / frames_per_launch,
                  "launches_captured": len(traffic), "duration_under_ncu": [r[iT] + " " + units[iT] for r in rows[2:]],
                  "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches"},
                 open(os.path.join(PR, "roofline_traffic.json"), "w"), indent=1)

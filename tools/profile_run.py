@@ -19,6 +19,8 @@ ap.add_argument("--crf", type=int, default=3)
 ap.add_argument("--ref", type=int, default=255)
 ap.add_argument("--dtm", type=int, default=7650)
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--batch", action="store_true", help="hand all frames to one integrate_frames_device call (multi-frame launches)")
+ap.add_argument("--cap", type=int, default=4, help="event records per pixel-channel per frame the output buffer holds")
 ap.add_argument("--manual", type=int, default=-1, help="quality_manual(c, c, dtm/ref, 1) instead of crf (BASELINE cfg 3 sweep)")
 ap.add_argument("--normal", action="store_true", help="PixelMultiMode::Normal")
 ap.add_argument("--count", action="store_true", help="one extra untimed pass with the counting twin: algorithmic bytes + roofline fraction")
@@ -39,8 +41,8 @@ if a.normal:
     v.write_out(None, A.MULTI_NORMAL)
 d_frames = v.device_alloc(P * a.frames)
 v.synth_frames(d_frames, 0, a.frames, a.kind, 0xADDE5)
-stride = P * 4
-d_events = v.device_alloc(stride * 12 * 4)
+stride = P * a.cap
+d_events = v.device_alloc(stride * 12 * (a.frames if a.batch else 4))
 v.sync()
 alg = None
 if a.count:
@@ -57,8 +59,11 @@ for rep in range(a.reps):
     v.reset_state()
     quality()
     v.timer_start()
-    for f in range(a.frames):
-        v.integrate_frames_device(d_frames.ptr + f * P, P, 1, float(a.ref), d_events.ptr + (f % 4) * stride * 12, stride, None)
+    if a.batch:
+        v.integrate_frames_device(d_frames.ptr, P, a.frames, float(a.ref), d_events.ptr, stride, None)
+    else:
+        for f in range(a.frames):
+            v.integrate_frames_device(d_frames.ptr + f * P, P, 1, float(a.ref), d_events.ptr + (f % 4) * stride * 12, stride, None)
     ms = v.timer_stop()
     v.sync()
     extra = f", {alg / ms / 1e6:.0f} GB/s = {alg / ms / 1e6 / 6540.2:.3f} of 6540" if alg else ""
