@@ -186,11 +186,6 @@ ADDER_HD uint8_t frame_value_u8(const PxParams& a, uint32_t d, uint32_t t, float
     case 0: { /* Intensity: f64 in the reference */
       if (d >= 128u) return 0; /* D_SHIFT_F64[128] = 0; d >= 129 -> 0 (:262-270) */
       const uint32_t tt = t == 0u ? 1u : t; /* t == 0 -> the intensity is 2^d itself */
-#ifdef ADDER_LUT_SHORTCUT
-      /* the commonest exactly integral case — an event that took exactly one reference interval, e.g. a
-       * fresh node fired by a power-of-two sample: 2^d / ref * ref, straight from the table */
-      if (tt == a.ref && d <= 8u) return a.exact_lut[1u << d];
-#endif
       const float est = rn_mul(fast_div(bits_f((d + 127u) << 23), u2f(tt)), a.tpf_f);
       if (!(est < 256.5f)) return 255; /* also +inf; the exact value is > 256 */
       const uint32_t k = f2u(est);
