@@ -184,6 +184,9 @@ constexpr uint32_t kWarps = kThreads / 32;
  * Warps 0 and 1 carry the CTA's serial work (scan + publish, look-back) and would otherwise finish
  * every iteration last, with the other six waiting for them (profiles/r01d).
  */
+#ifndef ADDER_NAMED_BARS
+#define ADDER_NAMED_BARS 1 /* rendezvous on named barriers (bar.sync parks the warp) instead of polled mbarriers */
+#endif
 #ifndef ADDER_DUTY_LESS
 #define ADDER_DUTY_LESS 1u /* rows fewer for warps 0/1 in the last round (experiments: 0) */
 #endif
@@ -201,7 +204,8 @@ __host__ __device__ constexpr size_t frame_kernel_smem(uint32_t R) {
   return 2u * (size_t)kThreads * R + kParkBufs * ((size_t)park_slots(R) * tile_px(R) * 4u + (size_t)tile_px(R) * 2u + (size_t)park_slots(R) * tile_px(R));
 }
 
-/* mbarriers in shared memory: A = "this warp's state machines of tile n are done" (8 arrivals per
+/* (ADDER_NAMED_BARS=0 only; the default rendezvous is on named barriers, below.)
+ * mbarriers in shared memory: A = "this warp's state machines of tile n are done" (8 arrivals per
  * phase, warps 0/1 wait), B = "serial work of iteration n done" (2 arrivals, the other warps wait for
  * the phase of the PREVIOUS iteration).  Arriving never blocks and waiting does not count as arriving,
  * so a warp waits only for the event it needs — a bar.sync would also make the six plain warps wait
@@ -223,6 +227,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
                  : "memory");
   } while (!ok);
 }
+/* The same two signals on named barriers (ADDER_NAMED_BARS): a warp waiting in bar.sync is parked by the hardware and
+ * issues nothing, while mbarrier.try_wait comes back every ~12 ns (9 % of the kernel's issued instructions were that
+ * spin, profiles/r01m).  A = barrier 1, 256 threads: the six plain warps bar.arrive, warps 0/1 bar.sync.  B = one
+ * barrier per plain warp (its warp number), 96 threads: warps 0/1 bar.arrive on each, the plain warp bar.syncs — with
+ * a single B the plain warps would also wait for each other. */
+__device__ __forceinline__ void nbar_sync(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(uint32_t id, uint32_t count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kMaxLaunchFrames = 512; /* frames one launch may span (FrameArgs::n_frames) */
 
@@ -467,11 +478,24 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
     /* ---- rendezvous + stage 2 (warps 0 and 1): the serial work ------------------------------------ */
     /* The plain warps wait for B(n-1) BEFORE they arrive at A(n): warps 0/1 can then not complete
      * B(n) (which would alias B(n-1)'s parity) while somebody still waits for B(n-1). */
+#if ADDER_NAMED_BARS
+    if (!duty) {
+      if (n != 0u) nbar_sync(warp, 96u); /* serial work of iteration n-1 (signalled a tile ago) */
+      __syncwarp();
+      __threadfence_block();
+      nbar_arrive(1u, 256u); /* this warp's rows of tile n are parked, their totals stored */
+    }
+#else
     if (!duty && n != 0u) mbar_wait(&s_bar_b, (n - 1u) & 1u); /* serial work of iteration n-1 (signalled a tile ago) */
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_bar_a); /* this warp's rows of tile n are parked, their totals stored */
+#endif
     if (duty) {
+#if ADDER_NAMED_BARS
+      nbar_sync(1u, 256u); /* every row total of tile n is in shared memory */
+#else
       mbar_wait(&s_bar_a, n & 1u); /* every row total of tile n is in shared memory */
+#endif
       if (warp == 0) {
         if (have_tile) {
           /* exclusive scan of the row totals, in pixel order; publish the aggregate */
@@ -524,7 +548,13 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         }
       }
       __syncwarp();
+#if ADDER_NAMED_BARS
+      __threadfence_block();
+#pragma unroll
+      for (uint32_t w = 2; w < kWarps; w++) nbar_arrive(w, 96u); /* serial work of iteration n done */
+#else
       if (lane == 0) mbar_arrive(&s_bar_b); /* serial work of iteration n done */
+#endif
     }
 
     /* ---- what iteration n+1 will need: its samples and its first row ------------------------------ */
