@@ -358,9 +358,10 @@ class Video:
         _check(self.L.adder_b200_video_set_counting(self.v, int(on)))
 
     def read_counters(self) -> dict:
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 6)()
         _check(self.L.adder_b200_video_read_counters(self.v, out))
-        return dict(node_loads=out[0], node_stores=out[1], display_writes=out[2], events=out[3])
+        return dict(node_loads=out[0], node_stores=out[1], display_writes=out[2], events=out[3],
+                    live_nodes_in=out[4], live_nodes_out=out[5])
 
     def reset_state(self):
         _check(self.L.adder_b200_video_reset_state(self.v))

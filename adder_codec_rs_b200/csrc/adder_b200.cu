@@ -580,8 +580,8 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
         for (uint32_t k = 0; k < kRtSlots; k++) CU(cudaMalloc(&v->d_running_t[k], (kMaxFramesPerLaunch + 1u) * sizeof(float)));
       }
       CU(cudaMalloc(&v->d_exact_lut, 257));
-      CU(cudaMalloc(&v->d_counters, 4 * sizeof(unsigned long long)));
-      CU(cudaMemsetAsync(v->d_counters, 0, 4 * sizeof(unsigned long long), v->stream));
+      CU(cudaMalloc(&v->d_counters, 6 * sizeof(unsigned long long)));
+      CU(cudaMemsetAsync(v->d_counters, 0, 6 * sizeof(unsigned long long), v->stream));
       if (int rc = realloc_chunks(v)) return rc;
       if (int rc = ensure_depth(v, derive_depth(v))) return rc;
       CU(cudaStreamSynchronize(v->stream));
@@ -819,17 +819,17 @@ int adder_b200_video_set_counting(adder_b200_video* v, int on) {
   if (!v) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
   if (int rc = set_device(v)) return rc;
   v->counting = on != 0;
-  CU(cudaMemsetAsync(v->d_counters, 0, 4 * sizeof(unsigned long long), v->stream));
+  CU(cudaMemsetAsync(v->d_counters, 0, 6 * sizeof(unsigned long long), v->stream));
   return ADDER_OK;
 }
 
-int adder_b200_video_read_counters(adder_b200_video* v, uint64_t out[4]) {
+int adder_b200_video_read_counters(adder_b200_video* v, uint64_t out[6]) {
   if (!v || !out) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
   if (int rc = set_device(v)) return rc;
-  unsigned long long h[4];
+  unsigned long long h[6];
   CU(cudaMemcpyAsync(h, v->d_counters, sizeof(h), cudaMemcpyDeviceToHost, v->stream));
   CU(cudaStreamSynchronize(v->stream));
-  for (int i = 0; i < 4; i++) out[i] = h[i];
+  for (int i = 0; i < 6; i++) out[i] = h[i];
   return ADDER_OK;
 }
 

@@ -73,7 +73,8 @@ struct FrameArgs {
   unsigned long long wc_magic; /* ceil(2^64 / WC), 0 for WC == 1: i / WC without a divide */
   unsigned long long chunk_magic; /* the same for chunk_px */
   uint32_t c_magic;            /* ceil(2^32 / C), unused for C == 1: rem / C for rem < 2^24 */
-  unsigned long long* counters; /* kCount only: [0] node loads [1] node stores [2] display writes [3] events */
+  unsigned long long* counters; /* kCount only: [0] node loads [1] node stores [2] display writes [3] events
+                                  * [4] live nodes at frame entry, summed over px [5] the same at frame exit */
 };
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;
@@ -227,9 +228,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
                  : "memory");
   } while (!ok);
 }
-/* The same two signals on named barriers (ADDER_NAMED_BARS): a warp waiting in bar.sync is parked by the hardware and
- * issues nothing, while mbarrier.try_wait comes back every ~12 ns (9 % of the kernel's issued instructions were that
- * spin, profiles/r01m).  A = barrier 1, 256 threads: the six plain warps bar.arrive, warps 0/1 bar.sync.  B = one
+/* The same two signals on named barriers (ADDER_NAMED_BARS): a warp waiting in bar.sync is parked by the hardware,
+ * while mbarrier.try_wait comes back every ~12 ns (profiles/r01m); the speed is the same, but compute-sanitizer
+ * racecheck models bar.arrive / bar.sync and reports no hazards (profiles/r01o_sanitizer.txt).  A = barrier 1, 256 threads: the six plain warps bar.arrive, warps 0/1 bar.sync.  B = one
  * barrier per plain warp (its warp number), 96 threads: warps 0/1 bar.arrive on each, the plain warp bar.syncs — with
  * a single B the plain warps would also wait for each other. */
 __device__ __forceinline__ void nbar_sync(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
       __syncwarp();
 
       uint32_t errbits = 0;
-      unsigned long long c_loads = 0, c_stores = 0, c_disp = 0;
+      unsigned long long c_loads = 0, c_stores = 0, c_disp = 0, c_len_in = 0, c_len_out = 0;
 #pragma unroll 1
       for (uint32_t r = 0; r < my_rows; r++) {
         const uint32_t row = row_of(r);
@@ -445,6 +446,8 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             c_loads += mem.n_loads;
             c_stores += mem.n_stores;
             c_disp += show ? 1u : 0u;
+            c_len_in += HDR_LENGTH(hraw.y);
+            c_len_out += HDR_LENGTH(h.y);
           }
         }
         /* place of this pixel's records inside its row's run: two ballots cover 0..2 events per
@@ -471,6 +474,8 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         atomicAdd(&a.counters[0], c_loads);
         atomicAdd(&a.counters[1], c_stores);
         atomicAdd(&a.counters[2], c_disp);
+        atomicAdd(&a.counters[4], c_len_in);
+        atomicAdd(&a.counters[5], c_len_out);
       }
       if (errbits) atomicOr(a.err, errbits);
     }

@@ -329,6 +329,15 @@ def run_ours(args):
         # per-GPU achieved bandwidth of the integrate kernel
         achieved = alg_bytes_step * args.steps / (ms * 1e-3) / 1e9
         traffic = ncu_traffic()
+        # SURVEY.md §8(d)'s planning formula on the same run, for comparison: 1 + 2*(12 + 16*L) + 1[display] + 12*E with L the
+        # mean live nodes per px at frame entry and exit, E the events per px-frame (both counted above).  It charges a
+        # 12-byte header and every live node; `achieved` uses the smaller, exactly counted figure.
+        L_mean = (cnt["live_nodes_in"] + cnt["live_nodes_out"]) / (2.0 * P * NF)
+        E_mean = cnt["events"] / (P * NF)
+        b_survey = 1 + 2 * (12 + 16 * L_mean) + 1 + 12 * E_mean
+        survey = {"bytes_per_px_frame": b_survey, "L_mean_live_nodes": L_mean, "E_events_per_px_frame": E_mean,
+                  "achieved": b_survey * P * NF * args.steps / (ms * 1e-3) / 1e9,
+                  "frac": b_survey * P * NF * args.steps / (ms * 1e-3) / 1e9 / peak}
         line = {
             "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -348,6 +357,7 @@ def run_ours(args):
                          "kernel": "integrate_frame_kernel<8,false>", "frames_per_launch": NF, "algorithmic_bytes_per_launch": alg_bytes_step,
                          "algorithmic_bytes_per_px_frame": alg_bytes_step / (P * NF),
                          "node_loads_per_px_frame": cnt["node_loads"] / (P * NF), "node_stores_per_px_frame": cnt["node_stores"] / (P * NF),
+                         "survey_formula": survey,
                          "note": "one integrate launch spans the step's 300 frames; time = CUDA events around the whole timed region on the launching stream (that launch + 2 reset kernels per step); traffic = ncu dram bytes per frame of a 16-frame launch x 300"},
         }
         # ---- CPU baseline on this box's host cores (bounded sample) -------------------------

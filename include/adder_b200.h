@@ -145,10 +145,11 @@ int adder_b200_video_set_in_interval_count(adder_b200_video* v, uint32_t n);
  * bands' streams in band order IS the reference's raster order (video.rs:677-734).  Default 0. */
 int adder_b200_video_set_row_offset(adder_b200_video* v, uint16_t row0);
 /* Measurement aid: while on, frames run through an instrumented twin of the kernel that also counts
- * node loads, node stores, display-byte writes and events (the data-dependent terms of the
- * algorithmic bytes).  Turning it on or off zeroes the counters.  Never on in timed runs. */
+ * [0] node loads, [1] node stores, [2] display-byte writes, [3] events (the data-dependent terms of the
+ * algorithmic bytes) and the live nodes of every pixel at frame [4] entry and [5] exit (the L of
+ * SURVEY.md §8(d)'s formula).  Turning it on or off zeroes the counters.  Never on in timed runs. */
 int adder_b200_video_set_counting(adder_b200_video* v, int on);
-int adder_b200_video_read_counters(adder_b200_video* v, uint64_t out[4]);
+int adder_b200_video_read_counters(adder_b200_video* v, uint64_t out[6]);
 
 /* ---- getters ---------------------------------------------------------------------------------- */
 typedef struct adder_b200_video_info {

@@ -47,12 +47,17 @@ v.sync()
 alg = None
 if a.count:
     v.set_counting(True)
-    for f in range(a.frames):
-        v.integrate_frames_device(d_frames.ptr + f * P, P, 1, float(a.ref), d_events.ptr + (f % 4) * stride * 12, stride, None)
+    if a.batch:
+        v.integrate_frames_device(d_frames.ptr, P, a.frames, float(a.ref), d_events.ptr, stride, None)
+    else:
+        for f in range(a.frames):
+            v.integrate_frames_device(d_frames.ptr + f * P, P, 1, float(a.ref), d_events.ptr + (f % 4) * stride * 12, stride, None)
     v.sync()
     c = v.read_counters()
     v.set_counting(False)
     alg = (1 + 8 + 8) * P * a.frames + 16 * (c["node_loads"] + c["node_stores"]) + c["display_writes"] + 12 * c["events"]
+    Lm = (c["live_nodes_in"] + c["live_nodes_out"]) / (2.0 * P * a.frames)
+    print(f"SURVEY 8(d) formula: L {Lm:.3f} -> {1 + 2 * (12 + 16 * Lm) + 1 + 12 * c['events'] / (P * a.frames):.2f} B/px-frame")
     print(f"counted: {alg / (P * a.frames):.2f} B/px-frame, loads {c['node_loads'] / (P * a.frames):.3f} stores {c['node_stores'] / (P * a.frames):.3f} "
           f"display {c['display_writes'] / (P * a.frames):.3f} events {c['events'] / (P * a.frames):.3f} per px-frame")
 for rep in range(a.reps):
