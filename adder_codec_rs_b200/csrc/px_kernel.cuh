@@ -159,7 +159,7 @@ struct EventPark {
 
 /* A tile's status word is published by ONE thread after it has passed the CTA's rendezvous behind the tile's
  * state machines: the release at gpu scope is cumulative over what that thread has observed through the
- * mbarrier, i.e. over every warp's state stores of the tile (the pattern of CUTLASS's Semaphore::release).
+ * rendezvous (barrier A), i.e. over every warp's state stores of the tile (the pattern of CUTLASS's Semaphore::release).
  * The next frame's tile over the same pixels acquires it before its first state load. */
 __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v, bool release) {
   if (release)
