@@ -243,13 +243,15 @@ template <int R>
 void launch_r(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
   const size_t smem = adder::frame_kernel_smem(R);
   if (v->counting)
-    adder::integrate_frame_kernel<R, true><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
-  else
-    adder::integrate_frame_kernel<R, false><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, true, true><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+  else if (a.n_frames > 1u)
+    adder::integrate_frame_kernel<R, false, true><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+  else /* one frame: the variant compiled without the cross-frame dependency, fences and L2-only state loads */
+    adder::integrate_frame_kernel<R, false, false><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
 }
 template <int R>
 int occupancy_r(int* ctas_per_sm) {
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, adder::integrate_frame_kernel<R, false>, ADDER_TILE_PX,
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, adder::integrate_frame_kernel<R, false, true>, ADDER_TILE_PX,
                                                    adder::frame_kernel_smem(R)));
   return ADDER_OK;
 }
@@ -283,8 +285,9 @@ void launch_variant(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t
 }
 template <int R>
 int set_smem_attr() {
-  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
-  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
   return ADDER_OK;
 }
 /* rounds per tile: 8 (62 rows = 1984 pixels: with one shared-memory park slot per pixel the three park
@@ -329,7 +332,11 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   v->epoch += n_frames;
 
   /* running_t before / after every frame of the launch: the same f32 add per frame as event_pixel_tree.rs:337 */
-  {
+  const float running_t_before = v->running_t;
+  if (n_frames == 1) { /* the two values travel in the kernel arguments: no copy in front of the launch */
+    v->running_t = v->running_t + time_spanned;
+    v->d_rt_cur = nullptr;
+  } else {
     std::vector<float> rt(n_frames + 1u);
     rt[0] = v->running_t;
     for (uint32_t f = 0; f < n_frames; f++) rt[f + 1] = rt[f] + time_spanned;
@@ -391,8 +398,8 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   adder::PxParams& p = a.px;
   p.depth = v->depth;
   p.time = time_spanned;
-  p.running_t_prev = 0.0f; /* per frame, from a.running_t[] */
-  p.running_t = 0.0f;
+  p.running_t_prev = running_t_before; /* read by single-frame launches; the others take both from a.running_t[] */
+  p.running_t = v->running_t;
   p.dtm_f = (float)v->delta_t_max;
   p.ref = v->ref_time;
   p.dtm = v->delta_t_max;

@@ -80,14 +80,20 @@ struct FrameArgs {
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kFlagAggregate = 1u, kFlagPrefix = 2u;
 
-/* level k of pixel i: one 128-bit access, 512 contiguous bytes per warp */
+/* level k of pixel i: one 128-bit access, 512 contiguous bytes per warp.  kCoherent: the launch spans several frames,
+ * so the state a tile reads may have been written by another SM a moment ago — read it where it is coherent (L2). */
+template <bool kCoherent>
+__device__ __forceinline__ uint4 ld_state(const uint4* p) { return kCoherent ? __ldcg(p) : *p; }
+template <bool kCoherent>
+__device__ __forceinline__ uint2 ld_state(const uint2* p) { return kCoherent ? __ldcg(p) : *p; }
+template <bool kCoherent>
 struct GlobalNodes {
   uint4* p; /* &nodes[i] */
   unsigned long long stride;
   uint32_t n_loads, n_stores; /* only read by the counting variant of the kernel */
   __device__ __forceinline__ Node load(uint32_t k) {
     n_loads++;
-    const uint4 v = __ldcg(p + (unsigned long long)k * stride); /* state is read where it is coherent between SMs: L2 */
+    const uint4 v = ld_state<kCoherent>(p + (unsigned long long)k * stride);
     Node n;
     n.integ = __uint_as_float(v.x);
     n.dt = __uint_as_float(v.y);
@@ -302,7 +308,7 @@ __device__ __forceinline__ uint32_t look_back(const unsigned long long* status, 
  * kCount = true is the instrumented twin used (untimed) to measure the algorithmic bytes of a
  * workload: it additionally sums node loads / stores, display writes and events into a.counters.
  */
-template <int R, bool kCount>
+template <int R, bool kCount, bool kMulti>
 __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame_kernel(const FrameArgs a) {
   constexpr uint32_t ROWS = tile_rows(R), TILE = tile_px(R);
   constexpr uint32_t S = park_slots(R);
@@ -324,10 +330,11 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   uint2* const arena = a.park_arena + (unsigned long long)blockIdx.x * kParkBufs * a.arena_slots * TILE; /* this CTA's */
   const uint32_t my_rows = duty ? (uint32_t)R - ADDER_DUTY_LESS : (uint32_t)R;
   const bool frame_aligned = ((reinterpret_cast<uintptr_t>(a.frame) | a.frame_stride) & 15u) == 0;
-  const uint32_t n_total = a.n_frames * a.n_tiles; /* tickets of this launch */
+  const uint32_t n_frames = kMulti ? a.n_frames : 1u; /* kMulti = false: the single-frame form without the cross-frame machinery */
+  const uint32_t n_total = n_frames * a.n_tiles; /* tickets of this launch */
   /* ticket -> frame (tile = ticket - frame * n_tiles); the frame's row of status words */
-  auto frame_of = [&](uint32_t k) { return a.tiles_magic ? mulhi_u32_u64(k, a.tiles_magic) : k; };
-  auto status_row = [&](uint32_t fi) { return a.tile_status + (unsigned long long)(fi & (a.status_ring - 1u)) * a.n_tiles; };
+  auto frame_of = [&](uint32_t k) { return !kMulti ? 0u : a.tiles_magic ? mulhi_u32_u64(k, a.tiles_magic) : k; };
+  auto status_row = [&](uint32_t fi) { return !kMulti ? a.tile_status : a.tile_status + (unsigned long long)(fi & (a.status_ring - 1u)) * a.n_tiles; };
   /* this warp's row of round r, and the tile-relative index of this thread's pixel in it */
   auto row_of = [&](uint32_t r) { return r + 1u < (uint32_t)R ? 8u * r + warp : 8u * ((uint32_t)R - 1u) + warp - 2u * ADDER_DUTY_LESS; };
 
@@ -341,7 +348,12 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
     mbar_init(&s_bar_b, 2u);
   }
   for (uint32_t j = tid; j < 257u; j += kThreads) s_lut[j] = a.px.exact_lut[j];
-  for (uint32_t j = tid; j <= a.n_frames; j += kThreads) s_running_t[j] = a.running_t[j];
+  if (kMulti && a.running_t) {
+    for (uint32_t j = tid; j <= n_frames; j += kThreads) s_running_t[j] = a.running_t[j];
+  } else if (tid == 0) { /* a single frame: both values came with the arguments */
+    s_running_t[0] = a.px.running_t_prev;
+    s_running_t[1] = a.px.running_t;
+  }
   PxParams px = a.px; /* the display table is read from shared memory */
   px.exact_lut = s_lut;
   __syncthreads();
@@ -370,9 +382,9 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   uint4 n0_next = make_uint4(0u, 0u, 0u, 0u), n1_next = n0_next;
   auto fetch_px = [&](uint32_t i) {
     if (i < a.P) {
-      h_next = __ldcg(a.hdr + i);
-      n0_next = __ldcg(a.nodes + i);
-      n1_next = __ldcg(a.nodes + a.level_stride + i);
+      h_next = ld_state<kMulti>(a.hdr + i);
+      n0_next = ld_state<kMulti>(a.nodes + i);
+      n1_next = ld_state<kMulti>(a.nodes + a.level_stride + i);
     }
   };
   /* First state load of tile t.  A launch spans n_frames frames; the tail of one frame overlaps the head of the
@@ -382,7 +394,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
    * Frame 0 of a launch follows the previous launch in stream order. */
   auto fetch_tile_head = [&](uint32_t t) {
     const uint32_t fi = frame_of(t), tl = t - fi * a.n_tiles;
-    if (fi != 0u) {
+    if (kMulti && fi != 0u) {
       const unsigned long long* dep = status_row(fi - 1u) + tl;
       const uint32_t want = a.epoch + fi - 1u;
       uint32_t shi;
@@ -431,7 +443,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         if (r + 1u < my_rows) fetch_px(tile_start + 32u * row_of(r + 1u) + lane);
         uint32_t nev = 0;
         if (i < a.P) {
-          GlobalNodes mem{a.nodes + i, a.level_stride, 1u, 0u};
+          GlobalNodes<kMulti> mem{a.nodes + i, a.level_stride, 1u, 0u};
           EventPark<S> park{slot_t + q, slot_d + q, arena + (unsigned long long)b * a.arena_slots * TILE + q, TILE, a.arena_slots, 0u, 0u};
           PxHeader h{__uint_as_float(hraw.x), hraw.y};
           const Node n0{__uint_as_float(n0raw.x), __uint_as_float(n0raw.y), __uint_as_float(n0raw.z), n0raw.w};
@@ -531,7 +543,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
              * inclusive prefix after their look-back, one iteration later */
             const uint32_t fi = frame_of(t_cur), tl = t_cur - fi * a.n_tiles;
             const unsigned long long tag = (unsigned long long)(a.epoch + fi) << 2;
-            st_status(status_row(fi) + tl, ((tag | (tl == 0u ? kFlagPrefix : kFlagAggregate)) << 32) | tot, a.n_frames > 1u);
+            st_status(status_row(fi) + tl, ((tag | (tl == 0u ? kFlagPrefix : kFlagAggregate)) << 32) | tot, kMulti && n_frames > 1u);
             s_tot[b] = tot;
             if (kCount) atomicAdd(&a.counters[3], (unsigned long long)tot);
           }
@@ -544,7 +556,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         if (lane == 0) {
           const uint32_t incl_all = excl + s_tot[b == 0u ? 2u : b - 1u];
           const unsigned long long tag = (unsigned long long)(a.epoch + fi) << 2;
-          if (tl != 0u) st_status(row + tl, ((tag | kFlagPrefix) << 32) | incl_all, a.n_frames > 1u); /* a dependent may acquire this value instead of the aggregate */
+          if (tl != 0u) st_status(row + tl, ((tag | kFlagPrefix) << 32) | incl_all, kMulti && n_frames > 1u); /* a dependent may acquire this value instead of the aggregate */
           s_prefix[(n + 1u) & 1u] = excl; /* slot (n-1) & 1 */
           if (tl == a.n_tiles - 1u) {
             if (a.chunk_off) a.chunk_off[(unsigned long long)fi * (a.n_chunks + 1u) + a.n_chunks] = incl_all;

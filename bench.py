@@ -354,7 +354,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ((traffic or {}).get("dram_bytes_per_frame") or 0) * NF or None, "peak_source": peak_src,
-                         "kernel": "integrate_frame_kernel<8,false>", "frames_per_launch": NF, "algorithmic_bytes_per_launch": alg_bytes_step,
+                         "kernel": "integrate_frame_kernel<8,false,true>", "frames_per_launch": NF, "algorithmic_bytes_per_launch": alg_bytes_step,
                          "algorithmic_bytes_per_px_frame": alg_bytes_step / (P * NF),
                          "node_loads_per_px_frame": cnt["node_loads"] / (P * NF), "node_stores_per_px_frame": cnt["node_stores"] / (P * NF),
                          "survey_formula": survey,
