@@ -346,9 +346,9 @@ def run_ours(args):
                        "sharding": "row bands, no collective" if world > 1 else "single GPU",
                        "l2": "per-frame working set (state 350 MB + frame + events) exceeds the 126 MB L2; no flush needed",
                        "events_per_step": events_all, "events_per_px_frame": events_all / px_step},
-            "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": P * NF, "d2h_bytes_per_step": int(events_per_step * 12 + (n_chunks + 1) * 4 * NF),
+            "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": P * NF * world, "d2h_bytes_per_step": int(events_all * 12 + (n_chunks + 1) * 4 * NF * world),
                     "steps": e2e_steps, "api": "adder_b200_video_integrate_frames_host, pinned host frames in, all events out to pinned host memory"},
-            "e2e_raw": {"value": px_step / raw_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": P * NF, "d2h_bytes_per_step": int(raw_bytes + (n_chunks + 1) * 4 * NF),
+            "e2e_raw": {"value": px_step / raw_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": P * NF * world, "d2h_bytes_per_step": int((raw_bytes + (n_chunks + 1) * 4 * NF) * world),
                         "steps": 1, "api": "adder_b200_video_integrate_frames_host_raw: the raw .adder stream body (wire records serialised on the device) to pinned host memory"},
             "gpu_launches": launches,
             "clocks": clocks,
