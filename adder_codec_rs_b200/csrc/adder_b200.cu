@@ -859,7 +859,7 @@ int adder_b200_video_get_info(const adder_b200_video* v, adder_b200_video_info_t
   out->crf = v->crf;
   out->max_depth = v->depth;
   out->device = (uint32_t)v->device;
-  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)v->depth * sizeof(uint4)); /* + 8 B/px of event spill scratch */
+  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)v->depth * sizeof(uint4)); /* the park arena is scratch, not state */
   out->events_capacity = v->events_capacity;
   return ADDER_OK;
 }

@@ -202,8 +202,8 @@ constexpr uint32_t kWarps = kThreads / 32;
 #endif
 __host__ __device__ constexpr uint32_t tile_rows(uint32_t R) { return 8u * R - 2u * ADDER_DUTY_LESS; }
 __host__ __device__ constexpr uint32_t tile_px(uint32_t R) { return 32u * tile_rows(R); }
-/* shared-memory slots per pixel: 1 for the large tile (a pixel's second event goes to the global spill
- * array) so that four CTAs with three park buffers each still fit an SM, else 3 */
+/* shared-memory slots per pixel: 1 for the large tile (a pixel's second and later events of a frame go to the
+ * CTA's arena in global memory) so that four CTAs with three park buffers each still fit an SM, else 3 */
 __host__ __device__ constexpr uint32_t park_slots(uint32_t R) { return R >= 8 ? 1u : 3u; }
 constexpr uint32_t kParkBufs = 3;
 __host__ __device__ constexpr size_t frame_kernel_smem(uint32_t R) {

@@ -231,7 +231,7 @@ def test_every_tile_shape(name, r, monkeypatch):
     _assert_state_equal(gv, ov, n, step=max(1, n // 200))
 
 
-def test_many_events_per_pixel_use_the_dead_level_park():
+def test_many_events_per_pixel_go_through_the_park_arena():
     """Normal mode, long integration under a wide threshold, then the threshold drops to 0 over the
     whole plane (the ROI write): every pixel pops a deep stack in one frame — up to 7 events per pixel,
     more than the shared-memory slots hold, 3.7 events per pixel on average in that frame."""
