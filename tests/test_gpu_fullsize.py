@@ -133,3 +133,42 @@ def test_two_bands_equal_the_whole_plane_at_4k():
             nb = int(do.to_host(np.uint32)[-1])
             got.append(de.to_host(A.EVENT_DTYPE, nbytes=nb * 12))
         assert np.concatenate(got).tobytes() == want.tobytes(), f"frame {f}"
+
+
+MULTI = [
+    ("cfg2_1080p_rgb_noise_24_frames", 1920, 1080, 3, synth.NOISE, 24, dict(crf=3)),
+    ("cfg3_4k_gray_jitter_c10_16_frames", 3840, 2160, 1, synth.JITTER, 16, dict(manual=(10, 10, 30, 1))),
+    ("cfg5_8k_gray_static_8_frames", 7680, 4320, 1, synth.STATIC_BLIPS, 8, dict(crf=3, ref=256, dtm=1 << 20)),
+]
+
+
+@pytest.mark.parametrize("spec", MULTI, ids=lambda s: s[0])
+def test_full_size_multi_frame_launch_matches_the_oracle(spec):
+    """All frames through ONE launch (what bench.py times): thousands of tiles per frame, frames overlapping in
+    flight, every frame's stream compared with the oracle run frame by frame."""
+    case = _case(*spec)
+    gv = A.Video(case.w, case.h, case.c)
+    ov = O.Video(case.w, case.h, case.c, O.MODE_FRAME_PERFECT)
+    cases.configure(gv, case)
+    cases.configure(ov, case)
+    P = case.w * case.h * case.c
+    nf = case.n_frames
+    d_frames = gv.device_alloc(P * nf)
+    gv.synth_frames(d_frames, 0, nf, case.kind, case.seed)
+    cap = P * 2
+    d_events = gv.device_alloc(cap * 12 * nf)
+    d_off = gv.device_alloc((gv.n_chunks + 1) * 4 * nf)
+    gv.integrate_frames_device(d_frames.ptr, P, nf, case.time, d_events.ptr, cap, d_off.ptr)
+    gv.sync()
+    offs = d_off.to_host(np.uint32).reshape(nf, gv.n_chunks + 1)
+    nt = O.max_threads()
+    for f in range(nf):
+        frame = d_frames.to_host(nbytes=P, offset=f * P).reshape(case.h, case.w, case.c)
+        eo, co = ov.integrate_matrix(frame, case.time, nt)
+        assert int(offs[f, -1]) == len(eo), f"frame {f}: {int(offs[f, -1])} vs {len(eo)} events"
+        assert np.array_equal(np.diff(offs[f]), co), f"frame {f}: chunk lengths differ"
+        eg = d_events.to_host(A.EVENT_DTYPE, nbytes=len(eo) * 12, offset=f * cap * 12)
+        assert eg.tobytes() == eo.tobytes(), f"frame {f}: event streams differ"
+    assert np.array_equal(gv.running_intensities(), ov.running_intensities())
+    for b in (d_frames, d_events, d_off):
+        b.free()
