@@ -131,13 +131,16 @@ struct adder_b200_video {
   uint8_t* d_frame[kRing] = {nullptr, nullptr, nullptr};
   uint8_t src_c = 0;                                   /* channels of the frames handed in; 0 = the video's own */
   uint8_t* d_rgb[kRing] = {nullptr, nullptr, nullptr}; /* three-channel staging of the host forms (gray transcode of a colour source) */
-  uint8_t* d_gray = nullptr;                           /* the same for the device-resident form */
+  uint8_t* d_gray = nullptr;                           /* the same for the device-resident form: gray_frames frames */
+  uint32_t gray_frames = 0;
+  bool gray_diag_ready = false;
   const uint8_t* d_last_input = nullptr;               /* the (gray) frame the last integrate call worked on */
   /* feature detection (video.rs:202-210) */
   bool feature_detection = false, feature_rate_adjustment = false;
   uint8_t* d_feat_mask = nullptr;  /* (H,W) */
   uint32_t* d_new_xy = nullptr;    /* x | y<<16 of the last frame's new features */
   uint32_t* d_n_new = nullptr;
+  uint8_t *d_new_mask = nullptr, *d_row_hit = nullptr; /* (H,W) each: this frame's new features, and their dilation along rows */
   uint32_t* d_feat_off = nullptr;  /* chunk offsets for frames whose caller did not ask for them */
   uint32_t new_cap = 0;
   adder_event_t* d_events[kRing] = {nullptr, nullptr, nullptr};
@@ -371,6 +374,8 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
       CU(cudaMemsetAsync(v->d_feat_mask, 0, hw, stream));
       CU(cudaMalloc(&v->d_new_xy, (size_t)v->new_cap * sizeof(uint32_t)));
       CU(cudaMalloc(&v->d_n_new, sizeof(uint32_t)));
+      CU(cudaMalloc(&v->d_new_mask, hw));
+      CU(cudaMalloc(&v->d_row_hit, hw));
     }
     if (!d_chunk_off) { /* the feature pass walks the stream chunk by chunk */
       if (!v->d_feat_off) CU(cudaMalloc(&v->d_feat_off, ((size_t)v->h + 1) * sizeof(uint32_t))); /* n_chunks <= h */
@@ -433,14 +438,23 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v->device));
     CU(cudaMemsetAsync(v->d_n_new, 0, sizeof(uint32_t), stream));
+    const bool adjust = v->feature_rate_adjustment && v->crf.feature_c_radius > 0; /* :1089-1104 */
+    if (adjust) CU(cudaMemsetAsync(v->d_new_mask, 0, (size_t)v->w * v->h, stream));
     adder::feature_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_events), d_chunk_off, v->n_chunks, v->chunk_rows,
                                                       v->row0, v->d_running, v->w, v->h, v->c, v->d_feat_mask, v->d_new_xy, v->d_n_new,
-                                                      v->new_cap);
+                                                      v->new_cap, adjust ? v->d_new_mask : nullptr);
     v->launches++;
-    if (v->feature_rate_adjustment && v->crf.feature_c_radius > 0) { /* :1089-1104 */
-      adder::feature_reset_kernel<<<sms * 4, 256, 0, stream>>>(v->d_hdr, v->d_new_xy, v->d_n_new, v->new_cap, v->w, v->h, v->c,
-                                                              (int)v->crf.feature_c_radius, std::min<uint32_t>(v->crf.c_thresh_baseline, 2u));
-      v->launches++;
+    if (adjust) {
+      /* per feature when they are few, by dilation of the new-feature bitmap when they are dense: decided on the
+       * device from the count (ADDER_B200_FEATURE_RESET=dilate|list forces one form, for the tests) */
+      int force = 0;
+      if (const char* e = getenv("ADDER_B200_FEATURE_RESET")) force = !strcmp(e, "dilate") ? 1 : !strcmp(e, "list") ? -1 : 0;
+      const int radius = (int)v->crf.feature_c_radius;
+      const uint32_t value = std::min<uint32_t>(v->crf.c_thresh_baseline, 2u);
+      adder::feature_reset_kernel<<<sms * 4, 256, 0, stream>>>(v->d_hdr, v->d_new_xy, v->d_n_new, v->new_cap, v->w, v->h, v->c, radius, value, force);
+      adder::feature_dilate_rows_kernel<<<sms * 8, 256, 0, stream>>>(v->d_new_mask, v->d_row_hit, v->d_n_new, v->new_cap, v->w, v->h, radius, force);
+      adder::feature_dilate_cols_kernel<<<sms * 8, 256, 0, stream>>>(v->d_hdr, v->d_row_hit, v->d_n_new, v->new_cap, v->w, v->h, v->c, radius, value, force);
+      v->launches += 3;
     }
     CU(cudaGetLastError());
   }
@@ -456,9 +470,16 @@ bool rgb_in(const adder_b200_video* v) { return v->src_c == 3 && v->c == 1; }
 size_t in_frame_bytes(const adder_b200_video* v) { return rgb_in(v) ? (size_t)v->P * 3u : (size_t)v->P; }
 
 /* handle_color on the device (utils/cv.rs:215-232): d_rgb (P*3 bytes) -> d_gray (P bytes) */
-int launch_gray(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_rgb, uint8_t* d_gray) {
-  const uint32_t groups = (v->P + 3u) / 4u;
-  adder::rgb_to_gray_kernel<<<(groups + 255u) / 256u, 256, 0, stream>>>(d_rgb, d_gray, v->P);
+int launch_gray(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_rgb, uint8_t* d_gray, uint32_t n_frames = 1) {
+  if (!v->gray_diag_ready) { /* the table of gray_math.h, once per handle */
+    uint8_t diag[256];
+    adder::build_gray_diag(diag);
+    CU(cudaMemcpyToSymbolAsync(adder::c_gray_diag, diag, sizeof(diag), 0, cudaMemcpyHostToDevice, stream)); /* pageable source: staged before the call returns */
+    v->gray_diag_ready = true;
+  }
+  const uint32_t n_px = v->P * n_frames; /* frames back to back on both sides */
+  const uint32_t groups = (n_px + 3u) / 4u;
+  adder::rgb_to_gray_kernel<<<(groups + 255u) / 256u, 256, 0, stream>>>(d_rgb, d_gray, n_px);
   v->launches++;
   CU(cudaGetLastError());
   return ADDER_OK;
@@ -624,6 +645,8 @@ void adder_b200_video_destroy(adder_b200_video* v) {
   cudaFree(v->d_feat_mask);
   cudaFree(v->d_new_xy);
   cudaFree(v->d_n_new);
+  cudaFree(v->d_new_mask);
+  cudaFree(v->d_row_hit);
   cudaFree(v->d_feat_off);
   if (v->h_err) cudaFreeHost(v->h_err);
   if (v->h_total) cudaFreeHost(v->h_total);
@@ -1134,23 +1157,40 @@ int adder_b200_video_integrate_frames_device(adder_b200_video* v, const uint8_t*
     if (!v || (!d_frames && n_frames) || (!d_events && events_stride)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
     if (int rc = set_device(v)) return rc;
     if (frame_stride == 0) frame_stride = in_frame_bytes(v);
-    if (rgb_in(v) && !v->d_gray) CU(cudaMalloc(&v->d_gray, v->P));
-    /* One launch per run of frames when nothing has to happen between frames: no colour conversion into the single
-     * scratch frame, no feature pass, no set_initial_d for the first frame. */
-    const bool per_frame = rgb_in(v) || v->feature_detection;
+    /* a colour source feeding a gray transcode is converted into a scratch run of gray frames first (up to 512 MB of
+     * them), so that the run still goes through one integrate launch */
+    const uint32_t gray_run = rgb_in(v) ? (uint32_t)std::min<uint64_t>(std::max<uint64_t>((512ull << 20) / v->P, 1u), kMaxFramesPerLaunch) : 0u;
+    if (rgb_in(v) && v->gray_frames < std::min(gray_run, n_frames)) {
+      CU(cudaStreamSynchronize(v->stream)); /* the old scratch may still be read */
+      cudaFree(v->d_gray);
+      v->d_gray = nullptr;
+      v->gray_frames = std::min(gray_run, n_frames);
+      CU(cudaMalloc(&v->d_gray, (size_t)v->P * v->gray_frames));
+    }
+    /* One launch per run of frames when nothing has to happen between frames: no feature pass, no set_initial_d for
+     * the first frame. */
     uint32_t f = 0;
     while (f < n_frames) {
       uint32_t* off = d_chunk_offsets ? d_chunk_offsets + (size_t)f * (v->n_chunks + 1) : nullptr;
       const uint8_t* d_in = d_frames + (size_t)f * frame_stride;
+      size_t in_stride = frame_stride;
       uint32_t batch = 1;
-      if (rgb_in(v)) { /* one scratch frame: the conversions and the integrate kernels alternate on the stream */
-        if (int rc = launch_gray(v, v->stream, d_in, v->d_gray)) return rc;
-        d_in = v->d_gray;
-      } else if (!per_frame && v->in_interval_count != 0) {
+      if (!v->feature_detection && v->in_interval_count != 0) {
         const uint64_t by_tickets = ((1ull << 31) - 1u) / std::max<uint32_t>(v->n_tiles_r, 1u);
         batch = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(n_frames - f, kMaxFramesPerLaunch), std::max<uint64_t>(by_tickets, 1u));
       }
-      if (int rc = launch_frames(v, v->stream, d_in, frame_stride, batch, time_spanned, d_events + (size_t)f * events_stride,
+      if (rgb_in(v)) {
+        batch = std::min(batch, v->gray_frames);
+        if (frame_stride == (size_t)v->P * 3u) {
+          if (int rc = launch_gray(v, v->stream, d_in, v->d_gray, batch)) return rc;
+        } else {
+          for (uint32_t k = 0; k < batch; k++)
+            if (int rc = launch_gray(v, v->stream, d_in + (size_t)k * frame_stride, v->d_gray + (size_t)k * v->P)) return rc;
+        }
+        d_in = v->d_gray;
+        in_stride = v->P;
+      }
+      if (int rc = launch_frames(v, v->stream, d_in, in_stride, batch, time_spanned, d_events + (size_t)f * events_stride,
                                  events_stride, off))
         return rc;
       f += batch;

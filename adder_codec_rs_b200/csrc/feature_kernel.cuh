@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) feature_kernel(const uint32_t* __restrict
                                                       uint32_t n_chunks, uint32_t chunk_rows, uint32_t row0,
                                                       const uint8_t* __restrict__ running, uint32_t W, uint32_t H, uint32_t C,
                                                       uint8_t* __restrict__ mask, uint32_t* __restrict__ new_xy, uint32_t* n_new,
-                                                      uint32_t new_cap) {
+                                                      uint32_t new_cap, uint8_t* __restrict__ new_mask) {
   const uint32_t total = chunk_off[n_chunks];
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
     const uint32_t w0 = ev_words[3ull * j], w1 = ev_words[3ull * j + 1ull];
@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) feature_kernel(const uint32_t* __restrict
     if (is_feature_dev(running, W, H, C, x, y)) {
       if (mask[p] == 0) { /* HashSet::insert returned true: a new feature */
         mask[p] = 1;
+        if (new_mask) new_mask[p] = 1;
         const uint32_t k = atomicAdd(n_new, 1u);
         if (k < new_cap) new_xy[k] = x | (y << 16);
       }
@@ -101,12 +102,23 @@ __global__ void __launch_bounds__(256) feature_kernel(const uint32_t* __restrict
   }
 }
 
+/* The reset of video.rs:1089-1104 costs (2r+1)^2 writes per new feature.  With few features (any real scene) that is
+ * the cheapest form; when features are dense (noise: every seventh pixel) the union of the windows is most of the
+ * plane and is found instead by dilating the bitmap of new features, first along rows, then along columns.  Both
+ * forms are launched; each looks at the count and leaves when it is the other's turn. */
+__device__ __forceinline__ bool reset_by_dilation(uint32_t n, int radius, uint32_t W, uint32_t H, int force) {
+  if (force) return force > 0;
+  const unsigned long long win = (unsigned long long)(2 * radius + 1) * (unsigned long long)(2 * radius + 1);
+  return (unsigned long long)n * win >= 16ull * W * H;
+}
+
 /* c_thresh := value for every pixel-channel within `radius` of each new feature (video.rs:1089-1104).
  * One CTA per feature (grid-stride), threads over the clipped window. */
 __global__ void __launch_bounds__(256) feature_reset_kernel(uint2* __restrict__ hdr, const uint32_t* __restrict__ new_xy,
                                                             const uint32_t* __restrict__ n_new, uint32_t new_cap, uint32_t W, uint32_t H,
-                                                            uint32_t C, int radius, uint32_t value) {
+                                                            uint32_t C, int radius, uint32_t value, int force) {
   const uint32_t n = min(*n_new, new_cap);
+  if (reset_by_dilation(n, radius, W, H, force)) return;
   for (uint32_t k = blockIdx.x; k < n; k += gridDim.x) {
     const int fx = (int)(new_xy[k] & 0xFFFFu), fy = (int)(new_xy[k] >> 16);
     const int r0 = max(fy - radius, 0), r1 = min(fy + radius, (int)H - 1);
@@ -117,6 +129,42 @@ __global__ void __launch_bounds__(256) feature_reset_kernel(uint2* __restrict__ 
       const uint32_t i = (((uint32_t)r0 + ry) * W + (uint32_t)c0) * C + rr;
       const uint32_t y = hdr[i].y;
       hdr[i].y = (y & ~0xFF00u) | (value << 8); /* several features may write the same pixel: the same value */
+    }
+  }
+}
+
+/* dilation, pass 1: new_mask (1 where a feature was inserted this frame) -> row_hit (1 where some new feature of
+ * the same row lies within `radius` columns) */
+__global__ void __launch_bounds__(256) feature_dilate_rows_kernel(const uint8_t* __restrict__ new_mask, uint8_t* __restrict__ row_hit,
+                                                                  const uint32_t* __restrict__ n_new, uint32_t new_cap, uint32_t W, uint32_t H,
+                                                                  int radius, int force) {
+  if (!reset_by_dilation(min(*n_new, new_cap), radius, W, H, force)) return;
+  const uint32_t P = W * H;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    const int y = (int)(p / W), x = (int)(p - (uint32_t)y * W);
+    const int c0 = max(x - radius, 0), c1 = min(x + radius, (int)W - 1);
+    const uint8_t* row = new_mask + (size_t)y * W;
+    uint8_t hit = 0;
+    for (int c = c0; c <= c1 && !hit; c++) hit = row[c];
+    row_hit[p] = hit;
+  }
+}
+/* pass 2: a pixel is reset when some row within `radius` rows has row_hit at its column */
+__global__ void __launch_bounds__(256) feature_dilate_cols_kernel(uint2* __restrict__ hdr, const uint8_t* __restrict__ row_hit,
+                                                                  const uint32_t* __restrict__ n_new, uint32_t new_cap, uint32_t W, uint32_t H,
+                                                                  uint32_t C, int radius, uint32_t value, int force) {
+  if (!reset_by_dilation(min(*n_new, new_cap), radius, W, H, force)) return;
+  const uint32_t P = W * H;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    const int y = (int)(p / W), x = (int)(p - (uint32_t)y * W);
+    const int r0 = max(y - radius, 0), r1 = min(y + radius, (int)H - 1);
+    uint8_t hit = 0;
+    for (int r = r0; r <= r1 && !hit; r++) hit = row_hit[(size_t)r * W + x];
+    if (hit) {
+      for (uint32_t c = 0; c < C; c++) {
+        const uint32_t i = p * C + c;
+        hdr[i].y = (hdr[i].y & ~0xFF00u) | (value << 8);
+      }
     }
   }
 }

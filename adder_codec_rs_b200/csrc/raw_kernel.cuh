@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gray_math.h"
+
 namespace adder {
 
 constexpr uint32_t kRawThreads = 256;
@@ -59,15 +61,11 @@ __global__ void __launch_bounds__(kRawThreads) raw_encode_kernel(const uint32_t*
 
 /*
  * handle_color (adder-codec-rs/src/utils/cv.rs:215-232), the pre-step of Framed::consume for a gray
- * transcode of a colour source (framed.rs:129): gray = (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in
- * f64, left to right, every product and sum rounded on its own (no FMA), truncating and saturating.
+ * transcode of a colour source (framed.rs:129); the arithmetic is in gray_math.h.
  * Four pixels per thread: three 32-bit loads in, one 32-bit store out.
  */
-__device__ __forceinline__ uint32_t gray_of(uint32_t c0, uint32_t c1, uint32_t c2) {
-  const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)c0, 0.114), __dmul_rn((double)c1, 0.587)), __dmul_rn((double)c2, 0.299));
-  const uint32_t u = __double2uint_rz(s);
-  return u > 255u ? 255u : u;
-}
+__constant__ uint8_t c_gray_diag[256]; /* gray_exact_f64(k, k, k), written once per device by the host */
+__device__ __forceinline__ uint32_t gray_of(uint32_t c0, uint32_t c1, uint32_t c2) { return gray_of(c0, c1, c2, c_gray_diag); }
 __global__ void __launch_bounds__(256) rgb_to_gray_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray, uint32_t n_px) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; /* group of four pixels */
   const uint32_t i = q * 4u;

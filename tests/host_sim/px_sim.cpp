@@ -13,6 +13,7 @@
 #define ADDER_HOST_SIM 1
 #include "../../include/adder_b200.h"
 #include "../../adder_codec_rs_b200/csrc/px_machine.cuh"
+#include "../../adder_codec_rs_b200/csrc/gray_math.h"
 
 namespace adder {
 int g_fast_div_ulps = 0;
@@ -130,6 +131,27 @@ uint32_t sim_frame_value_intensity(uint32_t d, uint32_t t, uint32_t ref) {
   adder::build_exact_lut(ref, lut);
   p.exact_lut = lut;
   return adder::frame_value_u8(p, d, t, 0.0f);
+}
+/* gray_math.h: the fixed-point shortcut against the reference's f64 expression over all 2^24 colours;
+ * returns the number of disagreements and how many colours took the shortcut */
+uint64_t sim_gray_check(uint64_t* n_fast) {
+  uint8_t diag[256];
+  adder::build_gray_diag(diag);
+  uint64_t bad = 0, fast = 0;
+  for (uint32_t c0 = 0; c0 < 256u; c0++)
+    for (uint32_t c1 = 0; c1 < 256u; c1++)
+      for (uint32_t c2 = 0; c2 < 256u; c2++) {
+        const uint32_t S = c0 * 1912603u + c1 * 9848226u + c2 * 5016388u, fr = S & 0xFFFFFFu;
+        fast += fr >= 257u && fr <= 0xFFFFFEu;
+        bad += adder::gray_of(c0, c1, c2, diag) != adder::gray_exact_f64(c0, c1, c2);
+      }
+  *n_fast = fast;
+  return bad;
+}
+uint32_t sim_gray_of(uint32_t c0, uint32_t c1, uint32_t c2) {
+  uint8_t diag[256];
+  adder::build_gray_diag(diag);
+  return adder::gray_of(c0, c1, c2, diag);
 }
 void sim_force_display(sim_video* v) { v->force_display = 1; }
 const adder_event_t* sim_events(const sim_video* v) { return v->events.data(); }

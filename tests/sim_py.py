@@ -12,7 +12,8 @@ _SO = os.path.join(_HERE, "libpx_sim.so")
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _DEPS = [os.path.join(_HERE, "px_sim.cpp"),
          os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "px_machine.cuh"),
-         os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "state_layout.h")]
+         os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "state_layout.h"),
+         os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "gray_math.h")]
 _lib = None
 
 
@@ -36,6 +37,10 @@ def lib():
         L.sim_running.argtypes = [vp]
         L.sim_force_display.argtypes = [vp]
         L.sim_set_fast_div_ulps.argtypes = [i32]
+        L.sim_gray_check.restype = C.c_uint64
+        L.sim_gray_check.argtypes = [C.POINTER(C.c_uint64)]
+        L.sim_gray_of.restype = u32
+        L.sim_gray_of.argtypes = [u32, u32, u32]
         L.sim_div_ref.restype = u32
         L.sim_div_ref.argtypes = [u32, u32]
         L.sim_frame_value_intensity.restype = u32

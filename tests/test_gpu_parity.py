@@ -303,7 +303,7 @@ def test_raw_encode_device_resident_events():
 def test_colour_source_gray_transcode_on_device():
     """set_source_channels(3): handle_color (utils/cv.rs:215-232) on the device in front of the integrate
     kernel, through all three forms, against the oracle's handle_color + transcode."""
-    w, h, nf = 52, 21, 12  # odd sizes: the 4-pixel groups of the conversion kernel end ragged
+    w, h, nf = 52, 21, 17  # odd sizes: the 4-pixel groups of the conversion kernel end ragged
     rgb = synth.frames(synth.NOISE, 11, 0, nf, w, h, 3)
     rgb[1] = 255
     rgb[2] = 0
@@ -341,6 +341,21 @@ def test_colour_source_gray_transcode_on_device():
         assert n == len(exp[8 + k])
         assert d_events.to_host(A.EVENT_DTYPE, nbytes=n * 12, offset=k * stride * 12).tobytes() == exp[8 + k].tobytes()
     assert np.array_equal(gv.input_frame(), O.handle_color(rgb[11]))
+    # the same with padded frames (frame_stride > H*W*3): frame-by-frame conversion into the scratch run, one integrate launch
+    pad = stride + 20
+    d_pad = gv.device_alloc(5 * pad)
+    for k in range(5):
+        d_pad.from_host(rgb[12 + k], offset=k * pad)
+    d_events5 = gv.device_alloc(5 * stride * 12)
+    d_off5 = gv.device_alloc(5 * (gv.n_chunks + 1) * 4)
+    gv.integrate_frames_device(d_pad.ptr, pad, 5, 255.0, d_events5.ptr, stride, d_off5.ptr)
+    gv.sync()
+    offs = d_off5.to_host(np.uint32).reshape(5, -1)
+    for k in range(5):
+        n = int(offs[k, -1])
+        assert n == len(exp[12 + k])
+        assert d_events5.to_host(A.EVENT_DTYPE, nbytes=n * 12, offset=k * stride * 12).tobytes() == exp[12 + k].tobytes()
+    assert np.array_equal(gv.input_frame(), O.handle_color(rgb[16]))
     assert np.array_equal(gv.running_intensities(), ov.running_intensities())
 
 
@@ -374,12 +389,21 @@ def test_raw_adder_file_layout(tmp_path):
     assert raw[-11:] == O.raw_eof() and wr.n_events == len(exp)
 
 
-@pytest.mark.parametrize("c,adjust,chunk_rows", [(1, True, 1), (3, True, 1), (1, False, 5), (1, True, 64)])
-def test_feature_detection_pass_matches_the_oracle(c, adjust, chunk_rows):
+@pytest.mark.parametrize("c,adjust,chunk_rows,reset", [(1, True, 1, None), (3, True, 1, None), (1, False, 5, None), (1, True, 64, None),
+                                                       (1, True, 1, "dilate"), (3, True, 4, "dilate"), (1, True, 1, "list"),
+                                                       (3, True, 1, "noise")])
+def test_feature_detection_pass_matches_the_oracle(c, adjust, chunk_rows, reset, monkeypatch):
     """handle_features (video.rs:883-1113) at the end of integrate_matrix: feature sets, newly found features
-    and — with rate adjustment — the c_thresh reset around them, which changes the following frames' events."""
+    and — with rate adjustment — the c_thresh reset around them, which changes the following frames' events.
+    The reset has two device forms (per feature / dilation of the new-feature bitmap, chosen from the count):
+    both are forced here, and the noise case (a feature at every seventh pixel) takes the dilation by itself."""
     w, h, nf = 96, 64, 40
+    if reset in ("dilate", "list"):
+        monkeypatch.setenv("ADDER_B200_FEATURE_RESET", reset)
     frames = synth.moving_blocks(3, nf, w, h, c)
+    if reset == "noise":
+        nf = 12
+        frames = cases.Case("feat_noise", w, h, c, synth.NOISE, nf, crf=6).frames()
     gv = A.Video(w, h, c)
     ov = O.Video(w, h, c, O.MODE_FRAME_PERFECT)
     n_new = 0
