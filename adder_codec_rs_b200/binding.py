@@ -555,10 +555,21 @@ class Framer:
         return self.ingest_events_events(ev, cc)
 
     def write_multi_frame_bytes(self, max_frames=1024) -> np.ndarray:
-        out = np.empty((max_frames, self.h, self.w, self.c), dtype=np.uint8)
+        """FrameSequence::write_multi_frame_bytes (driver.rs:971-982): every finished frame, (n, H, W, C) u8.  The frames
+        come through a small page-locked staging array, a few per call of the C entry point."""
+        if getattr(self, "_stage", None) is None:
+            self._stage = pinned_empty((4, self.h, self.w, self.c), np.uint8)
+        got = []
         n = C.c_uint32()
-        _check(self.L.adder_b200_framer_write_multi_frame_bytes(self.f, out.ctypes.data, max_frames, C.byref(n)))
-        return out[: n.value].copy()
+        while len(got) < max_frames:
+            want = min(len(self._stage), max_frames - len(got))
+            _check(self.L.adder_b200_framer_write_multi_frame_bytes(self.f, self._stage.ctypes.data, want, C.byref(n)))
+            got.extend(self._stage[k].copy() for k in range(n.value))
+            if n.value < want:
+                break
+        if not got:
+            return np.empty((0, self.h, self.w, self.c), dtype=np.uint8)
+        return np.stack(got)
 
     def flush_frame_buffer(self) -> bool:
         ready = C.c_int()

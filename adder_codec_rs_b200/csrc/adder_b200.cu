@@ -1343,6 +1343,7 @@ struct adder_b200_framer {
   uint8_t* d_out_stage = nullptr;
   uint32_t out_stage_frames = 0;
   uint32_t* h_result = nullptr; /* pinned: [0..2] predicates, [3] error word */
+  uint8_t* d_exact_lut = nullptr; /* [257] build_exact_lut(ref_interval) */
 };
 
 namespace {
@@ -1389,6 +1390,7 @@ int framer_ingest(adder_b200_framer* f, const adder_event_t* d_events, const uin
   a.view_mode = (uint32_t)f->view_mode;
   a.absolute_t = f->time_mode == ADDER_TIME_ABSOLUTE_T ? 1u : 0u;
   a.practical_d_max = f->practical_d_max;
+  a.exact_lut = f->d_exact_lut;
   a.buffer_limit = f->buffer_limit;
   a.running_ts = f->d_running_ts;
   a.last_filled = f->d_last_filled;
@@ -1466,6 +1468,12 @@ int adder_b200_framer_create(uint16_t width, uint16_t height, uint8_t channels, 
       CU(cudaMalloc(&f->d_err, sizeof(uint32_t)));
       CU(cudaMalloc(&f->d_off_stage, ((size_t)f->n_chunks + 1) * sizeof(uint32_t)));
       CU(cudaHostAlloc(&f->h_result, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+      CU(cudaMalloc(&f->d_exact_lut, 257));
+      {
+        uint8_t lut[257];
+        adder::build_exact_lut(ref_interval, lut);
+        CU(cudaMemcpyAsync(f->d_exact_lut, lut, sizeof(lut), cudaMemcpyHostToDevice, f->stream)); /* the build ends with a stream sync */
+      }
       CU(cudaMemsetAsync(f->d_running_ts, 0, P * sizeof(unsigned long long), f->stream));
       CU(cudaMemsetAsync(f->d_last_intensity, 0, P, f->stream));
       CU(cudaMemsetAsync(f->d_ring_val, 0, P * f->ring_frames, f->stream));
@@ -1491,6 +1499,7 @@ void adder_b200_framer_destroy(adder_b200_framer* f) {
   if (!f) return;
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
+  cudaFree(f->d_exact_lut);
   cudaFree(f->d_running_ts);
   cudaFree(f->d_last_filled);
   cudaFree(f->d_last_intensity);

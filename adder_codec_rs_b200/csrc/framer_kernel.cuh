@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "px_machine.cuh"
 #include "state_layout.h"
 
 namespace adder {
@@ -49,23 +50,33 @@ struct FramerArgs {
   long long* offset_max;   /* frame_idx_offsets: the furthest frame any pixel of the chunk has reached */
   long long* forced_frame; /* absolute frame whose filled_count was forced to full by buffer_limit, or -1 */
   uint32_t* err;           /* bit 0: an event reaches beyond the ring (the reference would grow its VecDeque) */
+  const uint8_t* exact_lut; /* [257] build_exact_lut(ref_interval): the Intensity byte of exactly integral intensities */
 };
 
-/* <u8 as FrameValue>::get_frame_value, SourceType::U8 (scale_intensity.rs:58-104, :262-270), literally */
-__device__ __forceinline__ uint8_t framer_value_u8(uint32_t view_mode, uint32_t d, uint32_t t, double tpf, float practical_d_max,
-                                                   uint32_t dtm, uint32_t sae_running, uint32_t sae_last) {
+/* n / d and n % d for a 64-bit n that almost always fits 32 bits (timestamps, frame numbers): the 64-bit division is a
+ * long dependent sequence, and this kernel is bound by latency */
+__device__ __forceinline__ unsigned long long udiv_fast(unsigned long long n, uint32_t d) {
+  return (n >> 32) == 0ull ? (unsigned long long)((uint32_t)n / d) : n / d;
+}
+__device__ __forceinline__ uint32_t urem_fast(unsigned long long n, uint32_t d) {
+  return (n >> 32) == 0ull ? (uint32_t)n % d : (uint32_t)(n % d);
+}
+
+/* <u8 as FrameValue>::get_frame_value, SourceType::U8 (scale_intensity.rs:58-104, :262-270).  The Intensity view is the
+ * expression the transcoder evaluates for its display byte: the same exact shortcut (px_machine.cuh frame_value_u8,
+ * checked exhaustively in tests/test_px_shortcuts_host.py) instead of an f64 division per event. */
+__device__ __forceinline__ uint8_t framer_value_u8(uint32_t view_mode, uint32_t d, uint32_t t, uint32_t ref, const uint8_t* exact_lut,
+                                                   float practical_d_max, uint32_t dtm, uint32_t sae_running, uint32_t sae_last) {
   float q;
   switch (view_mode) {
     case 0: {
-      double inten;
-      if (d >= 129u) {
-        inten = 0.0;
-      } else {
-        const double p = d >= 128u ? 0.0 : __longlong_as_double((long long)((unsigned long long)(d + 1023u) << 52));
-        inten = t == 0u ? p : __ddiv_rn(p, (double)t);
-      }
-      const uint32_t u = __double2uint_rz(__dmul_rn(inten, tpf));
-      return (uint8_t)(u > 255u ? 255u : u);
+      PxParams p{};
+      p.view_mode = 0u;
+      p.ref = ref;
+      p.tpf = (double)ref;
+      p.tpf_f = (float)ref;
+      p.exact_lut = exact_lut;
+      return frame_value_u8(p, d, t, 0.0f);
     }
     case 1: q = __fdiv_rn((float)d, practical_d_max); break;
     case 2: q = __fdiv_rn(__uint2float_rn(t), __uint2float_rn(dtm)); break;
@@ -78,15 +89,19 @@ __device__ __forceinline__ uint8_t framer_value_u8(uint32_t view_mode, uint32_t 
 __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) {
   const uint32_t total = a.chunk_off[a.n_chunks];
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
-    const uint32_t w0 = a.ev_words[3ull * j], w1 = a.ev_words[3ull * j + 1ull];
+    /* this record and the one before it, requested together: the kernel is bound by the latency of dependent loads.
+     * A run never crosses a chunk boundary (chunks are disjoint rows), so comparing coordinates is enough to find
+     * its first event and its end: the chunk offsets are not needed for that. */
+    const uint32_t w0 = a.ev_words[3ull * j], w1 = a.ev_words[3ull * j + 1ull], w2 = a.ev_words[3ull * j + 2ull];
+    uint32_t p0 = ~w0, p1 = 0u;
+    if (j > 0u) {
+      p0 = a.ev_words[3ull * (j - 1u)];
+      p1 = a.ev_words[3ull * (j - 1u) + 1ull];
+    }
     const uint32_t x = w0 & 0xFFFFu, y = w0 >> 16, cc = w1 & 0xFFu;
     const uint32_t chunk = y / a.chunk_rows;
-    if (chunk >= a.n_chunks) continue; /* malformed event: silently ignored, driver.rs:441-444 */
-    const uint32_t lo = a.chunk_off[chunk], hi = a.chunk_off[chunk + 1u];
-    if (j > lo) { /* only the first event of a run of same-pixel events works */
-      const uint32_t p0 = a.ev_words[3ull * (j - 1u)], p1 = a.ev_words[3ull * (j - 1u) + 1ull];
-      if (p0 == w0 && (p1 & 0xFFu) == cc) continue;
-    }
+    if (chunk >= a.n_chunks) continue;                 /* malformed event: silently ignored, driver.rs:441-444 */
+    if (p0 == w0 && (p1 & 0xFFu) == cc) continue;      /* only the first event of a run of same-pixel events works */
     const uint32_t channel = cc == ADDER_C_NONE ? 0u : cc;
     if (x >= a.W || y >= a.H || channel >= a.C) continue;
     const unsigned long long gi = ((unsigned long long)y * a.W + x) * a.C + channel;
@@ -95,48 +110,62 @@ __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) 
     uint32_t intensity = a.last_intensity[gi];
     long long reach = -1;
     bool force = false;
-    for (uint32_t e = j; e < hi; e++) {
-      const uint32_t e0 = a.ev_words[3ull * e], e1 = a.ev_words[3ull * e + 1ull];
-      if (e != j && !(e0 == w0 && (e1 & 0xFFu) == cc)) break;
+    uint32_t e1 = w1, e2 = w2;
+    for (uint32_t e = j;; e++) {
+      /* the next record is requested before this one is worked on */
+      const bool has_next = e + 1u < total;
+      uint32_t n0 = ~w0, n1 = 0u, n2 = 0u;
+      if (has_next) {
+        n0 = a.ev_words[3ull * (e + 1u)];
+        n1 = a.ev_words[3ull * (e + 1u) + 1ull];
+        n2 = a.ev_words[3ull * (e + 1u) + 2ull];
+      }
       const uint32_t d = (e1 >> 8) & 0xFFu;
-      uint32_t t = a.ev_words[3ull * e + 2ull];
+      uint32_t t = e2;
       const long long prev_last_filled = last_filled;
       const unsigned long long prev_running_ts = running_ts;
+      bool skip = false;
       if (a.codec_version >= 2u && a.absolute_t) { /* :1002-1012 */
-        if (prev_running_ts >= (unsigned long long)t) continue;
-        running_ts = t;
+        if (prev_running_ts >= (unsigned long long)t) skip = true; else running_ts = t;
       } else {
         running_ts += t;
       }
-      const long long fidx = (long long)(running_ts ? running_ts - 1ull : 0ull) / (long long)a.tpf;
-      if (fidx > last_filled) { /* :1014 */
-        if (d != ADDER_D_EMPTY) {
-          if (a.codec_version >= 2u && a.absolute_t && a.view_mode != 3u) {
-            const uint32_t prev32 = (uint32_t)prev_running_ts;
-            t = prev32 > t ? 0u : t - prev32; /* saturating_sub :1027 */
+      if (!skip) {
+        const long long fidx = (long long)udiv_fast(running_ts ? running_ts - 1ull : 0ull, a.tpf);
+        if (fidx > last_filled) { /* :1014 */
+          if (d != ADDER_D_EMPTY) {
+            if (a.codec_version >= 2u && a.absolute_t && a.view_mode != 3u) {
+              const uint32_t prev32 = (uint32_t)prev_running_ts;
+              t = prev32 > t ? 0u : t - prev32; /* saturating_sub :1027 */
+            }
+            intensity = framer_value_u8(a.view_mode, d, t, a.ref_interval, a.exact_lut, a.practical_d_max, a.source_dtm, (uint32_t)running_ts,
+                                        (uint32_t)prev_running_ts);
           }
-          intensity = framer_value_u8(a.view_mode, d, t, (double)a.ref_interval, a.practical_d_max, a.source_dtm, (uint32_t)running_ts,
-                                      (uint32_t)prev_running_ts);
+          last_filled = fidx;
+          if (last_filled > reach) reach = last_filled;
+          for (long long i = prev_last_filled; i < last_filled; i++) { /* :1078-1091: absolute frame i + 1 */
+            const long long fa = i + 1;
+            if (fa < a.frames_written) continue;
+            if (fa - a.frames_written >= (long long)a.ring_frames) { /* beyond what the ring can hold */
+              atomicOr(a.err, 1u);
+              break;
+            }
+            const unsigned long long slot = (unsigned long long)urem_fast((unsigned long long)fa, a.ring_frames) * a.frame_px + gi;
+            if (!a.ring_some[slot]) {
+              a.ring_some[slot] = 1;
+              a.ring_val[slot] = (uint8_t)intensity;
+            }
+          }
         }
-        last_filled = fidx;
-        if (last_filled > reach) reach = last_filled;
-        for (long long i = prev_last_filled; i < last_filled; i++) { /* :1078-1091: absolute frame i + 1 */
-          const long long fa = i + 1;
-          if (fa < a.frames_written) continue;
-          if (fa - a.frames_written >= (long long)a.ring_frames) { /* beyond what the ring can hold */
-            atomicOr(a.err, 1u);
-            break;
-          }
-          const unsigned long long slot = (unsigned long long)(fa % (long long)a.ring_frames) * a.frame_px + gi;
-          if (!a.ring_some[slot]) {
-            a.ring_some[slot] = 1;
-            a.ring_val[slot] = (uint8_t)intensity;
-          }
+        if (a.codec_version >= 1u && a.framed_source) { /* :1094-1113 */
+          const uint32_t over = urem_fast(running_ts, a.ref_interval);
+          if (over) running_ts += a.ref_interval - over; /* = (running_ts / ref_interval + 1) * ref_interval */
         }
+        if (a.buffer_limit >= 0 && last_filled > a.frames_written + a.buffer_limit) force = true; /* :1115-1121 */
       }
-      if (a.codec_version >= 1u && a.framed_source && running_ts % a.ref_interval > 0ull) /* :1094-1113 */
-        running_ts = (running_ts / a.ref_interval + 1ull) * (unsigned long long)a.ref_interval;
-      if (a.buffer_limit >= 0 && last_filled > a.frames_written + a.buffer_limit) force = true; /* :1115-1121 */
+      if (!(n0 == w0 && (n1 & 0xFFu) == cc)) break; /* the run ends (or the stream does) */
+      e1 = n1;
+      e2 = n2;
     }
     a.running_ts[gi] = running_ts;
     a.last_filled[gi] = last_filled;
