@@ -45,9 +45,11 @@ def num(s):
     return float(s.replace(",", ""))
 
 
-src = os.path.join(G, f"{tag}_launches.csv")
-if os.path.exists(src):
-    shutil.copy(src, os.path.join(PR, f"{tag}_launches.csv"))
+for stem in ("launches", "bench_launches"):
+    src = os.path.join(G, f"{tag}_{stem}.csv")
+    if not os.path.exists(src):
+        continue
+    shutil.copy(src, os.path.join(PR, f"{tag}_{stem}.csv"))
     rows = [r for r in csv.reader(open(src)) if len(r) > 5]
     hdr = rows[0]
     iK, iV = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -58,7 +60,7 @@ if os.path.exists(src):
         except ValueError:
             pass
     tot = sum(sum(v) for v in agg.values())
-    with open(os.path.join(PR, f"{tag}_launch_shares.txt"), "w") as f:
+    with open(os.path.join(PR, f"{tag}_{stem.replace('launches', 'launch_shares')}.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n")
         f.write(f"{'kernel':70} {'launches':>8} {'mean_ns':>10} {'share':>7}\n")
         for k, v in agg.items():
