@@ -48,11 +48,19 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.p = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        """the timed region starts now (the sampler itself is started earlier: nvidia-smi needs up to a second to come up)"""
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -71,17 +79,25 @@ class ClockSampler:
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        import datetime
+
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        window = "timed region"
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        if not inside:  # a timed region shorter than the sampling period: the warm-up steps just before it ran the same work
+            inside, window = rows, "warm-up + timed region"
+        sm, mx, reasons = [r[1] for r in inside], [r[2] for r in inside], set()
+        for r in inside:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
@@ -89,7 +105,7 @@ class ClockSampler:
         # under load = the upper half of the samples (the sampler also sees the idle edges)
         sm_sorted = sorted(sm)
         load = sm_sorted[len(sm_sorted) // 2:]
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def measured_peak_gbs():
@@ -232,18 +248,20 @@ def run_ours(args):
     v.sync()
     cnt = v.read_counters()
     v.set_counting(False)
+    sampler = ClockSampler(local)
+    sampler.start()  # before the warm-up: it is sampling by the time the timed region begins
     for _ in range(max(args.warmup, 3)):
         step_device()
     v.sync()
 
-    sampler = ClockSampler(local)
     barrier()
     ev0, l0 = v.events_emitted(), v.launch_count
-    sampler.start()
+    sampler.mark_begin()
     v.timer_start()
     for _ in range(args.steps):
         step_device()
     ms = v.timer_stop()
+    sampler.mark_end()
     clocks = sampler.stop()
     v.sync()
     barrier()
