@@ -93,7 +93,13 @@ __global__ void __launch_bounds__(256) feature_kernel(const uint32_t* __restrict
       if (mask[p] == 0) { /* HashSet::insert returned true: a new feature */
         mask[p] = 1;
         if (new_mask) new_mask[p] = 1;
-        const uint32_t k = atomicAdd(n_new, 1u);
+        /* one atomic per group of lanes that got here together (the list is unordered anyway): on noise every seventh
+         * pixel is a new feature and they all count on the one word */
+        const uint32_t grp = __activemask(), lane = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)grp) - 1u;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(n_new, (uint32_t)__popc(grp));
+        base = __shfl_sync(grp, base, (int)leader);
+        const uint32_t k = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
         if (k < new_cap) new_xy[k] = x | (y << 16);
       }
     } else {
