@@ -172,3 +172,36 @@ def test_full_size_multi_frame_launch_matches_the_oracle(spec):
     assert np.array_equal(gv.running_intensities(), ov.running_intensities())
     for b in (d_frames, d_events, d_off):
         b.free()
+
+
+def test_long_multi_frame_launch_at_bench_geometry():
+    """The bench step in small: 1080p RGB noise, 120 frames through ONE launch.  Every frame's event total and chunk
+    offsets against the oracle, the full streams of a few frames byte for byte, and the final display plane."""
+    case = _case("bench_120", 1920, 1080, 3, synth.NOISE, 120, dict(crf=3))
+    gv = A.Video(case.w, case.h, case.c)
+    ov = O.Video(case.w, case.h, case.c, O.MODE_FRAME_PERFECT)
+    cases.configure(gv, case)
+    cases.configure(ov, case)
+    P = case.w * case.h * case.c
+    nf = case.n_frames
+    d_frames = gv.device_alloc(P * nf)
+    gv.synth_frames(d_frames, 0, nf, case.kind, case.seed)
+    cap = P * 2
+    d_events = gv.device_alloc(cap * 12 * nf)
+    d_off = gv.device_alloc((gv.n_chunks + 1) * 4 * nf)
+    gv.integrate_frames_device(d_frames.ptr, P, 1, case.time, d_events.ptr, cap, d_off.ptr)  # a fresh state: the first frame goes alone
+    gv.integrate_frames_device(d_frames.ptr + P, P, nf - 1, case.time, d_events.ptr + cap * 12, cap, d_off.ptr + (gv.n_chunks + 1) * 4)
+    gv.sync()
+    offs = d_off.to_host(np.uint32).reshape(nf, gv.n_chunks + 1)
+    nt = O.max_threads()
+    for f in range(nf):
+        frame = d_frames.to_host(nbytes=P, offset=f * P).reshape(case.h, case.w, case.c)
+        eo, co = ov.integrate_matrix(frame, case.time, nt)
+        assert int(offs[f, -1]) == len(eo), f"frame {f}: {int(offs[f, -1])} vs {len(eo)} events"
+        assert np.array_equal(np.diff(offs[f]), co), f"frame {f}: chunk lengths differ"
+        if f in (1, 2, 57, 118, 119):
+            eg = d_events.to_host(A.EVENT_DTYPE, nbytes=len(eo) * 12, offset=f * cap * 12)
+            assert eg.tobytes() == eo.tobytes(), f"frame {f}: event streams differ"
+    assert np.array_equal(gv.running_intensities(), ov.running_intensities())
+    for b in (d_frames, d_events, d_off):
+        b.free()
