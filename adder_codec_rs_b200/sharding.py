@@ -95,25 +95,47 @@ def gather_events(events, chunk_counts, group=None, dst: Optional[int] = 0):
     dist.all_gather(metas, meta, group=group)  # G counts: 16 bytes per rank
     sizes = [int(m[0]) for m in metas]
     n_chunks = [int(m[1]) for m in metas]
-    pad_e, pad_c = max(max(sizes), 1), max(max(n_chunks), 1)
-    send_e = torch.zeros(pad_e, dtype=torch.uint8, device=dev)
-    send_e[:events.numel()] = events
-    send_c = torch.zeros(pad_c, dtype=torch.int64, device=dev)
-    send_c[:chunk_counts.numel()] = chunk_counts
-    if dst is None:
+    if dst is None:  # every rank wants the frame: padded all-gather
+        pad_e, pad_c = max(max(sizes), 1), max(max(n_chunks), 1)
+        send_e = torch.zeros(pad_e, dtype=torch.uint8, device=dev)
+        send_e[:events.numel()] = events
+        send_c = torch.zeros(pad_c, dtype=torch.int64, device=dev)
+        send_c[:chunk_counts.numel()] = chunk_counts
         recv_e = [torch.empty_like(send_e) for _ in range(world)]
         recv_c = [torch.empty_like(send_c) for _ in range(world)]
         dist.all_gather(recv_e, send_e, group=group)
         dist.all_gather(recv_c, send_c, group=group)
-    else:
-        recv_e = [torch.empty_like(send_e) for _ in range(world)] if rank == dst else None
-        recv_c = [torch.empty_like(send_c) for _ in range(world)] if rank == dst else None
-        dist.gather(send_e, recv_e, dst=dst, group=group)
-        dist.gather(send_c, recv_c, dst=dst, group=group)
-        if rank != dst:
-            return None, None
-    ev = torch.cat([recv_e[g][:sizes[g]] for g in range(world)])  # rank order == raster order
-    cc = torch.cat([recv_c[g][:n_chunks[g]] for g in range(world)])
+        ev = torch.cat([recv_e[g][:sizes[g]] for g in range(world)])  # rank order == raster order
+        cc = torch.cat([recv_c[g][:n_chunks[g]] for g in range(world)])
+        return ev, cc
+    # one consumer: every band goes straight from where the kernel left it into its place in the consumer's frame
+    # buffer (exact sizes, no padding, no staging copy): rank order == raster order
+    if rank != dst:
+        ops = []
+        if sizes[rank]:
+            ops.append(dist.P2POp(dist.isend, events, dst, group=group))
+        if n_chunks[rank]:
+            ops.append(dist.P2POp(dist.isend, chunk_counts.contiguous(), dst, group=group))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        return None, None
+    ev = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
+    cc = torch.empty(sum(n_chunks), dtype=torch.int64, device=dev)
+    e0 = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    c0 = np.concatenate([[0], np.cumsum(n_chunks)]).astype(np.int64)
+    ops = []
+    for g in range(world):
+        if g == dst:
+            continue
+        if sizes[g]:
+            ops.append(dist.P2POp(dist.irecv, ev[e0[g]:e0[g + 1]], g, group=group))
+        if n_chunks[g]:
+            ops.append(dist.P2POp(dist.irecv, cc[c0[g]:c0[g + 1]], g, group=group))
+    works = dist.batch_isend_irecv(ops) if ops else []
+    ev[e0[dst]:e0[dst + 1]] = events  # this rank's own band, while the others arrive
+    cc[c0[dst]:c0[dst + 1]] = chunk_counts
+    for w in works:
+        w.wait()
     return ev, cc
 
 
