@@ -191,6 +191,9 @@ constexpr uint32_t kWarps = kThreads / 32;
  * Warps 0 and 1 carry the CTA's serial work (scan + publish, look-back) and would otherwise finish
  * every iteration last, with the other six waiting for them (profiles/r01d).
  */
+#ifndef ADDER_EV_STREAM
+#define ADDER_EV_STREAM 1 /* event records (and with 2 the display bytes) leave with st.global.cs: written once, not read again by the kernel (-0.6 % time) */
+#endif
 #ifndef ADDER_NAMED_BARS
 #define ADDER_NAMED_BARS 1 /* rendezvous on named barriers (bar.sync parks the warp) instead of polled mbarriers */
 #endif
@@ -451,7 +454,11 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           uint8_t disp;
           const bool show = px_step(px, samples[r * 32u + lane], h, n0, n1, mem, park, errbits, &disp);
           a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
+#if ADDER_EV_STREAM >= 2
+          if (show) __stcs(a.running + i, disp);
+#else
           if (show) a.running[i] = disp;
+#endif
           if (park.overflow) errbits |= ADDER_DEVERR_DEPTH;
           nev = park.n;
           if (kCount) {
@@ -648,9 +655,15 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             const unsigned long long rec = (unsigned long long)first + e;
             if (rec < a.ev_cap) {
               uint32_t* dst = ev_out + rec * 3ull;
+#if ADDER_EV_STREAM
+              __stcs(dst, w0); /* records are written once and not read again by this kernel */
+              __stcs(dst + 1, c | (dd << 8));
+              __stcs(dst + 2, tt);
+#else
               dst[0] = w0;
               dst[1] = c | (dd << 8);
               dst[2] = tt;
+#endif
             } else {
               capbits = ADDER_DEVERR_CAPACITY;
             }
@@ -665,9 +678,15 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             const unsigned long long rec = (unsigned long long)first + e;
             if (rec < a.ev_cap) {
               uint32_t* dst = ev_out + rec * 3ull;
+#if ADDER_EV_STREAM
+              __stcs(dst, w0); /* records are written once and not read again by this kernel */
+              __stcs(dst + 1, c | (dd << 8));
+              __stcs(dst + 2, tt);
+#else
               dst[0] = w0;
               dst[1] = c | (dd << 8);
               dst[2] = tt;
+#endif
             } else {
               capbits = ADDER_DEVERR_CAPACITY;
             }
