@@ -608,7 +608,9 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
       const uint16_t* const pinfo = s_info + pb * TILE;
       uint32_t capbits = 0;
       if (chunk_out) { /* lengths of the reference's Vec<Vec<Event>>, video.rs:677-734 */
-        if (a.chunk_px >= TILE) { /* at most one chunk starts inside this tile */
+        if (a.chunk_px >= TILE) { /* at most one chunk starts inside this tile.  The thread that OWNS that pixel writes the offset:
+                                   * info[] of this park buffer is rewritten by warps already in iteration n+1, each for its own
+                                   * rows only, so no other warp may read it here (tried: a full-size test caught the race) */
           const uint32_t t_end = pstart + TILE - 1u < a.P - 1u ? pstart + TILE - 1u : a.P - 1u;
           const uint32_t ch = a.chunk_magic ? mulhi_u32_u64(t_end, a.chunk_magic) : t_end; /* chunk of the tile's last pixel */
           const uint32_t cb = ch * a.chunk_px;                                              /* its first pixel */

@@ -23,6 +23,7 @@ ap.add_argument("--batch", action="store_true", help="hand all frames to one int
 ap.add_argument("--cap", type=int, default=4, help="event records per pixel-channel per frame the output buffer holds")
 ap.add_argument("--manual", type=int, default=-1, help="quality_manual(c, c, dtm/ref, 1) instead of crf (BASELINE cfg 3 sweep)")
 ap.add_argument("--normal", action="store_true", help="PixelMultiMode::Normal")
+ap.add_argument("--offsets", action="store_true", help="also ask for the per-frame chunk offsets (as bench.py does)")
 ap.add_argument("--count", action="store_true", help="one extra untimed pass with the counting twin: algorithmic bytes + roofline fraction")
 a = ap.parse_args()
 
@@ -43,6 +44,7 @@ d_frames = v.device_alloc(P * a.frames)
 v.synth_frames(d_frames, 0, a.frames, a.kind, 0xADDE5)
 stride = P * a.cap
 d_events = v.device_alloc(stride * 12 * (a.frames if a.batch else 4))
+d_off = v.device_alloc((v.n_chunks + 1) * 4 * a.frames) if a.offsets else None
 v.sync()
 alg = None
 if a.count:
@@ -65,10 +67,10 @@ for rep in range(a.reps):
     quality()
     v.timer_start()
     if a.batch:
-        v.integrate_frames_device(d_frames.ptr, P, a.frames, float(a.ref), d_events.ptr, stride, None)
+        v.integrate_frames_device(d_frames.ptr, P, a.frames, float(a.ref), d_events.ptr, stride, d_off.ptr if d_off else None)
     else:
         for f in range(a.frames):
-            v.integrate_frames_device(d_frames.ptr + f * P, P, 1, float(a.ref), d_events.ptr + (f % 4) * stride * 12, stride, None)
+            v.integrate_frames_device(d_frames.ptr + f * P, P, 1, float(a.ref), d_events.ptr + (f % 4) * stride * 12, stride, d_off.ptr if d_off else None)
     ms = v.timer_stop()
     v.sync()
     extra = f", {alg / ms / 1e6:.0f} GB/s = {alg / ms / 1e6 / 6540.2:.3f} of 6540" if alg else ""
