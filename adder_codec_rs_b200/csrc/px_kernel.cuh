@@ -565,6 +565,21 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           const unsigned long long tag = (unsigned long long)(a.epoch + fi) << 2;
           if (tl != 0u) st_status(row + tl, ((tag | kFlagPrefix) << 32) | incl_all, kMulti && n_frames > 1u); /* a dependent may acquire this value instead of the aggregate */
           s_prefix[(n + 1u) & 1u] = excl; /* slot (n-1) & 1 */
+          if (a.chunk_off && a.chunk_px >= TILE) {
+            /* lengths of the reference's Vec<Vec<Event>>, video.rs:677-734: at most one chunk starts inside this tile.  Its
+             * offset is written here, by the one thread that has just learnt the tile's prefix: the row prefixes (warp 0's
+             * scan, a tile ago) and the pixel's place in its row are in the park buffer of tile n-1, which no warp rewrites
+             * before iteration n+2 — and nobody starts that before this warp has signalled B(n). */
+            const uint32_t pbm1 = b == 0u ? 2u : b - 1u;
+            const uint32_t ps = tl * TILE;
+            const uint32_t t_end = ps + TILE - 1u < a.P - 1u ? ps + TILE - 1u : a.P - 1u;
+            const uint32_t ch = a.chunk_magic ? mulhi_u32_u64(t_end, a.chunk_magic) : t_end; /* chunk of the tile's last pixel */
+            const uint32_t cb = ch * a.chunk_px;                                              /* its first pixel */
+            if (cb >= ps) {
+              const uint32_t qq = cb - ps;
+              a.chunk_off[(unsigned long long)fi * (a.n_chunks + 1u) + ch] = excl + s_wtot[pbm1][qq >> 5] + ((s_info + pbm1 * TILE)[qq] & 1023u);
+            }
+          }
           if (tl == a.n_tiles - 1u) {
             if (a.chunk_off) a.chunk_off[(unsigned long long)fi * (a.n_chunks + 1u) + a.n_chunks] = incl_all;
             if (a.total_events) atomicAdd(a.total_events, (unsigned long long)incl_all);
@@ -607,19 +622,9 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
       const uint8_t* const pslot_d = s_slot_d + pb * (S * TILE);
       const uint16_t* const pinfo = s_info + pb * TILE;
       uint32_t capbits = 0;
-      if (chunk_out) { /* lengths of the reference's Vec<Vec<Event>>, video.rs:677-734 */
-        if (a.chunk_px >= TILE) { /* at most one chunk starts inside this tile.  The thread that OWNS that pixel writes the offset:
-                                   * info[] of this park buffer is rewritten by warps already in iteration n+1, each for its own
-                                   * rows only, so no other warp may read it here (tried: a full-size test caught the race) */
-          const uint32_t t_end = pstart + TILE - 1u < a.P - 1u ? pstart + TILE - 1u : a.P - 1u;
-          const uint32_t ch = a.chunk_magic ? mulhi_u32_u64(t_end, a.chunk_magic) : t_end; /* chunk of the tile's last pixel */
-          const uint32_t cb = ch * a.chunk_px;                                              /* its first pixel */
-          if (cb >= pstart) {
-            const uint32_t qq = cb - pstart, row = qq >> 5;
-            const uint32_t owner = row < 8u * ((uint32_t)R - 1u) ? (row & 7u) : row - 8u * ((uint32_t)R - 1u) + 2u * ADDER_DUTY_LESS;
-            if (owner * 32u + (qq & 31u) == tid) chunk_out[ch] = prefix + s_wtot[pb][row] + (pinfo[qq] & 1023u);
-          }
-        } else {
+      if (chunk_out) { /* chunks smaller than a tile: several may start here, each offset written by the thread that owns the pixel
+                        * (a chunk of a tile or more is handled by warp 1 when it learns the tile's prefix) */
+        if (a.chunk_px < TILE) {
 #pragma unroll 1
           for (uint32_t r = 0; r < my_rows; r++) {
             const uint32_t row = row_of(r), q = 32u * row + lane, i = pstart + q;
