@@ -76,3 +76,35 @@ def test_two_rank_gloo_gather_equals_whole_frame_oracle(case_name, dst, tmp_path
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), case_name, dst, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def _ragged_worker(rank, world, port, dst, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        sizes = [0, 7, 3]  # records per rank: one band with nothing to give
+        chunks = [2, 1, 3]
+        for rnd in range(3):
+            mine = torch.full((sizes[rank] * 12,), 10 * rnd + rank, dtype=torch.uint8)
+            cc = torch.arange(chunks[rank], dtype=torch.int64) + 100 * rank + rnd
+            ev, gc = S.gather_events(mine, cc, dst=dst)
+            if dst is None or rank == dst:
+                want = torch.cat([torch.full((sizes[g] * 12,), 10 * rnd + g, dtype=torch.uint8) for g in range(world)])
+                want_c = torch.cat([torch.arange(chunks[g], dtype=torch.int64) + 100 * g + rnd for g in range(world)])
+                assert torch.equal(ev, want) and torch.equal(gc, want_c)
+            else:
+                assert ev is None and gc is None
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dst", [1, None])
+def test_three_rank_gather_with_an_empty_band_and_a_consumer_that_is_not_rank_0(dst, tmp_path):
+    import torch.multiprocessing as mp
+
+    world = 3
+    mp.spawn(_ragged_worker, args=(world, _free_port(), dst, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
