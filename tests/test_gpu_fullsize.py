@@ -135,43 +135,121 @@ def test_two_bands_equal_the_whole_plane_at_4k():
         assert np.concatenate(got).tobytes() == want.tobytes(), f"frame {f}"
 
 
-MULTI = [
-    ("cfg2_1080p_rgb_noise_24_frames", 1920, 1080, 3, synth.NOISE, 24, dict(crf=3)),
-    ("cfg3_4k_gray_jitter_c10_16_frames", 3840, 2160, 1, synth.JITTER, 16, dict(manual=(10, 10, 30, 1))),
-    ("cfg5_8k_gray_static_8_frames", 7680, 4320, 1, synth.STATIC_BLIPS, 8, dict(crf=3, ref=256, dtm=1 << 20)),
-]
+# Frames whose complete streams are compared byte for byte in the long runs below: the first frames, the frames
+# around the first Δt_max pop (dtm = 30 ref: a pixel that never changed pops its root at frame 30,
+# event_pixel_tree.rs:394-396) and the end of the crf-3 c_thresh ramp (2 -> 7, +1 every 7 frames: frame ~35,
+# :402-412), and the last frames.  Every other frame is compared by event total and per-chunk lengths.
+FULL_STREAM_FRAMES = (0, 1, 2, 29, 30, 31, 32, 33, 34, 35, 36, 37, 62, 63)
 
 
-@pytest.mark.parametrize("spec", MULTI, ids=lambda s: s[0])
-def test_full_size_multi_frame_launch_matches_the_oracle(spec):
-    """All frames through ONE launch (what bench.py times): thousands of tiles per frame, frames overlapping in
-    flight, every frame's stream compared with the oracle run frame by frame."""
-    case = _case(*spec)
+def _one_launch_against_the_oracle(case, nf, cap_per_px, full_frames):
+    """All nf frames through ONE integrate launch (what bench.py times) against the oracle run frame by frame:
+    event totals and chunk lengths for every frame, whole streams for `full_frames`, and the display plane at the end."""
     gv = A.Video(case.w, case.h, case.c)
     ov = O.Video(case.w, case.h, case.c, O.MODE_FRAME_PERFECT)
     cases.configure(gv, case)
     cases.configure(ov, case)
     P = case.w * case.h * case.c
-    nf = case.n_frames
     d_frames = gv.device_alloc(P * nf)
     gv.synth_frames(d_frames, 0, nf, case.kind, case.seed)
-    cap = P * 2
+    cap = int(P * cap_per_px)
     d_events = gv.device_alloc(cap * 12 * nf)
     d_off = gv.device_alloc((gv.n_chunks + 1) * 4 * nf)
+    l0 = gv.launch_count
     gv.integrate_frames_device(d_frames.ptr, P, nf, case.time, d_events.ptr, cap, d_off.ptr)
     gv.sync()
+    assert gv.launch_count - l0 == 1, "the frames were meant to go through one launch"
     offs = d_off.to_host(np.uint32).reshape(nf, gv.n_chunks + 1)
     nt = O.max_threads()
+    compared = 0
     for f in range(nf):
         frame = d_frames.to_host(nbytes=P, offset=f * P).reshape(case.h, case.w, case.c)
         eo, co = ov.integrate_matrix(frame, case.time, nt)
         assert int(offs[f, -1]) == len(eo), f"frame {f}: {int(offs[f, -1])} vs {len(eo)} events"
         assert np.array_equal(np.diff(offs[f]), co), f"frame {f}: chunk lengths differ"
-        eg = d_events.to_host(A.EVENT_DTYPE, nbytes=len(eo) * 12, offset=f * cap * 12)
-        assert eg.tobytes() == eo.tobytes(), f"frame {f}: event streams differ"
+        if f in full_frames:
+            eg = d_events.to_host(A.EVENT_DTYPE, nbytes=len(eo) * 12, offset=f * cap * 12)
+            assert eg.tobytes() == eo.tobytes(), f"frame {f}: event streams differ"
+            compared += 1
+    assert compared >= min(8, nf)
     assert np.array_equal(gv.running_intensities(), ov.running_intensities())
     for b in (d_frames, d_events, d_off):
         b.free()
+    return ov
+
+
+# every BASELINE geometry, 64 frames through one launch (cap_per_px bounds the events of one frame)
+LONG = [
+    ("cfg2_1080p_rgb_noise_64_frames", 1920, 1080, 3, synth.NOISE, 64, dict(crf=3), 2),
+    ("cfg3_4k_gray_jitter_c10_64_frames", 3840, 2160, 1, synth.JITTER, 64, dict(manual=(10, 10, 30, 1)), 2),
+    ("cfg4_4k_rgb_noise_64_frames", 3840, 2160, 3, synth.NOISE, 64, dict(crf=3), 1.25),
+    ("cfg5_8k_gray_static_collapse_64_frames", 7680, 4320, 1, synth.STATIC_BLIPS, 64, dict(crf=3, ref=256, dtm=1 << 20), 0.5),
+    ("cfg5_8k_gray_static_normal_64_frames", 7680, 4320, 1, synth.STATIC_BLIPS, 64,
+     dict(crf=3, ref=256, dtm=1 << 20, multi_mode=O.MULTI_NORMAL), 0.5),
+]
+
+
+@pytest.mark.parametrize("spec", LONG, ids=lambda s: s[0])
+def test_full_size_64_frames_in_one_launch_match_the_oracle(spec):
+    """VERDICT r1 task 1(a): at every BASELINE geometry the run goes past the first Δt_max pop and the end of the
+    c ramp, so pop_top_event, Collapse / D_EMPTY and the park arena are compared at full size."""
+    case = _case(*spec[:7])
+    _one_launch_against_the_oracle(case, case.n_frames, spec[7], FULL_STREAM_FRAMES)
+
+
+@pytest.mark.parametrize("c", list(range(11)))
+def test_cfg3_contrast_threshold_sweep_at_4k(c):
+    """VERDICT r1 task 1(b): BASELINE configs[2], every c_thresh of the sweep 0..=10 (quality_manual(c, c, 30, 1, 0.0)),
+    40 frames of 4K gray jitter through one launch."""
+    case = _case(f"cfg3_4k_c{c}", 3840, 2160, 1, synth.JITTER, 40, dict(manual=(c, c, 30, 1)))
+    _one_launch_against_the_oracle(case, 40, 2, (0, 1, 2, 29, 30, 31, 32, 33, 34, 35, 36, 39))
+
+
+@pytest.mark.parametrize("multi", [O.MULTI_COLLAPSE, O.MULTI_NORMAL], ids=["collapse", "normal"])
+def test_cfg5_long_integration_past_delta_t_max(multi):
+    """VERDICT r1 task 1(c): ref 256, dtm 2^20 = 4096 ref.  A small static plane (every intensity 0..255 present, no
+    blips) run for 4200 frames: the deep stacks (11+ live nodes) and their Δt_max pop at frame 4096 are compared with
+    the oracle, every event of every frame, and the complete pixel state at the end."""
+    w, h, nf = 64, 24, 4200
+    base = synth.frame(synth.NOISE, 0xC0FFEE, 0, w, h, 1)
+    base.reshape(-1)[:256] = np.arange(256, dtype=np.uint8)
+    gv = A.Video(w, h, 1)
+    ov = O.Video(w, h, 1, O.MODE_FRAME_PERFECT)
+    for v in (gv, ov):
+        assert v.time_parameters(256 * 30, 256, 1 << 20, None)
+        v.write_out(None, multi)
+        v.update_crf(3)
+    P = w * h
+    batch = 300
+    frames = np.broadcast_to(base[None], (batch, h, w, 1)).copy()
+    d_frames = gv.device_alloc(P * batch)
+    d_frames.from_host(frames)
+    cap = P * 16
+    d_events = gv.device_alloc(cap * 12 * batch)
+    d_off = gv.device_alloc((gv.n_chunks + 1) * 4 * batch)
+    max_len = 0
+    total = 0
+    for f0 in range(0, nf, batch):
+        gv.integrate_frames_device(d_frames.ptr, P, batch, 256.0, d_events.ptr, cap, d_off.ptr)
+        gv.sync()
+        offs = d_off.to_host(np.uint32).reshape(batch, gv.n_chunks + 1)
+        for k in range(batch):
+            eo, co = ov.integrate_matrix(base, 256.0)
+            assert int(offs[k, -1]) == len(eo), f"frame {f0 + k}: {int(offs[k, -1])} vs {len(eo)} events"
+            assert np.array_equal(np.diff(offs[k]), co), f"frame {f0 + k}"
+            if len(eo):
+                eg = d_events.to_host(A.EVENT_DTYPE, nbytes=len(eo) * 12, offset=k * cap * 12)
+                assert eg.tobytes() == eo.tobytes(), f"frame {f0 + k}: event streams differ"
+            total += len(eo)
+        if f0 + batch in (3900, 4200):
+            for i in range(0, P, 7):
+                a = cases.canonical_oracle_px(ov.px(i))
+                b = cases.canonical(gv.px_dict(i))
+                assert a == b, f"after frame {f0 + batch}, pixel {i}: state differs\noracle {a}\ngpu    {b}"
+                max_len = max(max_len, a["length"])
+    assert max_len >= 11, f"deepest stack seen: {max_len}"
+    assert total >= P - 16, "the Δt_max pops at frame 4096 should have produced an event for (nearly) every pixel"
+    assert np.array_equal(gv.running_intensities(), ov.running_intensities())
 
 
 def test_long_multi_frame_launch_at_bench_geometry():
