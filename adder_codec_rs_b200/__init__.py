@@ -30,4 +30,3 @@ from .binding import (  # noqa: F401
     raw_eof,
 )
 from .framed import Framed, RawAdderWriter  # noqa: F401
-from .simulproc import SimulProcessor  # noqa: F401

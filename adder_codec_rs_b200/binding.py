@@ -418,8 +418,10 @@ class Video:
         _check(rc)
         return events_out[: n.value], counts
 
-    def integrate_frames_host(self, frames: np.ndarray, time_spanned: float, events_out: np.ndarray):
-        """n frames, host buffers, copies and kernels pipelined.  Returns (events, frame_counts, chunk_counts)."""
+    def integrate_frames_host(self, frames: np.ndarray, time_spanned: float, events_out: np.ndarray, partial: bool = False):
+        """n frames, host buffers, copies and kernels pipelined.  Returns (events, frame_counts, chunk_counts).
+        partial=True: a full events_out is not an error; returns (events, frame_counts, chunk_counts, frames_done) for the
+        frames delivered — call again with frames[frames_done:] (the header's resume contract)."""
         assert frames.dtype == np.uint8 and frames.flags.c_contiguous
         nf = frames.shape[0]
         assert frames[0].size == self.w * self.h * self.src_c
@@ -429,8 +431,10 @@ class Video:
         rc = self.L.adder_b200_video_integrate_frames_host(self.v, frames.ctypes.data, frames[0].size, nf, time_spanned,
                                                            events_out.ctypes.data, len(events_out), fc.ctypes.data,
                                                            cc.ctypes.data, C.byref(n), C.byref(done))
+        if rc == ERR_CAPACITY and partial:
+            return events_out[: n.value], fc[: done.value], cc[: done.value], done.value
         _check(rc)
-        return events_out[: n.value], fc, cc
+        return (events_out[: n.value], fc, cc, nf) if partial else (events_out[: n.value], fc, cc)
 
     # ---- raw .adder output ----
     def raw_header(self, version=3, source_camera=0, adu_interval=0) -> bytes:

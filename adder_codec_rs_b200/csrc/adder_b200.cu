@@ -149,6 +149,9 @@ struct adder_b200_video {
   uint32_t* h_chunk_off[kRing] = {nullptr, nullptr, nullptr}; /* pinned */
   uint64_t events_capacity = 0;                               /* records per slot */
   int last_slot = -1;                                         /* slot holding the last single-frame call's events */
+  /* frames integrated by integrate_frames_host[_raw] whose events did not fit the caller's buffer (frames_host_impl) */
+  uint32_t pend_n = 0, pend_slot0 = 0;
+  bool pend_raw = false;
 
   cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
   cudaEvent_t ev_in[kRing] = {}, ev_k[kRing] = {}, ev_out[kRing] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -166,6 +169,11 @@ uint32_t derive_depth(const adder_b200_video* v) {
   /* live nodes grow like log2 of the frames a pixel can integrate before Δt_max pops the root
    * (7 at Δt_max/ref = 24, 11 at 4096); +6 leaves two levels of margin over the
    * floor(log2)+4 bound observed there.  The kernel reports ADDER_DEVERR_DEPTH if it is ever exceeded. */
+  /* PixelMultiMode::Normal: popped_dtm stays set after the first Δt_max pop (only pop_best_events clears it,
+   * event_pixel_tree.rs:283), the root is never popped again and a static pixel's stack grows with the logarithm of
+   * the frames integrated since its last change — bounded by nothing but the reference's own 30-iteration guard
+   * (:387-389).  Allocate that guard's depth. */
+  if (v->multi_mode == ADDER_MULTI_NORMAL) return ADDER_MAX_DEPTH;
   uint32_t ratio = v->delta_t_max / std::max<uint32_t>(v->ref_time, 1u);
   uint32_t lg = 0;
   while ((ratio >> (lg + 1)) != 0) lg++;
@@ -319,7 +327,26 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   if (n_frames == 0) return ADDER_OK;
   if (n_frames > 1 && (v->feature_detection || n_frames > kMaxFramesPerLaunch || (uint64_t)n_frames * v->n_tiles_r >= (1ull << 31)))
     return fail(ADDER_ERR_INTERNAL, "launch_frames: batch not split by the caller");
+  /* everything that can fail comes before the first side effect (host counters, queued kernels) */
+  if (v->feature_detection && v->row0 != 0)
+    return fail(ADDER_ERR_UNSUPPORTED, "feature detection on a row band: the FAST neighbourhood would cross bands");
   if (int rc = ensure_depth(v, derive_depth(v))) return rc;
+  if (v->feature_detection) {
+    if (!v->d_feat_mask) {
+      const size_t hw = (size_t)v->w * v->h;
+      v->new_cap = (uint32_t)std::min<size_t>(hw, 1u << 24);
+      CU(cudaMalloc(&v->d_feat_mask, hw));
+      CU(cudaMemsetAsync(v->d_feat_mask, 0, hw, stream));
+      CU(cudaMalloc(&v->d_new_xy, (size_t)v->new_cap * sizeof(uint32_t)));
+      CU(cudaMalloc(&v->d_n_new, sizeof(uint32_t)));
+      CU(cudaMalloc(&v->d_new_mask, hw));
+      CU(cudaMalloc(&v->d_row_hit, hw));
+    }
+    if (!d_chunk_off) { /* the feature pass walks the stream chunk by chunk */
+      if (!v->d_feat_off) CU(cudaMalloc(&v->d_feat_off, ((size_t)v->h + 1) * sizeof(uint32_t))); /* n_chunks <= h */
+      d_chunk_off = v->d_feat_off;
+    }
+  }
 
   if (v->in_interval_count == 0) { /* video.rs:656-658 */
     adder::set_initial_d_kernel<<<(v->P + 255) / 256, 256, 0, stream>>>(v->d_hdr, v->d_nodes, d_frame, v->P);
@@ -365,23 +392,6 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   a.running = v->d_running;
   a.ev_words = reinterpret_cast<uint32_t*>(d_events);
   a.ev_cap = cap;
-  if (v->feature_detection) {
-    if (v->row0 != 0) return fail(ADDER_ERR_UNSUPPORTED, "feature detection on a row band: the FAST neighbourhood would cross bands");
-    if (!v->d_feat_mask) {
-      const size_t hw = (size_t)v->w * v->h;
-      v->new_cap = (uint32_t)std::min<size_t>(hw, 1u << 24);
-      CU(cudaMalloc(&v->d_feat_mask, hw));
-      CU(cudaMemsetAsync(v->d_feat_mask, 0, hw, stream));
-      CU(cudaMalloc(&v->d_new_xy, (size_t)v->new_cap * sizeof(uint32_t)));
-      CU(cudaMalloc(&v->d_n_new, sizeof(uint32_t)));
-      CU(cudaMalloc(&v->d_new_mask, hw));
-      CU(cudaMalloc(&v->d_row_hit, hw));
-    }
-    if (!d_chunk_off) { /* the feature pass walks the stream chunk by chunk */
-      if (!v->d_feat_off) CU(cudaMalloc(&v->d_feat_off, ((size_t)v->h + 1) * sizeof(uint32_t))); /* n_chunks <= h */
-      d_chunk_off = v->d_feat_off;
-    }
-  }
   a.chunk_off = d_chunk_off;
   a.tile_status = v->d_status;
   a.ticket = v->d_ticket;
@@ -896,6 +906,7 @@ int adder_b200_video_reset_state(adder_b200_video* v) {
   v->running_t = 0.0f;
   v->in_interval_count = 1;
   v->display_force = true;
+  v->pend_n = 0; /* events of frames integrated before the reset are dropped with the state */
   if (v->d_feat_mask) CU(cudaMemsetAsync(v->d_feat_mask, 0, (size_t)v->w * v->h, v->stream));
   return ADDER_OK;
 }
@@ -911,6 +922,7 @@ int adder_b200_video_integrate_matrix(adder_b200_video* v, const uint8_t* frame,
                                       uint64_t* n_events) {
   return guarded([&]() -> int {
     if (!v || !frame) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (v->pend_n) return fail(ADDER_ERR_BAD_PARAMS, "%u frames integrated by integrate_frames_host are waiting to be delivered: resume that call first", v->pend_n);
     if (int rc = set_device(v)) return rc;
     if (int rc = ensure_depth(v, derive_depth(v))) return rc;
     if (int rc = ensure_host_form(v)) return rc;
@@ -973,11 +985,24 @@ int launch_raw_encode(adder_b200_video* v, cudaStream_t stream, const adder_even
 }
 
 /* n_frames consecutive calls of integrate_matrix with H2D / kernels / D2H overlapped on three streams.
- * raw = false: 12-byte records to out; raw = true: the wire bytes of the same events. */
+ * raw = false: 12-byte records to out; raw = true: the wire bytes of the same events.
+ *
+ * Capacity.  A frame's event count is known only after its kernel has run, and up to kRing frames are in flight, so when
+ * `out` fills up some frames have been integrated whose events no longer fit.  Their events are NOT lost and the frames are
+ * NOT integrated twice: they stay in the handle's ring ("pending"), the call returns ADDER_ERR_CAPACITY with *frames_done =
+ * the frames delivered, and the next call — which the caller makes with frames + frames_done * stride, as documented —
+ * delivers the pending frames first and skips integrating them. */
 int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_stride, uint32_t n_frames, float time_spanned,
                      void* out, size_t out_cap /* records, or bytes when raw */, bool raw, uint64_t* frame_counts,
                      uint32_t* chunk_counts, uint64_t* n_out, uint32_t* frames_done) {
   if (!v || (!frames && n_frames)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+  if (n_out) *n_out = 0;
+  if (frames_done) *frames_done = 0;
+  if (v->pend_n && v->pend_raw != raw)
+    return fail(ADDER_ERR_BAD_PARAMS, "%u integrated frames are waiting to be delivered in the %s form: resume with the same call",
+                v->pend_n, v->pend_raw ? "raw" : "record");
+  if (v->pend_n > n_frames)
+    return fail(ADDER_ERR_BAD_PARAMS, "%u integrated frames are waiting to be delivered: resume with at least that many frames", v->pend_n);
   if (int rc = set_device(v)) return rc;
   if (int rc = ensure_depth(v, derive_depth(v))) return rc;
   if (int rc = ensure_host_form(v)) return rc;
@@ -991,24 +1016,26 @@ int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_st
       if (!v->d_rgb[s]) CU(cudaMalloc(&v->d_rgb[s], in_bytes));
   if (frame_stride == 0) frame_stride = in_bytes;
   if (frame_stride < in_bytes) return fail(ADDER_ERR_BAD_PARAMS, "frame_stride smaller than a frame");
-  if (n_out) *n_out = 0;
-  if (frames_done) *frames_done = 0;
   CU(cudaStreamSynchronize(v->stream)); /* setters queued on the main stream come first */
 
   uint64_t written = 0; /* in units */
-  uint32_t submitted = 0, delivered = 0;
+  /* Frame f of this call uses ring slot (slot0 + f) % kRing; the pending frames of the previous call are frames
+   * 0 .. pend_n-1 of this one and already sit in their slots, kernels finished. */
+  const uint32_t slot0 = v->pend_n ? v->pend_slot0 : 0u;
+  uint32_t submitted = v->pend_n, delivered = 0;
+  v->pend_n = 0;
   int rc_final = ADDER_OK;
-  /* Frame f uses ring slot f % kRing.  Its kernel waits for its H2D copy (ev_in) and for the D2H
-   * copy that last used the slot (ev_out); its D2H copy is issued once the host knows the count. */
+  /* Frame f's kernel waits for its H2D copy (ev_in) and for the D2H copy that last used the slot (ev_out); its D2H
+   * copy is issued once the host knows the count. */
   auto deliver = [&](uint32_t f) -> int {
-    const int s = f % kRing;
+    const int s = (int)((slot0 + f) % kRing);
     CU(cudaEventSynchronize(v->ev_k[s]));
     const uint32_t* off = v->h_chunk_off[s];
     const uint64_t total = off[v->n_chunks];
     const uint64_t need = raw ? total * unit : total;
     if (written + need > out_cap)
-      return fail(ADDER_ERR_CAPACITY, "output holds %zu %s; frame %u needs %llu more than fit", out_cap, raw ? "bytes" : "records", f,
-                  (unsigned long long)(written + need - out_cap));
+      return fail(ADDER_ERR_CAPACITY, "output holds %zu %s; frame %u needs %llu more than fit (its events are kept: call again from frames_done)",
+                  out_cap, raw ? "bytes" : "records", f, (unsigned long long)(written + need - out_cap));
     if (total) {
       const void* src = raw ? (const void*)v->d_raw[s] : (const void*)v->d_events[s];
       CU(cudaMemcpyAsync((uint8_t*)out + written * (raw ? 1 : unit), src, total * unit, cudaMemcpyDeviceToHost, v->stream_out));
@@ -1019,16 +1046,8 @@ int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_st
     written += need;
     return ADDER_OK;
   };
-
-  for (uint32_t f = 0; f < n_frames; f++) {
-    const int s = f % kRing;
-    if (f >= (uint32_t)kRing) { /* the slot's previous tenant must be delivered before it is reused */
-      if (int rc = deliver(f - kRing)) {
-        rc_final = rc;
-        break;
-      }
-      delivered++;
-    }
+  auto submit = [&](uint32_t f) -> int {
+    const int s = (int)((slot0 + f) % kRing);
     CU(cudaStreamWaitEvent(v->stream_in, v->ev_k[s], 0)); /* previous kernel on this slot has read its frame */
     CU(cudaMemcpyAsync(rgb_in(v) ? v->d_rgb[s] : v->d_frame[s], frames + (size_t)f * frame_stride, in_bytes, cudaMemcpyHostToDevice,
                        v->stream_in));
@@ -1045,20 +1064,31 @@ int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_st
     CU(cudaMemcpyAsync(v->h_chunk_off[s], v->d_chunk_off[s], ((size_t)v->n_chunks + 1) * sizeof(uint32_t),
                        cudaMemcpyDeviceToHost, v->stream));
     CU(cudaEventRecord(v->ev_k[s], v->stream));
-    submitted++;
+    return ADDER_OK;
+  };
+
+  for (uint32_t f = submitted; f < n_frames && rc_final == ADDER_OK; f++) {
+    while (rc_final == ADDER_OK && submitted - delivered >= (uint32_t)kRing) { /* the slot's previous tenant goes first */
+      if (int rc = deliver(delivered)) rc_final = rc; else delivered++;
+    }
+    if (rc_final != ADDER_OK) break;
+    if (int rc = submit(f)) rc_final = rc; else submitted++;
   }
   while (rc_final == ADDER_OK && delivered < submitted) {
-    if (int rc = deliver(delivered)) {
-      rc_final = rc;
-      break;
-    }
-    delivered++;
+    if (int rc = deliver(delivered)) rc_final = rc; else delivered++;
   }
-  CU(cudaStreamSynchronize(v->stream_out));
-  CU(cudaStreamSynchronize(v->stream));
+  /* every path drains the three streams: no copy into the caller's buffers is in flight when the call returns */
+  cudaError_t e1 = cudaStreamSynchronize(v->stream_in), e2 = cudaStreamSynchronize(v->stream), e3 = cudaStreamSynchronize(v->stream_out);
   v->last_slot = -1;
   if (n_out) *n_out = written;
   if (frames_done) *frames_done = delivered;
+  if (rc_final == ADDER_ERR_CAPACITY && delivered < submitted) { /* integrated, not delivered: kept for the resuming call */
+    v->pend_n = submitted - delivered;
+    v->pend_slot0 = (slot0 + delivered) % kRing;
+    v->pend_raw = raw;
+  }
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+    return fail(ADDER_ERR_CUDA, "draining the streams: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
   if (int rc = collect_errors(v, v->stream)) return rc;
   return rc_final;
 }
@@ -1155,6 +1185,7 @@ int adder_b200_video_integrate_frames_device(adder_b200_video* v, const uint8_t*
                                              size_t events_stride, uint32_t* d_chunk_offsets) {
   return guarded([&]() -> int {
     if (!v || (!d_frames && n_frames) || (!d_events && events_stride)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (v->pend_n) return fail(ADDER_ERR_BAD_PARAMS, "%u frames integrated by integrate_frames_host are waiting to be delivered: resume that call first", v->pend_n);
     if (int rc = set_device(v)) return rc;
     if (frame_stride == 0) frame_stride = in_frame_bytes(v);
     /* a colour source feeding a gray transcode is converted into a scratch run of gray frames first (up to 512 MB of

@@ -32,17 +32,6 @@ class NoData(SourceError):
     """The frame source is exhausted (the reference surfaces the decoder's EOF error)."""
 
 
-def handle_color(frame: np.ndarray, color: bool) -> np.ndarray:
-    """utils/cv.rs:215-232: gray = (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in f64, truncating.
-    Host-side statement of the formula for callers that want the gray frame without a Video; `Framed`
-    itself runs the conversion on the device (adder_b200_video_set_source_channels)."""
-    if color:
-        return frame
-    f = frame.astype(np.float64)
-    g = f[..., 0] * 0.114 + f[..., 1] * 0.587 + f[..., 2] * 0.299
-    return np.clip(np.trunc(g), 0, 255).astype(np.uint8)[..., None]
-
-
 class Framed:
     def __init__(self, frames: Iterable[np.ndarray], width: int, height: int, color_input: bool,
                  source_fps: float = 30.0, frame_count: Optional[int] = None, device: int = 0, max_depth: int = 0):

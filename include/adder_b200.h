@@ -222,9 +222,12 @@ int adder_b200_video_events_emitted(adder_b200_video* v, uint64_t* out);
  *   frame_counts     n_frames entries: events of each frame                          [host, may be NULL]
  *   chunk_counts     n_frames * n_chunks entries                                     [host, may be NULL]
  *   n_events         total
- * Unlike the single-frame call this one cannot keep a frame's events for a retry: when
- * `events_cap` is too small it stops BEFORE integrating the first frame that does not fit, returns
- * ADDER_ERR_CAPACITY and reports in *frames_done how many frames were integrated and delivered. */
+ * When `events_cap` is too small the call returns ADDER_ERR_CAPACITY and reports in *frames_done how many frames
+ * were delivered (frame_counts / chunk_counts / events_out are valid for those).  Up to three further frames may
+ * already have been integrated (the pipeline's depth); their events are kept in the handle and the frames are not
+ * integrated twice: call again with frames + frames_done * frame_stride and n_frames - frames_done — the same
+ * frames — and a buffer with room; that call first delivers the kept frames, then goes on integrating.  Until then
+ * integrate_matrix / integrate_frames_device fail with ADDER_ERR_BAD_PARAMS; reset_state drops the kept events. */
 int adder_b200_video_integrate_frames_host(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
                                            uint32_t n_frames, float time_spanned, adder_event_t* events_out,
                                            size_t events_cap, uint64_t* frame_counts, uint32_t* chunk_counts,

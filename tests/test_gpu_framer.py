@@ -129,7 +129,9 @@ def test_simulproc_mirror_writes_the_oracle_pipeline_frames_and_stream(tmp_path)
     src = A.Framed(list(rgb), w, h, color_input=False, source_fps=24.0)
     src = src.crf(2).auto_time_parameters(255, 255 * 8, None).write_out(A.TIME_ABSOLUTE_T, A.MULTI_COLLAPSE)
     frames_io, raw_io = io.BytesIO(), io.BytesIO()
-    sp = A.SimulProcessor(src, 255, frames_io, raw_output=raw_io, ring_frames=200)
+    from tools.simulproc_mirror import SimulProcessor
+
+    sp = SimulProcessor(src, 255, frames_io, raw_output=raw_io, ring_frames=200)
     assert sp.run() == nf
     # the oracle, step by step
     ov = O.Video(w, h, 1, O.MODE_FRAME_PERFECT)

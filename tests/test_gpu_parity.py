@@ -200,12 +200,10 @@ def test_framed_source_mirror():
     assert ov.time_parameters(int(255 * 24), 255, 6120, None)
     ov.write_out(O.TIME_DELTA_T, O.MULTI_NORMAL)
     ov.set_crf_parameters(0, 0, 10)
-    from adder_codec_rs_b200.framed import handle_color
-
     for f in range(1, 30):
         chunks = src.consume()
         assert len(chunks) == h  # chunk_rows 1 -> one Vec<Event> per row (driver.rs:566)
-        eo, co = ov.integrate_matrix(handle_color(rgb[f], False), 255.0)
+        eo, co = ov.integrate_matrix(O.handle_color(rgb[f]), 255.0)
         assert np.concatenate(chunks).tobytes() == eo.tobytes()
         assert [len(c) for c in chunks] == list(co)
     with pytest.raises(Exception):
@@ -437,3 +435,57 @@ def test_feature_detection_is_refused_on_a_row_band():
     with pytest.raises(A.AdderError) as e:
         gv.integrate_matrix(np.zeros((16, 32, 1), np.uint8), 255.0)
     assert e.value.code == B.ERR_UNSUPPORTED
+
+
+def test_host_form_resumes_after_a_full_output_buffer():
+    """events_cap too small in the middle of a batch.  The call reports the frames it delivered; the frames the
+    pipeline had already integrated are neither lost nor integrated twice: resuming from frames_done yields the oracle's
+    stream for every frame, and the state agrees at the end."""
+    case = cases.CASES_BY_NAME["cfg2_rgb_noise_crf3"]
+    gv, ov = _pair(case)
+    frames = case.frames()
+    exp = [ov.integrate_matrix(frames[f], case.time)[0] for f in range(case.n_frames)]
+    sizes = [len(e) for e in exp]
+    small = np.empty(sum(sizes[:7]) + sizes[7] // 2, dtype=A.EVENT_DTYPE)  # room for 7 frames and a half
+    got, f0, calls = [], 0, 0
+    while f0 < case.n_frames:
+        ev, fc, cc, done = gv.integrate_frames_host(frames[f0:], case.time, small, partial=True)
+        calls += 1
+        assert done >= 1, "no progress"
+        assert [int(x) for x in fc] == sizes[f0:f0 + done]
+        got.append(ev.copy())
+        f0 += done
+        if calls == 1:  # the kept frames block the other entry points until the call is resumed
+            assert done == 7
+            with pytest.raises(A.AdderError) as e:
+                gv.integrate_matrix(frames[0], case.time)
+            assert e.value.code == A.ERR_BAD_PARAMS
+    assert calls >= 3
+    assert np.concatenate(got).tobytes() == np.concatenate(exp).tobytes()
+    n = case.w * case.h * case.c
+    _assert_state_equal(gv, ov, n, step=3)
+    assert gv.info().in_interval_count == ov.in_interval_count
+
+
+def test_normal_mode_long_static_run_needs_no_depth_hint():
+    """ADVICE r1: PixelMultiMode::Normal never pops the root again after the first Δt_max pop, so a static pixel's stack
+    keeps growing past what delta_t_max / ref_time suggests (11-13 live nodes after 5000 frames at dtm = ref).  The
+    handle derives the depth from the mode: no ADDER_ERR_ARENA_DEPTH, and the oracle's events."""
+    w, h, nf, batch = 24, 8, 5000, 500
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 256, (h, w, 1)).astype(np.uint8)
+    gv = A.Video(w, h, 1)
+    ov = O.Video(w, h, 1, O.MODE_FRAME_PERFECT)
+    for v in (gv, ov):
+        assert v.time_parameters(255 * 30, 255, 255, None)  # dtm = ref: the shallowest derived depth
+        v.write_out(None, O.MULTI_NORMAL)
+    frames = np.broadcast_to(base[None], (batch, h, w, 1)).copy()
+    buf = np.empty(w * h * 4 * batch, dtype=A.EVENT_DTYPE)
+    for f0 in range(0, nf, batch):
+        ev, fc, cc = gv.integrate_frames_host(frames, 255.0, buf)
+        exp = [ov.integrate_matrix(base, 255.0)[0] for _ in range(batch)]
+        assert [int(x) for x in fc] == [len(e) for e in exp]
+        assert ev.tobytes() == np.concatenate(exp).tobytes()
+    deepest = max(ov.px(i).length for i in range(w * h))
+    assert deepest >= 11, deepest
+    _assert_state_equal(gv, ov, w * h)

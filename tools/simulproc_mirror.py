@@ -1,4 +1,7 @@
-"""SimulProcessor — host-side mirror of the reference's transcode-and-frame driver
+"""TEST DRIVER, not part of the product package (SURVEY.md §2 #17 marks the reference's SimulProcessor out of scope):
+used by tests/test_gpu_framer.py to run the transcoder and the framer in lock step the way the reference's caller does.
+
+SimulProcessor — host-side mirror of the reference's transcode-and-frame driver
 (adder-codec-rs/src/utils/simulproc.rs:87-278): a `Framed` source feeds the INSTANTANEOUS framer frame by frame and
 the reconstructed frames are written out as they fill.  Both halves run on the device; between them the events stay in
 HBM (the reference hands a Vec<Vec<Event>> across an mpsc channel, simulproc.rs:235).  Optionally the raw .adder
@@ -10,18 +13,21 @@ from typing import BinaryIO, Optional
 
 import numpy as np
 
-from . import binding as B
-from .framed import Framed, NoData, RawAdderWriter
+from adder_codec_rs_b200 import binding as B
+from adder_codec_rs_b200.framed import Framed, NoData, RawAdderWriter
 
 
 class SimulProcessor:
     def __init__(self, source: Framed, ref_time: int, output: BinaryIO, frame_max: int = 0, codec_version: int = 3,
-                 time_mode: int = B.TIME_ABSOLUTE_T, view_mode: int = B.VIEW_INTENSITY, raw_output: Optional[BinaryIO] = None,
+                 time_mode: Optional[int] = None, view_mode: int = B.VIEW_INTENSITY, raw_output: Optional[BinaryIO] = None,
                  ring_frames: int = 0):
         """SimulProcessor::new, simulproc.rs:113-225."""
         self.source = source
         self.video = source.get_video_ref()
         info = self.video.info()
+        if time_mode is None:  # the framer must read the stream in the time mode the transcoder writes it in
+            time_mode = info.time_mode
+        assert time_mode == info.time_mode, "the framer's time mode must be the source video's"
         reconstructed_frame_rate = source.source_fps
         # For instantaneous reconstruction the frame rate must match the source rate (simulproc.rs:142-146)
         assert info.tps // ref_time == int(reconstructed_frame_rate), "tps / ref_time must equal the source frame rate"
@@ -34,7 +40,7 @@ class SimulProcessor:
         self.raw = RawAdderWriter(raw_output, self.video, codec_version) if raw_output is not None else None
         self._P_out = info.width * info.height * info.channels
         self._d_frame = self.video.device_alloc(info.width * info.height * max(3, info.channels))  # a colour source may feed a gray transcode
-        self._cap = self._P_out * 4
+        self._cap = self._P_out * (info.max_depth + 2)  # the library's worst case: 1 + max(L, 2) + 1 events per pixel per frame
         self._d_events = self.video.device_alloc(self._cap * 12)
         self._d_off = self.video.device_alloc((info.n_chunks + 1) * 4)
         self._d_raw = self.video.device_alloc(self._cap * 11) if self.raw else None
