@@ -246,6 +246,12 @@ class DeviceBuffer:
             _check(self.video.L.adder_b200_copy_to_host(self.video.v, out.ctypes.data, self.p.value + offset, nbytes))
         return out.view(dtype)
 
+    def to_host_into(self, out: np.ndarray, nbytes, offset=0):
+        """Copy into an existing (e.g. page-locked) host array."""
+        assert out.flags.c_contiguous and out.nbytes >= nbytes
+        if nbytes:
+            _check(self.video.L.adder_b200_copy_to_host(self.video.v, out.ctypes.data, self.p.value + offset, nbytes))
+
     def from_host(self, arr: np.ndarray, offset=0):
         arr = np.ascontiguousarray(arr)
         _check(self.video.L.adder_b200_copy_to_device(self.video.v, self.p.value + offset, arr.ctypes.data, arr.nbytes))

@@ -1338,7 +1338,8 @@ int adder_b200_synth_frames(adder_b200_video* v, uint8_t* d_frames, size_t frame
   if (frame_stride == 0) frame_stride = v->P;
   const uint32_t blocks = (v->P + 255) / 256;
   for (uint32_t f = 0; f < n_frames; f++) {
-    adder::synth_frame_kernel<<<blocks, 256, 0, v->stream>>>(d_frames + (size_t)f * frame_stride, v->P, v->w, v->c, f0 + f, kind, seed);
+    adder::synth_frame_kernel<<<blocks, 256, 0, v->stream>>>(d_frames + (size_t)f * frame_stride, v->P, v->w, v->c, f0 + f, kind, seed,
+                                                             v->row0 * (uint32_t)v->w * v->c);
     v->launches++;
   }
   CU(cudaGetLastError());

@@ -122,6 +122,14 @@ struct GlobalNodes {
   }
   __device__ __forceinline__ void used_preloaded() { n_loads++; }
   __device__ __forceinline__ void unused_load() { n_loads--; }
+  /* px_frame falls back to px_step: root and level 1 again, as they are in memory (nothing has been stored yet) */
+  __device__ __forceinline__ void reload(Node& n0, Node& n1) {
+    const uint4 a = ld_state<kCoherent>(p), b = ld_state<kCoherent>(p + stride);
+    n0.integ = __uint_as_float(a.x), n0.dt = __uint_as_float(a.y), n0.best_dt = __uint_as_float(a.z), n0.w = a.w;
+    n1.integ = __uint_as_float(b.x), n1.dt = __uint_as_float(b.y), n1.best_dt = __uint_as_float(b.z), n1.w = b.w;
+    n_loads = 1u; /* the root; level 1 counts when px_step uses it */
+    n_stores = 0u;
+  }
 };
 
 /*
@@ -151,6 +159,8 @@ struct EventPark {
     }
     n++;
   }
+  __device__ __forceinline__ uint32_t mark() const { return n; }
+  __device__ __forceinline__ void rewind(uint32_t m) { n = m; overflow = 0; }
   __device__ __forceinline__ void get(uint32_t e, uint32_t& dd, uint32_t& tt) const {
     if (e < S) {
       tt = t[e * tile_px];
@@ -202,6 +212,12 @@ constexpr uint32_t kWarps = kThreads / 32;
 #endif
 #ifndef ADDER_MIN_CTAS
 #define ADDER_MIN_CTAS 4
+#endif
+#ifndef ADDER_LEAN
+#define ADDER_LEAN 0 /* 1: px_frame (short path + fallback) instead of px_step; measured slower in this kernel (profiles/r02a_ab.txt) */
+#endif
+#ifndef ADDER_ROW_RUNS
+#define ADDER_ROW_RUNS 0 /* 1: every warp works on a contiguous run of rows of the tile instead of every eighth row */
 #endif
 __host__ __device__ constexpr uint32_t tile_rows(uint32_t R) { return 8u * R - 2u * ADDER_DUTY_LESS; }
 __host__ __device__ constexpr uint32_t tile_px(uint32_t R) { return 32u * tile_rows(R); }
@@ -339,7 +355,14 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   auto frame_of = [&](uint32_t k) { return !kMulti ? 0u : a.tiles_magic ? mulhi_u32_u64(k, a.tiles_magic) : k; };
   auto status_row = [&](uint32_t fi) { return !kMulti ? a.tile_status : a.tile_status + (unsigned long long)(fi & (a.status_ring - 1u)) * a.n_tiles; };
   /* this warp's row of round r, and the tile-relative index of this thread's pixel in it */
+#if ADDER_ROW_RUNS
+  /* a warp's rows are one contiguous run of the tile (warps 0/1: R - 1 rows each, then R rows per plain warp): the pixel
+   * index, and with it every state / park address, advances by a constant from one row to the next */
+  const uint32_t row0w = duty ? warp * ((uint32_t)R - ADDER_DUTY_LESS) : 2u * ((uint32_t)R - ADDER_DUTY_LESS) + (warp - 2u) * (uint32_t)R;
+  auto row_of = [&](uint32_t r) { return row0w + r; };
+#else
   auto row_of = [&](uint32_t r) { return r + 1u < (uint32_t)R ? 8u * r + warp : 8u * ((uint32_t)R - 1u) + warp - 2u * ADDER_DUTY_LESS; };
+#endif
 
   /* tiles are handed out in ticket order so that a tile's predecessors are always held by CTAs that
    * are already running: the look-back can then never wait on a CTA that has not been scheduled. */
@@ -452,7 +475,11 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           const Node n0{__uint_as_float(n0raw.x), __uint_as_float(n0raw.y), __uint_as_float(n0raw.z), n0raw.w};
           const Node n1{__uint_as_float(n1raw.x), __uint_as_float(n1raw.y), __uint_as_float(n1raw.z), n1raw.w};
           uint8_t disp;
+#if ADDER_LEAN /* A/B: the short path of px_frame in front of the general state machine */
+          const bool show = px_frame(px, samples[r * 32u + lane], h, n0, n1, mem, park, errbits, &disp);
+#else
           const bool show = px_step(px, samples[r * 32u + lane], h, n0, n1, mem, park, errbits, &disp);
+#endif
           a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
 #if ADDER_EV_STREAM >= 2
           if (show) __stcs(a.running + i, disp);

@@ -411,4 +411,168 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
   return false;
 }
 
+
+/*
+ * px_frame — what the kernel calls: the common cases of px_step on a short path, everything else through px_step.
+ *
+ * px_step serves every corner of the reference's state machine in one body (arena shift on a Δt_max pop, Collapse after
+ * a pop, synthesised and zero events ...) and pays for that generality in every level of every pixel: the profile of
+ * round 1 shows ~95 instructions per node level, most of them address re-computation, register moves and the branches
+ * that select among the rare variants (profiles/r01n_*).  The short path covers a pixel-frame in which
+ *   - the pixel is not in the "Collapse after a Δt_max pop" regime (popped_dtm && Collapse: :249-265, :360-362), and
+ *   - integrating the root does not raise need_to_pop_top (:394-396), i.e. no pop_top_event this frame,
+ * which is every pixel-frame of a noise / jitter / static workload except the one frame per delta_t_max in which an
+ * unchanged pixel pops its root.  Under these conditions the reference's frame is: [changed: pop_best_events over all
+ * nodes, the tail becomes the root (:267-270)]; integrate nodes 0, 1, ... until the first one fires, give it a fresh child
+ * and drop the rest (:340-390, FramePerfect :366).  The firing node's arithmetic (the division) is done once, after the
+ * walk, by all lanes of a warp together instead of inside the divergent level loop.
+ *
+ * The short path decides whether it applies BEFORE its first state store; if not, the events it parked are rewound
+ * (Sink::rewind) and px_step runs from the untouched state (Mem::reload re-reads the header's nodes: nothing was stored).
+ */
+template <class Mem, class Sink>
+ADDER_HD bool px_frame(const PxParams& a, uint32_t v, PxHeader& h, const Node& n0_in, const Node& n1_in, Mem& mem, Sink& sink,
+                       uint32_t& errbits, uint8_t* disp) {
+  const uint32_t hy = h.y;
+  uint32_t len = HDR_LENGTH(hy);
+  const uint32_t popped_in = HDR_POPPED(hy);
+  bool lean = !(popped_in && a.collapse);
+  if (lean) {
+    mem.prefetch_levels(len);
+    const float intensity = (float)v;
+    const float time = a.time;
+    float lf = h.lf;
+    uint32_t base = HDR_BASE(hy), cth = HDR_CTHRESH(hy), cnt = HDR_COUNTER(hy);
+    uint32_t popped = popped_in;
+    const uint32_t d_i = get_d_from_intensity(intensity); /* the d of a fresh node, :332-335 / :502-514 */
+    const uint32_t lo = base > cth ? base - cth : 0u;
+    const uint32_t hi = base + cth > 255u ? 255u : base + cth;
+    const auto mark = sink.mark();
+    Node cur = n0_in;
+    bool root_new = false;
+    if (v < lo || v > hi) { /* video.rs:1338-1358 -> pop_best_events :213-287, the plain arm */
+      pop_node(a, sink, lf, cur);
+      if (len > 1u) {
+        mem.used_preloaded();
+        cur = n1_in;
+        pop_node(a, sink, lf, cur);
+        for (uint32_t k = 2; k < len; k++) {
+          cur = mem.load(k);
+          pop_node(a, sink, lf, cur);
+        }
+      }
+      len = 1; /* :267-270: the tail (in cur) is the new root */
+      popped = 0;
+      base = v;
+      root_new = true;
+    }
+    /* ---- integrate (:317-413): walk the levels up to the first node that fires -------------------------------- */
+    /* node 0 */
+    uint32_t w = cur.w;
+    if (len == 1u && cur.dt == 0.0f && cur.integ == 0.0f) w = (w & ~0xFFu) | d_i;
+    float sum = rn_add(cur.integ, intensity);
+    bool fire = sum >= d_shift_f32(NODE_D(w));
+    uint32_t kf = 0;
+    bool have_fire = fire;
+    uint32_t dtm_reached = 0;
+    bool disp_has = false;
+    uint32_t disp_d = 0;
+    float disp_dt = 0.0f;
+    if (!fire) {
+      cur.integ = sum;
+      cur.dt = rn_add(cur.dt, time);
+      cur.w = w;
+      dtm_reached = cur.dt >= a.dtm_f ? 1u : 0u;
+      if (NODE_D(w) == ADDER_D_MAX || (dtm_reached && !popped)) {
+        lean = false; /* pop_top_event this frame */
+      } else {
+        mem.store(0, cur);
+        if (NODE_HAS_BEST(w)) {
+          disp_has = true;
+          disp_d = NODE_BEST_D(w);
+          disp_dt = cur.best_dt;
+        }
+        if (len > 1u) {
+          mem.used_preloaded();
+          cur = n1_in;
+          for (uint32_t k = 1;;) {
+            Node nxt = cur;
+            if (k + 1u < len) nxt = mem.load(k + 1u);
+            w = cur.w;
+            if (k == len - 1u && cur.dt == 0.0f && cur.integ == 0.0f) w = (w & ~0xFFu) | d_i;
+            sum = rn_add(cur.integ, intensity);
+            if (sum >= d_shift_f32(NODE_D(w))) {
+              kf = k;
+              have_fire = true;
+              if (k + 1u < len) mem.unused_load();
+              break;
+            }
+            cur.integ = sum;
+            cur.dt = rn_add(cur.dt, time);
+            cur.w = w;
+            mem.store(k, cur);
+            if (++k == len) break;
+            cur = nxt;
+          }
+        }
+      }
+    }
+    uint32_t new_len = len;
+    if (lean && have_fire) {
+      /* integrate_main's firing arm (:424-466) for the node in cur / w / sum, once per pixel */
+      const uint32_t d_old = NODE_D(w);
+      const uint32_t nd = get_d_from_intensity(sum);
+      float prop = rn_div(rn_sub(d_shift_f32(nd), cur.integ), intensity);
+      if (nd == ADDER_D_ZERO_INTEGRATION || d_old == ADDER_D_ZERO_INTEGRATION || intensity < 1.1920929e-07f) prop = 1.0f;
+      cur.best_dt = rn_add(cur.dt, rn_mul(time, prop));
+      uint32_t d_after = nd;
+      if (nd < ADDER_D_MAX) {
+        cur.integ = sum;
+        cur.dt = rn_add(cur.dt, time);
+        d_after = nd + 1u;
+      }
+      cur.w = NODE_PACK(d_after, nd, 1);
+      if (kf == 0u) {
+        dtm_reached = cur.dt >= a.dtm_f ? 1u : 0u;
+        if (d_after == ADDER_D_MAX || (dtm_reached && !popped)) lean = false; /* pop_top_event this frame */
+        root_new = true;
+        disp_has = true;
+        disp_d = nd;
+        disp_dt = cur.best_dt;
+      }
+      if (lean) {
+        mem.store(kf, cur);
+        if (kf + 1u < a.depth) mem.store(kf + 1u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+        new_len = kf + 2u;
+        if (new_len > a.depth) new_len = a.depth;
+      }
+    }
+    if (lean) {
+      if (cth < a.c_max) { /* :402-412 */
+        if (cnt >= a.vel_m1) {
+          cth = cth + 1u > 255u ? 255u : cth + 1u;
+          cnt = 0;
+        } else {
+          cnt = cnt + a.cnt_inc > 255u ? 255u : cnt + a.cnt_inc;
+        }
+      }
+      h.lf = lf;
+      h.y = HDR_PACK(base, cth, cnt, new_len, dtm_reached, popped);
+      if (disp_has && a.display && (root_new || a.display == 2u || a.view_mode == 3u)) {
+        *disp = frame_value_u8(a, disp_d, f2u(disp_dt), lf);
+        return true;
+      }
+      return false;
+    }
+    sink.rewind(mark); /* nothing was stored: start over on the general path */
+  }
+#ifdef ADDER_LEAN_ONLY /* experiment: the cost of the short path alone (pixels that need px_step are flagged, not served) */
+  errbits |= ADDER_DEVERR_INTERNAL;
+  return false;
+#endif
+  Node n0 = n0_in, n1 = n1_in;
+  mem.reload(n0, n1);
+  return px_step(a, v, h, n0, n1, mem, sink, errbits, disp);
+}
+
 }  // namespace adder

@@ -40,9 +40,11 @@ __host__ __device__ inline uint8_t synth_value(int kind, uint64_t seed, uint32_t
   }
 }
 
-__global__ void synth_frame_kernel(uint8_t* out, uint32_t P, uint32_t W, uint32_t C, uint32_t f, int kind, uint64_t seed) {
+/* i0: flat index of the plane's first sample inside the whole frame (a row band starts at row0 * W * C), so that a band
+ * gets exactly the rows of the undivided frame */
+__global__ void synth_frame_kernel(uint8_t* out, uint32_t P, uint32_t W, uint32_t C, uint32_t f, int kind, uint64_t seed, uint32_t i0) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P) out[i] = synth_value(kind, seed, f, i, W, C);
+  if (i < P) out[i] = synth_value(kind, seed, f, i + i0, W, C);
 }
 
 }  // namespace adder

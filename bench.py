@@ -1,26 +1,31 @@
 #!/usr/bin/env python
 """bench.py — framed→ADΔER transcode throughput (Mpixels/s) on B200, beside the CPU path.
 
-Workload (BASELINE.json configs[1]): 1920x1080 RGB 8-bit synthetic uniform noise, 300 frames,
-crf 3 (c_thresh baseline 2 / max 7 / velocity 7), ref_time 255, delta_t_max 7650, FramePerfect,
-PixelMultiMode::Collapse, TimeMode::AbsoluteT, chunk_rows 1, fresh pixel state at the start of every
-step.  One step = the whole 300-frame sequence through the hot path (adder_b200_video_integrate_frames_device:
-one persistent kernel launch for the 300 frames, the tail of each frame overlapping the head of the next).
-At N GPUs the frame is N row bands of 1080 rows (weak scaling: each rank permanently owns one band's
-state); there is no data-path collective — rank-order concatenation of the bands'
-event streams is the reference's raster order.
+Headline workload (BASELINE.json configs[4], the largest single-GPU configuration and the one north_star's scaling
+target is quoted on): 7680x4320 gray 8-bit, 2000 frames, static scene with rare one-frame changes (p = 2/256 per pixel
+per frame, SURVEY.md §8(d) cfg 5), ref_time 256, delta_t_max 2^20 (long-integration mode), crf 3, FramePerfect /
+Collapse / AbsoluteT, chunk_rows 1, fresh pixel state at the start of every step.  One step = the whole 2000-frame
+sequence through the hot path.  STRONG scaling: at N GPUs the one 8K frame is split into N row bands (sharding.band_of,
+SURVEY.md §8(e)); rank g permanently owns band g's pixel state; rank-order concatenation of the bands' event streams is
+the reference's raster order.
 
-  value     device-resident: frames already in HBM, events left in HBM, CUDA-event timed.
-  e2e       the same step through adder_b200_video_integrate_frames_host: pinned HOST frames in,
-            all events out to pinned HOST memory, copies inside the timed region.
-  roofline  algorithmic bytes of the integrate kernel (counted exactly by the instrumented twin of
-            the kernel in an untimed pass) / CUDA-event time of the timed region.
-  cpu_baseline  the C oracle (a port: the Rust reference cannot be built here) on the host cores,
-            on a bounded sample of the same workload.
+  value     device-resident: frames already in HBM, events left in HBM (adder_b200_video_integrate_frames_device:
+            one persistent kernel launch per run of 250 frames), CUDA-event timed on the launching stream, max over ranks.
+  e2e       the same step through adder_b200_video_integrate_frames_host: pinned HOST frames in, all events out to
+            pinned HOST memory, copies inside the timed region.
+  gather    (N > 1) the same step with the whole frame's events delivered in raster order into ONE consumer rank's
+            HBM after every frame (the exchange step a single downstream encoder needs, video.rs:736-740).
+  roofline  algorithmic bytes of the integrate kernel (counted exactly by the instrumented twin of the kernel in an
+            untimed pass) / CUDA-event time of the timed region; traffic = DRAM bytes measured in this
+            run by an `ncu --metrics dram__bytes_*` side pass over a short launch of the same workload.
+  workloads (N = 1) the other BASELINE configs on the same kernel: cfg 1, cfg 2, cfg 3 for every c_thresh 0..10, cfg 4.
+  cpu_baseline  the C oracle (a port: the Rust reference cannot be built here) on the host cores, bounded sample.
 
-`--impl reference` times that CPU port alone, all host threads, on the same config.
+`--impl reference` times that CPU port alone, all host cores, on the same config.
 """
 import argparse
+import csv
+import io
 import json
 import os
 import subprocess
@@ -33,11 +38,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-W, H, C, NF = 1920, 1080, 3, 300
-REF, DTM, CRF = 255, 7650, 3
-KIND_NOISE, SEED = 1, 0xADDE5
+KIND_GRADIENT, KIND_NOISE, KIND_JITTER, KIND_STATIC = 0, 1, 2, 3
+SEED = 0xADDE5
 METRIC = "Mpixels/s framed->ADDER transcode (bit-exact events)"
-WORKLOAD = "1920x1080 RGB 8-bit synthetic noise, 300 frames, crf 3 (c 2..7, velocity 7), ref 255, dtm 7650, FramePerfect/Collapse/AbsoluteT"
+
+# the headline: BASELINE configs[4]
+W, H, C, NF = 7680, 4320, 1, 2000
+REF, DTM, CRF = 256, 1 << 20, 3
+WORKLOAD = ("7680x4320 gray 8-bit synthetic static scene + rare one-frame changes (p=2/256), 2000 frames, crf 3 (c 2..7, velocity 7), "
+            "ref 256, dtm 2^20, FramePerfect/Collapse/AbsoluteT; one frame strong-scaled over N row bands")
+BATCH = 250        # frames per integrate launch (events of one batch stay in HBM until the next batch overwrites them)
+EV_PER_PX = 0.25   # event records per pixel per frame the device buffer holds (overflow is an error, not a silent drop)
 
 
 def env_int(k, d):
@@ -64,7 +75,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -102,8 +113,7 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # under load = the upper half of the samples (the sampler also sees the idle edges)
-        sm_sorted = sorted(sm)
+        sm_sorted = sorted(sm)  # under load = the upper half of the samples (the sampler also sees the idle edges)
         load = sm_sorted[len(sm_sorted) // 2:]
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
@@ -118,82 +128,230 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the integrate kernel from the committed ncu --set full capture, if any."""
-    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(p):
+# ---- measured-in-run DRAM traffic: an ncu side pass over a short launch of the same workload ------------------------
+
+def ncu_dram_bytes_per_px_frame(extra_args, frames, px_per_frame, timeout_s=240):
+    """Runs tools/profile_run.py under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (one pass, no replay) and
+    returns (dram bytes per px-frame of the last integrate launch, counted algorithmic bytes per px-frame of that same
+    launch) or None when ncu is not usable here."""
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+           "-k", "regex:integrate_frame", sys.executable, os.path.join(ROOT, "tools", "profile_run.py"), "--batch", "--count",
+           "--reps", "1", "--frames", str(frames)] + [str(x) for x in extra_args]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+    except Exception:
+        return None
+    if r.returncode != 0:
+        return None
+    rows = [row for row in csv.reader(io.StringIO(r.stdout)) if len(row) > 5]
+    hdr = next((row for row in rows if "Metric Name" in row), None)
+    if hdr is None:
+        return None
+    i_id, i_name, i_unit, i_val = hdr.index("ID"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    per_launch = {}
+    for row in rows:
+        if row is hdr or not row[i_name].startswith("dram__bytes"):
+            continue
         try:
-            return json.load(open(p))
-        except Exception:
-            return None
-    return None
+            per_launch.setdefault(int(row[i_id]), 0.0)
+            per_launch[int(row[i_id])] += float(row[i_val].replace(",", "")) * scale.get(row[i_unit], 1.0)
+        except ValueError:
+            continue
+    if not per_launch:
+        return None
+    dram = per_launch[max(per_launch)]  # the last launch: the timed rep (the first is the counting twin)
+    counted = None
+    for line in r.stdout.splitlines():
+        if line.startswith("counted:"):
+            counted = float(line.split()[1])
+    return dram / (px_per_frame * frames), counted
 
 
-def make_oracle_video(n_rows=H):
-    from oracle import oracle_py as O
+# ---- one device-resident workload -----------------------------------------------------------------------------------
 
-    ov = O.Video(W, n_rows, C, O.MODE_FRAME_PERFECT)
-    assert ov.time_parameters(REF * 30, REF, DTM, None)
-    ov.update_crf(CRF)
-    return ov, O
+class DeviceWorkload:
+    """A plane (or this rank's band of it), its frames resident in HBM, and the step that runs them through the hot path."""
+
+    def __init__(self, A, S, *, w, h, c, kind, frames, ref, dtm, crf=None, manual=None, multi=None, rank=0, world=1, device=0,
+                 batch=BATCH, ev_per_px=2.0, offsets=True):
+        self.A = A
+        self.w, self.c, self.kind, self.nf, self.ref = w, c, kind, frames, ref
+        self.crf, self.manual = crf, manual
+        self.row0, self.rows = S.band_of(h, 1, rank, world)
+        self.v = A.Video(w, self.rows, c, A.MODE_FRAME_PERFECT, device=device)
+        v = self.v
+        assert v.time_parameters(ref * 30, ref, dtm, None)
+        if multi is not None:
+            v.write_out(None, multi)
+        v.set_row_offset(self.row0)
+        self.P = w * self.rows * c
+        self.batch = min(batch, frames)
+        self.ev_stride = int(self.P * ev_per_px)
+        self.d_frames = v.device_alloc(self.P * frames)
+        v.synth_frames(self.d_frames, 0, frames, kind, SEED)  # a band gets its rows of the undivided frame
+        self.d_events = v.device_alloc(self.ev_stride * 12 * self.batch)
+        self.d_off = v.device_alloc((v.n_chunks + 1) * 4 * self.batch) if offsets else None
+        self.quality()
+        v.sync()
+
+    def quality(self):
+        if self.manual is not None:
+            c = self.manual
+            self.v.update_quality_manual(c, c, 30, 1, 0.0)  # SURVEY.md §8(d) cfg 3: quality_manual(c, c, 30, 1, 0.0)
+        elif self.crf is not None:
+            self.v.update_crf(self.crf)
+
+    def step(self):
+        v = self.v
+        v.reset_state()
+        self.quality()
+        for f0 in range(0, self.nf, self.batch):
+            n = min(self.batch, self.nf - f0)
+            v.integrate_frames_device(self.d_frames.ptr + f0 * self.P, self.P, n, float(self.ref), self.d_events.ptr, self.ev_stride,
+                                      self.d_off.ptr if self.d_off else None)
+
+    def count(self):
+        """One untimed step with the counting twin of the kernel: exact algorithmic bytes of the workload."""
+        v = self.v
+        v.set_counting(True)
+        self.step()
+        v.sync()
+        cnt = v.read_counters()
+        v.set_counting(False)
+        pxf = self.P * self.nf
+        alg = (1 + 8 + 8) * pxf + 16 * (cnt["node_loads"] + cnt["node_stores"]) + cnt["display_writes"] + 12 * cnt["events"]
+        return cnt, alg
+
+    def timed(self, steps, warmup, barrier=lambda: None, sampler=None):
+        v = self.v
+        for _ in range(warmup):
+            self.step()
+        v.sync()
+        barrier()
+        l0 = v.launch_count
+        if sampler:
+            sampler.mark_begin()
+        v.timer_start()
+        for _ in range(steps):
+            self.step()
+        ms = v.timer_stop()
+        if sampler:
+            sampler.mark_end()
+        v.sync()
+        barrier()
+        return ms, v.launch_count - l0
+
+    def free(self):
+        for b in (self.d_frames, self.d_events, self.d_off):
+            if b is not None:
+                b.free()
+        self.d_frames = self.d_events = self.d_off = None
+        self.v.close()
 
 
-def cpu_baseline_run(n_threads, budget_s, frames_fn, max_frames=NF):
-    """Times the oracle port on `n_threads` host threads over the first frames of the workload until
-    about budget_s seconds are spent.  Returns (Mpx/s, frames used, seconds)."""
-    ov, O = make_oracle_video()
-    P = W * H * C
+def survey_formula(cnt, pxf):
+    """SURVEY.md §8(d)'s planning formula on the same run: 1 + 2*(12 + 16*L) + 1[display] + 12*E."""
+    L_mean = (cnt["live_nodes_in"] + cnt["live_nodes_out"]) / (2.0 * pxf)
+    E_mean = cnt["events"] / pxf
+    return 1 + 2 * (12 + 16 * L_mean) + 1 + 12 * E_mean, L_mean, E_mean
+
+
+def run_side_workloads(A, S, args, peak):
+    """The other BASELINE configs on one GPU (VERDICT r1 task 2): value, counted bytes, roofline fraction each."""
+    out = []
+    specs = [("cfg1: 640x480 gray gradient, 30 frames, API defaults (c 10), dtm = ref 255, one frame per launch",
+              dict(w=640, h=480, c=1, kind=KIND_GRADIENT, frames=30, ref=255, dtm=255, batch=1, ev_per_px=4.0), 20, None),
+             ("cfg2: 1920x1080 RGB noise, 300 frames, crf 3, ref 255, dtm 7650",
+              dict(w=1920, h=1080, c=3, kind=KIND_NOISE, frames=300, ref=255, dtm=7650, crf=3, batch=300, ev_per_px=2.0), 3,
+              ["--w", 1920, "--h", 1080, "--c", 3, "--kind", 1, "--crf", 3, "--cap", 2])]
+    for c in range(11):
+        specs.append((f"cfg3: 3840x2160 gray jitter, 1000 frames, quality_manual(c={c}), ref 255, dtm 7650",
+                      dict(w=3840, h=2160, c=1, kind=KIND_JITTER, frames=1000, ref=255, dtm=7650, manual=c, batch=250, ev_per_px=2.0), 2,
+                      ["--w", 3840, "--h", 2160, "--c", 1, "--kind", 2, "--manual", c, "--cap", 2] if c in (0, 5, 10) or args.traffic == "all" else None))
+    specs.append(("cfg4: 3840x2160 RGB noise, 1000 frames, crf 3, ref 255, dtm 7650 (the whole plane on one GPU)",
+                  dict(w=3840, h=2160, c=3, kind=KIND_NOISE, frames=1000, ref=255, dtm=7650, crf=3, batch=100, ev_per_px=1.25), 2,
+                  ["--w", 3840, "--h", 2160, "--c", 3, "--kind", 1, "--crf", 3, "--cap", 1.25] if args.traffic == "all" else None))
+    jitter_frames = None
+    for name, kw, steps, ncu_args in specs:
+        nf = kw["frames"] if not args.frames else min(kw["frames"], args.frames)
+        kw = dict(kw, frames=nf)
+        traffic = None
+        if ncu_args is not None and args.traffic != "off":
+            traffic = ncu_dram_bytes_per_px_frame(ncu_args, 16, kw["w"] * kw["h"] * kw["c"])
+        wl = DeviceWorkload(A, S, **kw)
+        cnt, alg = wl.count()
+        ms, launches = wl.timed(steps, 1)
+        pxf = wl.P * nf
+        b_survey, L_mean, E_mean = survey_formula(cnt, pxf)
+        achieved = alg * steps / (ms * 1e-3) / 1e9
+        e = {"workload": name, "value": pxf * steps / (ms * 1e-3) / 1e6, "unit": "Mpx/s", "us_per_frame": ms * 1e3 / (steps * nf),
+             "frames": nf, "steps": steps, "launches": launches, "bytes_per_px_frame": alg / pxf, "achieved_gbs": achieved,
+             "frac": achieved / peak, "events_per_px_frame": E_mean, "live_nodes_mean": L_mean,
+             "survey_formula_bytes_per_px_frame": b_survey, "survey_formula_frac": b_survey * pxf * steps / (ms * 1e-3) / 1e9 / peak}
+        if traffic is not None:
+            e["dram_bytes_per_px_frame"] = traffic[0]
+            e["dram_over_counted"] = traffic[0] / traffic[1] if traffic[1] else None
+            e["traffic_source"] = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum side pass in this run, a 16-frame launch of the same plane from a fresh state"
+        out.append(e)
+        wl.free()
+        del wl
+    return out
+
+
+def oracle_video(O, w, h, c, ref, dtm, crf):
+    ov = O.Video(w, h, c, O.MODE_FRAME_PERFECT)
+    assert ov.time_parameters(ref * 30, ref, dtm, None)
+    ov.update_crf(crf)
+    return ov
+
+
+def cpu_baseline_run(O, n_threads, budget_s, max_frames, min_frames=2):
+    """Times the oracle port on `n_threads` host threads over the first frames of the headline workload (whole 8K plane,
+    fresh state) until about budget_s seconds are spent.  Returns (Mpx/s, frames used, seconds)."""
+    ov = oracle_video(O, W, H, C, REF, DTM, CRF)
     t_total, n = 0.0, 0
-    f = 0
-    while f < max_frames:
-        fr = frames_fn(f)
+    for f in range(max_frames):
+        fr = O.synth_frame(KIND_STATIC, SEED, f, W, H, C)
         t0 = time.perf_counter()
         ov.integrate_matrix_count_only(fr, float(REF), n_threads)
         t_total += time.perf_counter() - t0
         n += 1
-        f += 1
-        if t_total >= budget_s and n >= 4:
+        if t_total >= budget_s and n >= min_frames:
             break
-    return P * n / t_total / 1e6, n, t_total
+    return W * H * C * n / t_total / 1e6, n, t_total
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port, all host threads) on the same config."""
-    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    """--impl reference: the reference's CPU path (oracle port, all host cores) on the headline config."""
+    rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    from tests import synth
     from oracle import oracle_py as O
 
-    n_threads = O.max_threads()
-    sample_frames = 8
-    ov, _ = make_oracle_video()
+    n_threads = O.host_threads()  # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers
+    sample_frames = 2
+    ov = oracle_video(O, W, H, C, REF, DTM, CRF)
     P = W * H * C
-    cache = {}
-
-    def frame(f):
-        f = f % NF
-        if f not in cache:
-            cache[f] = synth.frame(KIND_NOISE, SEED, f, W, H, C)
-        return cache[f]
-
     f = 0
     for _ in range(args.warmup):
         for _ in range(sample_frames):
-            fr = frame(f)
-            ov.integrate_matrix_count_only(fr, float(REF), n_threads)
+            ov.integrate_matrix_count_only(O.synth_frame(KIND_STATIC, SEED, f, W, H, C), float(REF), n_threads)
             f += 1
-    pre = [frame(f + k) for k in range(args.steps * sample_frames)]
-    t0 = time.perf_counter()
-    for fr in pre:
-        ov.integrate_matrix_count_only(fr, float(REF), n_threads)
-    dt = time.perf_counter() - t0
-    value = P * len(pre) / dt / 1e6
-    sample = (f"{sample_frames} consecutive frames of the workload per step (state carried across steps, frames "
-              f"{args.warmup * sample_frames}..{args.warmup * sample_frames + len(pre) - 1}), frames resident in host memory")
+    dt = 0.0
+    for _ in range(args.steps):
+        pre = [O.synth_frame(KIND_STATIC, SEED, f + k, W, H, C) for k in range(sample_frames)]  # frames resident before the clock starts
+        t0 = time.perf_counter()
+        for fr in pre:
+            ov.integrate_matrix_count_only(fr, float(REF), n_threads)
+        dt += time.perf_counter() - t0
+        f += sample_frames
+    value = P * sample_frames * args.steps / dt / 1e6
+    sample = (f"{sample_frames} consecutive whole 8K frames of the workload per step (state carried across steps: frames "
+              f"{args.warmup * sample_frames}..{f - 1}), frames resident in host memory")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": n_threads, "kind": "port", "sample": sample},
@@ -221,6 +379,7 @@ def bind_to_gpu_numa_node(local):
 
 def run_ours(args):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    nf = args.frames or NF
     n_cpus = bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa else 0
     dist = None
     if world > 1:
@@ -231,179 +390,149 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import adder_codec_rs_b200 as A
+    from adder_codec_rs_b200 import sharding as S
 
     if A.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU port)")
-    P = W * H * C
-    v = A.Video(W, H, C, A.MODE_FRAME_PERFECT, device=local)
-    assert v.time_parameters(REF * 30, REF, DTM, None)
-    v.update_crf(CRF)
-    v.set_row_offset(rank * H)  # this rank's band of the N*1080-row frame
-    n_chunks = v.n_chunks
-
-    # ---- inputs resident in HBM: this band's 300 frames --------------------------------------
-    d_frames = v.device_alloc(P * NF)
-    v.synth_frames(d_frames, 0, NF, KIND_NOISE, SEED + rank)
-    ev_stride = P * 2  # records per frame; overflow would be reported by sync()
-    d_events = v.device_alloc(ev_stride * 12 * NF)
-    d_off = v.device_alloc((n_chunks + 1) * 4 * NF)
-
-    def step_device():
-        v.reset_state()
-        v.update_crf(CRF)
-        v.integrate_frames_device(d_frames.ptr, P, NF, float(REF), d_events.ptr, ev_stride, d_off.ptr)
+    peak, peak_src = measured_peak_gbs()
 
     def barrier():
         if dist is not None:
             dist.barrier()
 
+    # ---- side passes first (they need the GPU's memory for themselves): measured DRAM traffic of the headline kernel
+    traffic = None
+    workloads = None
+    if world == 1 and rank == 0:
+        if args.traffic != "off":
+            # aged stacks: the launch measured is frames 592..607 of the sequence (the first frames have two-node stacks)
+            traffic = ncu_dram_bytes_per_px_frame(["--w", W, "--h", H, "--c", C, "--kind", KIND_STATIC, "--crf", CRF, "--ref", REF, "--dtm", DTM,
+                                                   "--cap", EV_PER_PX, "--warm-frames", 592], 16, W * H * C)
+        if not args.no_workloads:
+            workloads = run_side_workloads(A, S, args, peak)
+
+    # ---- the headline: this rank's band of the 8K frame, 2000 frames resident in HBM ------------------------------
+    wl = DeviceWorkload(A, S, w=W, h=H, c=C, kind=KIND_STATIC, frames=nf, ref=REF, dtm=DTM, crf=CRF, rank=rank, world=world,
+                        device=local, batch=BATCH, ev_per_px=EV_PER_PX)
+    v, P = wl.v, wl.P
+    n_chunks = v.n_chunks
     sampler = ClockSampler(local)
     sampler.start()  # well before the timed region: with eight GPUs on the box nvidia-smi needs a second to come up
-    # untimed counting pass: exact algorithmic bytes of this workload (also the first warm-up)
-    v.set_counting(True)
-    step_device()
-    v.sync()
-    cnt = v.read_counters()
-    v.set_counting(False)
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    v.sync()
-
-    barrier()
-    ev0, l0 = v.events_emitted(), v.launch_count
-    sampler.mark_begin()
-    v.timer_start()
-    for _ in range(args.steps):
-        step_device()
-    ms = v.timer_stop()
-    sampler.mark_end()
+    cnt, alg_bytes_step = wl.count()  # untimed: exact algorithmic bytes of this band's step (also the first warm-up)
+    ev0 = v.events_emitted()
+    ms, launches = wl.timed(args.steps, max(args.warmup, 3), barrier, sampler)
     clocks = sampler.stop()
-    v.sync()
-    barrier()
-    launches = v.launch_count - l0
-    events_per_step = (v.events_emitted() - ev0) // args.steps
+    events_per_step = (v.events_emitted() - ev0) // (args.steps + max(args.warmup, 3))
     assert events_per_step == cnt["events"], (events_per_step, cnt)
 
-    # algorithmic bytes of one step of the integrate kernel:
-    #   per px-frame: 1 sample + 8 header read + 8 header write; per node load/store 16; per display write 1; per event 12
-    alg_bytes_step = (1 + 8 + 8) * P * NF + 16 * (cnt["node_loads"] + cnt["node_stores"]) + cnt["display_writes"] + 12 * cnt["events"]
-
-    # ---- e2e: host buffers through the C ABI --------------------------------------------------
-    sub = 20
-    host_frames = A.pinned_empty((NF, H, W, C), np.uint8)
-    hf = np.asarray(host_frames)
-    hf.reshape(-1)[:] = d_frames.to_host()
-    d_events.free()
-    d_off.free()
-    max_sub_events = int(events_per_step / NF * sub * 1.25) + 4096
+    # ---- e2e: host buffers through the C ABI -------------------------------------------------------------------
+    # The step's frames come from pinned host memory in runs of `sub` frames; the pinned run is refilled from the
+    # frames in HBM between calls, outside the timed calls (2000 8K frames would be 66 GB of page-locked memory).
+    sub = min(100, nf)
+    host_frames = np.asarray(A.pinned_empty((sub, wl.rows, W, C), np.uint8))
+    wl.d_events.free()
+    wl.d_events = None
+    max_sub_events = int(events_per_step / nf * sub * 3) + (1 << 20)
     host_events = np.asarray(A.pinned_empty((max_sub_events,), A.EVENT_DTYPE))
 
     def step_host():
         v.reset_state()
-        v.update_crf(CRF)
-        total = 0
-        for f0 in range(0, NF, sub):
-            ev, fc, cc = v.integrate_frames_host(hf[f0:f0 + sub], float(REF), host_events)
+        wl.quality()
+        total, secs = 0, 0.0
+        for f0 in range(0, nf, sub):
+            n = min(sub, nf - f0)
+            wl.d_frames.to_host_into(host_frames, n * P, offset=f0 * P)  # refill (untimed)
+            t0 = time.perf_counter()
+            ev, fc, cc = v.integrate_frames_host(host_frames[:n], float(REF), host_events)
+            secs += time.perf_counter() - t0
             total += len(ev)
-        return total
+        return total, secs
 
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 2))
     step_host()
     barrier()
-    t0 = time.perf_counter()
-    tot = 0
+    tot, e2e_s = 0, 0.0
     for _ in range(e2e_steps):
-        tot += step_host()
-    e2e_s = time.perf_counter() - t0
+        t, s = step_host()
+        tot += t
+        e2e_s += s
     barrier()
-    assert tot == events_per_step * e2e_steps
+    assert tot == events_per_step * e2e_steps, (tot, events_per_step)
 
-    # the same step delivering the raw .adder body (11-byte wire records for RGB) instead of 12-byte records:
-    # what Framed::consume + Encoder<RawOutput>::ingest_event produce.  One timed step.
-    esize = v.raw_event_size
-    del host_events
-    host_bytes = np.asarray(A.pinned_empty((max_sub_events * esize,), np.uint8))
-
-    def step_host_raw():
-        v.reset_state()
-        v.update_crf(CRF)
-        total = 0
-        for f0 in range(0, NF, sub):
-            body, fc, cc = v.integrate_frames_host_raw(hf[f0:f0 + sub], float(REF), host_bytes)
-            total += len(body)
-        return total
-
-    step_host_raw()
-    barrier()
-    t0 = time.perf_counter()
-    raw_bytes = step_host_raw()
-    raw_s = time.perf_counter() - t0
-    barrier()
-    assert raw_bytes == events_per_step * esize
-
-    # ---- reduce over ranks -------------------------------------------------------------------
+    # ---- reduce over ranks -----------------------------------------------------------------------------------
     if dist is not None:
         import torch
 
-        t = torch.tensor([ms, e2e_s, raw_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, raw_s = t[0].item(), t[1].item(), t[2].item()
-        s = torch.tensor([float(alg_bytes_step), float(events_per_step), float(launches)], dtype=torch.float64, device="cuda")
+        ms, e2e_s = t[0].item(), t[1].item()
+        s = torch.tensor([float(alg_bytes_step), float(events_per_step), float(launches), float(P)], dtype=torch.float64, device="cuda")
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        alg_bytes_all, events_all, launches = s[0].item(), s[1].item(), int(s[2].item())
+        alg_bytes_all, events_all, launches, P_all = s[0].item(), s[1].item(), int(s[2].item()), int(s[3].item())
     else:
-        alg_bytes_all, events_all = float(alg_bytes_step), float(events_per_step)
+        alg_bytes_all, events_all, P_all = float(alg_bytes_step), float(events_per_step), P
+    assert P_all == W * H * C
 
     if rank == 0:
-        px_step = P * NF * world
+        px_step = W * H * C * nf  # the whole frame, whatever N
         value = px_step * args.steps / (ms * 1e-3) / 1e6
         e2e_value = px_step * e2e_steps / e2e_s / 1e6
-        peak, peak_src = measured_peak_gbs()
-        # per-GPU achieved bandwidth of the integrate kernel
+        # the integrate kernel of THIS rank (its band): achieved bandwidth per GPU
         achieved = alg_bytes_step * args.steps / (ms * 1e-3) / 1e9
-        traffic = ncu_traffic()
-        # SURVEY.md §8(d)'s planning formula on the same run, for comparison: 1 + 2*(12 + 16*L) + 1[display] + 12*E with L the
-        # mean live nodes per px at frame entry and exit, E the events per px-frame (both counted above).  It charges a
-        # 12-byte header and every live node; `achieved` uses the smaller, exactly counted figure.
-        L_mean = (cnt["live_nodes_in"] + cnt["live_nodes_out"]) / (2.0 * P * NF)
-        E_mean = cnt["events"] / (P * NF)
-        b_survey = 1 + 2 * (12 + 16 * L_mean) + 1 + 12 * E_mean
-        survey = {"bytes_per_px_frame": b_survey, "L_mean_live_nodes": L_mean, "E_events_per_px_frame": E_mean,
-                  "achieved": b_survey * P * NF * args.steps / (ms * 1e-3) / 1e9,
-                  "frac": b_survey * P * NF * args.steps / (ms * 1e-3) / 1e9 / peak}
+        pxf = P * nf
+        b_survey, L_mean, E_mean = survey_formula(cnt, pxf)
+        n_launch = (nf + wl.batch - 1) // wl.batch
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "integrate_frame_kernel<8,false,true>",
+                "frames_per_launch": wl.batch, "launches_per_step": n_launch,
+                "algorithmic_bytes_per_launch": alg_bytes_step / n_launch, "algorithmic_bytes_per_px_frame": alg_bytes_step / pxf,
+                "node_loads_per_px_frame": cnt["node_loads"] / pxf, "node_stores_per_px_frame": cnt["node_stores"] / pxf,
+                "survey_formula": {"bytes_per_px_frame": b_survey, "L_mean_live_nodes": L_mean, "E_events_per_px_frame": E_mean,
+                                   "frac": b_survey * pxf * args.steps / (ms * 1e-3) / 1e9 / peak},
+                "note": "per GPU (rank 0's band); time = CUDA events around the whole timed region on the launching stream "
+                        "(the integrate launches + 2 reset kernels per step); bytes counted exactly by the instrumented twin of the kernel"}
+        if traffic is not None:
+            roof["traffic"] = traffic[0] * W * H * C * wl.batch  # per launch of `frames_per_launch` whole-plane frames
+            roof["traffic_bytes_per_px_frame"] = traffic[0]
+            roof["traffic_over_algorithmic"] = traffic[0] / traffic[1] if traffic[1] else None
+            roof["traffic_source"] = ("measured in this run: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum side pass over a 16-frame "
+                                      "launch of the same plane with aged stacks (frames 592..607), scaled to frames_per_launch; the ratio is "
+                                      "against the bytes counted for that same launch")
         line = {
             "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "plane_per_gpu": f"{W}x{H}x{C}", "frames_per_step": NF,
-                       "sharding": (f"row bands, no collective; each rank bound to the {n_cpus} CPUs next to its GPU" if n_cpus else "row bands, no collective") if world > 1 else "single GPU",
-                       "l2": "per-frame working set (state 350 MB + frame + events) exceeds the 126 MB L2; no flush needed",
+            "config": {"workload": WORKLOAD, "plane": f"{W}x{H}x{C}", "plane_per_gpu": f"{W}x{wl.rows}x{C}", "frames_per_step": nf,
+                       "sharding": (f"{world} row bands of one frame, no data-path collective in `value`; each rank bound to the {n_cpus} CPUs next to its GPU"
+                                    if n_cpus else f"{world} row bands of one frame, no data-path collective in `value`") if world > 1 else "single GPU",
+                       "l2": "per-frame working set (headers 265 MB + live node levels + frame) exceeds the 126 MB L2; no flush needed",
                        "events_per_step": events_all, "events_per_px_frame": events_all / px_step},
-            "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": P * NF * world, "d2h_bytes_per_step": int(events_all * 12 + (n_chunks + 1) * 4 * NF * world),
-                    "steps": e2e_steps, "api": "adder_b200_video_integrate_frames_host, pinned host frames in, all events out to pinned host memory"},
-            "e2e_raw": {"value": px_step / raw_s / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": P * NF * world, "d2h_bytes_per_step": int((raw_bytes + (n_chunks + 1) * 4 * NF) * world),
-                        "steps": 1, "api": "adder_b200_video_integrate_frames_host_raw: the raw .adder stream body (wire records serialised on the device) to pinned host memory"},
+            "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": px_step, "d2h_bytes_per_step": int(events_all * 12 + (H + world) * 4 * nf),
+                    "steps": e2e_steps,
+                    "api": f"adder_b200_video_integrate_frames_host in runs of {sub} frames: pinned host frames in, all events out to pinned host memory; "
+                           "timed = the calls (the pinned run is refilled from HBM between calls, untimed)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ((traffic or {}).get("dram_bytes_per_frame") or 0) * NF or None, "peak_source": peak_src,
-                         "kernel": "integrate_frame_kernel<8,false,true>", "frames_per_launch": NF, "algorithmic_bytes_per_launch": alg_bytes_step,
-                         "algorithmic_bytes_per_px_frame": alg_bytes_step / (P * NF),
-                         "node_loads_per_px_frame": cnt["node_loads"] / (P * NF), "node_stores_per_px_frame": cnt["node_stores"] / (P * NF),
-                         "survey_formula": survey,
-                         "note": "one integrate launch spans the step's 300 frames; time = CUDA events around the whole timed region on the launching stream (that launch + 2 reset kernels per step); traffic = ncu dram bytes per frame of a 16-frame launch x 300"},
+            "roofline": roof,
         }
-        # ---- CPU baseline on this box's host cores (bounded sample) -------------------------
+        if workloads is not None:
+            line["workloads"] = workloads
+        # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------------------
         if world == 1 and not args.no_cpu:
             from oracle import oracle_py as O
 
-            nt = O.max_threads()
-            mt, n_mt, s_mt = cpu_baseline_run(nt, args.cpu_seconds, lambda f: hf[f])
-            st, n_st, s_st = cpu_baseline_run(1, min(args.cpu_seconds, 6.0), lambda f: hf[f], max_frames=8)
+            nt = O.host_threads()
+            mt, n_mt, s_mt = cpu_baseline_run(O, nt, args.cpu_seconds, 64)
+            st, n_st, s_st = cpu_baseline_run(O, 1, min(args.cpu_seconds, 6.0), 4, min_frames=1)
             line["cpu_baseline"] = {"value": mt, "unit": "Mpx/s", "cores": nt, "kind": "port",
-                                    "sample": f"first {n_mt} frames of the same workload from a fresh state ({s_mt:.1f} s), frames resident in host memory",
+                                    "sample": f"first {n_mt} whole 8K frames of the same workload from a fresh state ({s_mt:.1f} s), frames resident in host memory",
                                     "single_thread": {"value": st, "frames": n_st, "seconds": s_st}}
         print(json.dumps(line))
+        if workloads is not None:  # the table, readable in the tail of the log
+            sys.stderr.write("workload table (1 GPU, device-resident):\n")
+            for e in workloads:
+                sys.stderr.write(f"  {e['value'] / 1e3:7.2f} Gpx/s  {e['us_per_frame']:8.1f} us/frame  {e['bytes_per_px_frame']:6.1f} B/px-frame  "
+                                 f"frac {e['frac']:.3f}  dram/counted {e.get('dram_over_counted') or float('nan'):.2f}  {e['workload']}\n")
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -412,10 +541,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per step instead of the config's 2000 (debugging: not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the table of the other BASELINE configs (N = 1)")
+    ap.add_argument("--traffic", default="some", choices=["off", "some", "all"], help="ncu side passes for measured DRAM traffic: headline + cfg 2 + cfg 3 c in {0,5,10} (some), every workload (all)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind each rank to the CPUs next to its GPU (N > 1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

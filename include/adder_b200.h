@@ -346,7 +346,8 @@ int adder_b200_video_timer_start(adder_b200_video* v);
 int adder_b200_video_timer_stop(adder_b200_video* v, float* ms);
 /* Synthetic frames generated on the device (bench input; tests/synth.py holds the same generator in
  * numpy): n_frames frames of `px` bytes, frame index starting at f0.  kind: 0 gradient (x+2y+3f)&255,
- * 1 uniform noise h(seed,f,i), 2 base +-10 jitter, 3 static base with rare changes (p = 2/256). */
+ * 1 uniform noise h(seed,f,i), 2 base +-10 jitter, 3 static base with rare changes (p = 2/256).
+ * On a row band (adder_b200_video_set_row_offset) the band's rows of the undivided frame are produced. */
 int adder_b200_synth_frames(adder_b200_video* v, uint8_t* d_frames, size_t frame_stride, uint32_t f0,
                             uint32_t n_frames, int kind, uint64_t seed);
 

@@ -895,6 +895,60 @@ int oracle_max_threads(void) {
 #endif
 }
 
+/* The host cores this process may run on, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its
+ * workers, which made the round-1 reference arm run on one core at N >= 2). */
+int oracle_num_procs(void) {
+#ifdef _OPENMP
+  return omp_get_num_procs();
+#else
+  return 1;
+#endif
+}
+
+/* ---- bench / test input --------------------------------------------------------------------------
+ * The synthetic frames of SURVEY.md §8(d), byte for byte what tests/synth.py (numpy) and the product's device generator
+ * produce; here only so that the CPU arm of bench.py can make 8K frames at memory speed.
+ *   h(seed, f, i) = splitmix64(seed ^ (f << 40) ^ i) & 0xFF,  i = flat raster index ((y*W + x)*C + c) of the whole plane */
+static inline uint64_t oracle_splitmix64(uint64_t x) {
+  uint64_t z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static inline uint32_t oracle_synth_hash(uint64_t seed, uint32_t f, uint64_t i) {
+  return (uint32_t)(oracle_splitmix64(seed ^ ((uint64_t)f << 40) ^ i) & 0xFFu);
+}
+/* kind 0 gradient, 1 noise, 2 base +-10 jitter, 3 static base with one-frame blips; n pixels-channels starting at flat
+ * index i0 of a plane `w` wide with `c` channels */
+void oracle_synth_frame(int kind, uint64_t seed, uint32_t f, uint32_t w, uint32_t c, uint64_t i0, uint64_t n, uint8_t* out,
+                        int n_threads) {
+  (void)n_threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+  for (int64_t k = 0; k < (int64_t)n; k++) {
+    const uint64_t i = i0 + (uint64_t)k;
+    uint32_t v;
+    switch (kind) {
+      case 0: {
+        const uint64_t p = i / c, x = p % w, y = p / w;
+        v = (uint32_t)((x + 2u * y + 3u * (uint64_t)f) & 255u);
+        break;
+      }
+      case 1: v = oracle_synth_hash(seed, f, i); break;
+      case 2: {
+        const int t = (int)oracle_synth_hash(seed ^ 1ull, 0, i) + (int)(oracle_synth_hash(seed ^ 2ull, f, i) % 21u) - 10;
+        v = (uint32_t)(t < 0 ? 0 : (t > 255 ? 255 : t));
+        break;
+      }
+      default:
+        v = oracle_synth_hash(seed ^ 3ull, f, i) < 2u ? oracle_synth_hash(seed ^ 4ull, f, i) : oracle_synth_hash(seed ^ 1ull, 0, i);
+        break;
+    }
+    out[k] = (uint8_t)v;
+  }
+}
+
 /* ---- raw .adder wire format ------------------------------------------------------------------- */
 
 static uint8_t* put_u16(uint8_t* p, uint16_t v) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; return p + 2; }

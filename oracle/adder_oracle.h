@@ -137,6 +137,10 @@ void oracle_video_stats(const oracle_video* v, uint64_t* live_nodes_entry, uint6
 const oracle_px* oracle_video_px(const oracle_video* v, size_t index);
 
 int oracle_max_threads(void);
+int oracle_num_procs(void); /* host cores available to this process, whatever OMP_NUM_THREADS says */
+/* synthetic bench / test frames, identical to tests/synth.py and the device generator */
+void oracle_synth_frame(int kind, uint64_t seed, uint32_t f, uint32_t w, uint32_t c, uint64_t i0, uint64_t n, uint8_t* out,
+                        int n_threads);
 
 /* ---- feature detection inside integrate_matrix ---------------------------
  * is_feature, utils/cv.rs:22-212 (FAST 9_16 on channel 0; parity UNPINNED by reference tests — none exist;

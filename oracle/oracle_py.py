@@ -188,6 +188,9 @@ def lib() -> C.CDLL:
     L.oracle_video_px.restype = C.POINTER(Px)
     L.oracle_video_px.argtypes = [vp, sz]
     L.oracle_max_threads.restype = i32
+    L.oracle_num_procs.restype = i32
+    L.oracle_synth_frame.restype = None
+    L.oracle_synth_frame.argtypes = [i32, C.c_uint64, u32, u32, u32, C.c_uint64, C.c_uint64, vp, i32]
     _lib = L
     return L
 
@@ -356,6 +359,21 @@ def crf_parameters(crf, w, h) -> CrfParameters:
 
 def max_threads() -> int:
     return lib().oracle_max_threads()
+
+
+def host_threads() -> int:
+    """The host cores this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, lib().oracle_num_procs())
+
+
+def synth_frame(kind: int, seed: int, f: int, w: int, h: int, c: int, row0: int = 0, full_w: int = None, n_threads: int = 0) -> np.ndarray:
+    """One (h, w, c) u8 synthetic frame — rows row0 .. row0+h of the plane — identical to tests/synth.py and the device generator."""
+    out = np.empty((h, w, c), dtype=np.uint8)
+    lib().oracle_synth_frame(kind, seed & 0xFFFFFFFFFFFFFFFF, f, w, c, row0 * w * c, out.size, out.ctypes.data, n_threads or host_threads())
+    return out
 
 
 def raw_header(width, height, channels, tps, ref_interval, delta_t_max, version=3, source_camera=0, time_mode=TIME_ABSOLUTE_T,

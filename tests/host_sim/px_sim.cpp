@@ -27,6 +27,7 @@ struct HostNodes {
   void used_preloaded() const {}
   void prefetch_levels(uint32_t) const {}
   void unused_load() const {}
+  void reload(adder::Node& n0, adder::Node& n1) const { n0 = p[0]; n1 = p[stride]; }
 };
 struct VecSink {
   std::vector<adder_event_t>* out;
@@ -37,6 +38,8 @@ struct VecSink {
     e.x = x; e.y = y; e.c = c; e.d = (uint8_t)d; e.reserved = 0; e.t = t;
     out->push_back(e);
   }
+  size_t mark() const { return out->size(); }
+  void rewind(size_t m) { out->resize(m); }
 };
 }  // namespace
 
@@ -109,7 +112,7 @@ size_t sim_integrate(sim_video* v, const uint8_t* frame, float time, uint32_t re
     uint8_t disp = 0;
     /* like the kernel: level 1 is fetched before the length is known */
     const adder::Node n1 = v->depth > 1 ? mem.load(1) : mem.load(0);
-    if (adder::px_step(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)) v->running[i] = disp;
+    if (adder::px_frame(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)) v->running[i] = disp;
   }
   return v->events.size();
 }

@@ -459,7 +459,7 @@ def test_host_form_resumes_after_a_full_output_buffer():
             assert done == 7
             with pytest.raises(A.AdderError) as e:
                 gv.integrate_matrix(frames[0], case.time)
-            assert e.value.code == A.ERR_BAD_PARAMS
+            assert e.value.code == A.binding.ERR_BAD_PARAMS
     assert calls >= 3
     assert np.concatenate(got).tobytes() == np.concatenate(exp).tobytes()
     n = case.w * case.h * case.c

@@ -234,3 +234,16 @@ def test_crf_table(oracle):
     assert (p.c_thresh_baseline, p.c_thresh_max, p.c_increase_velocity, p.feature_c_radius) == (0, 0, 10, 0)
     p = oracle.crf_parameters(9, 640, 480)
     assert (p.c_thresh_baseline, p.c_thresh_max, p.c_increase_velocity, p.feature_c_radius) == (15, 25, 1, 16)
+
+
+def test_oracle_synth_frames_equal_the_numpy_generator():
+    """oracle_synth_frame (the CPU bench arm's frame source) == tests/synth.py for every kind, including a row band."""
+    from oracle import oracle_py as O
+    from tests import synth
+
+    for kind in (synth.GRADIENT, synth.NOISE, synth.JITTER, synth.STATIC_BLIPS):
+        for (w, h, c) in ((37, 13, 3), (64, 9, 1)):
+            want = synth.frame(kind, 0xADDE5, 7, w, h, c)
+            assert np.array_equal(O.synth_frame(kind, 0xADDE5, 7, w, h, c), want)
+            assert np.array_equal(O.synth_frame(kind, 0xADDE5, 7, w, 4, c, row0=5), want[5:9])
+    assert O.host_threads() >= 1
