@@ -8,6 +8,7 @@ importing works anywhere, but creating a `Video` without a CUDA device raises.
 """
 from .binding import (  # noqa: F401
     EVENT_DTYPE,
+    Exchange,
     Framer,
     AdderError,
     MODE_CONTINUOUS,

@@ -45,7 +45,11 @@ SYMBOLS = [
     "adder_b200_framer_create", "adder_b200_framer_destroy", "adder_b200_framer_ingest_events_device",
     "adder_b200_framer_ingest_events_host", "adder_b200_framer_write_multi_frame_bytes",
     "adder_b200_framer_flush_frame_buffer", "adder_b200_framer_state",
+    "adder_b200_comm_create", "adder_b200_comm_export", "adder_b200_comm_open", "adder_b200_comm_attach", "adder_b200_comm_destroy",
+    "adder_b200_comm_push_frames", "adder_b200_comm_wait_frames", "adder_b200_comm_frame", "adder_b200_comm_release_frames",
+    "adder_b200_comm_sync", "adder_b200_comm_stream",
 ]
+COMM_BLOB_BYTES = 256
 
 
 class AdderError(RuntimeError):
@@ -167,6 +171,17 @@ def lib() -> C.CDLL:
         "adder_b200_framer_write_multi_frame_bytes": (i32, [vp, vp, u32, P(u32)]),
         "adder_b200_framer_flush_frame_buffer": (i32, [vp, P(i32)]),
         "adder_b200_framer_state": (i32, [vp, P(C.c_int64), P(u32)]),
+        "adder_b200_comm_create": (i32, [vp, u32, u32, u32, sz, P(vp)]),
+        "adder_b200_comm_export": (i32, [vp, vp, sz]),
+        "adder_b200_comm_open": (i32, [vp, vp, sz, P(vp)]),
+        "adder_b200_comm_attach": (i32, [vp, vp, P(vp)]),
+        "adder_b200_comm_destroy": (None, [vp]),
+        "adder_b200_comm_push_frames": (i32, [vp, u32, u32, vp, sz, vp, u32, u64]),
+        "adder_b200_comm_wait_frames": (i32, [vp, u64, u32]),
+        "adder_b200_comm_frame": (i32, [vp, u64, P(vp), P(vp)]),
+        "adder_b200_comm_release_frames": (i32, [vp, u64]),
+        "adder_b200_comm_sync": (i32, [vp]),
+        "adder_b200_comm_stream": (vp, [vp]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -585,3 +600,77 @@ class Framer:
         ready = C.c_int()
         _check(self.L.adder_b200_framer_flush_frame_buffer(self.f, C.byref(ready)))
         return bool(ready.value)
+
+
+class Exchange:
+    """The event exchange between row bands (include/adder_b200.h, comm section): the consumer's ring of whole-frame
+    buffers, or a band's mapping of it.  Build with Exchange.consumer(...), then .export() / Exchange.open(...) across
+    processes or .attach(...) inside one."""
+
+    def __init__(self, handle, video, owner):
+        self.L = lib()
+        self.c = handle
+        self.video = video
+        self.owner = owner
+
+    @classmethod
+    def consumer(cls, video: "Video", world: int, total_chunks: int, slots: int, out_stride: int) -> "Exchange":
+        h = C.c_void_p()
+        _check(video.L.adder_b200_comm_create(video.v, world, total_chunks, slots, out_stride, C.byref(h)))
+        return cls(h, video, True)
+
+    def export(self) -> bytes:
+        buf = (C.c_uint8 * COMM_BLOB_BYTES)()
+        _check(self.L.adder_b200_comm_export(self.c, buf, COMM_BLOB_BYTES))
+        return bytes(buf)
+
+    @classmethod
+    def open(cls, video: "Video", blob: bytes) -> "Exchange":
+        h = C.c_void_p()
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(video.L.adder_b200_comm_open(video.v, buf, len(blob), C.byref(h)))
+        return cls(h, video, False)
+
+    def attach(self, video: "Video") -> "Exchange":
+        assert self.owner
+        h = C.c_void_p()
+        _check(self.L.adder_b200_comm_attach(video.v, self.c, C.byref(h)))
+        return Exchange(h, video, False)
+
+    def push_frames(self, band, chunk0, d_events, events_stride, d_chunk_offsets, n_frames, frame_seq0):
+        _check(self.L.adder_b200_comm_push_frames(self.c, band, chunk0, d_events, events_stride, d_chunk_offsets, n_frames, frame_seq0))
+
+    def wait_frames(self, frame_seq0, n_frames):
+        _check(self.L.adder_b200_comm_wait_frames(self.c, frame_seq0, n_frames))
+
+    def release_frames(self, upto_seq):
+        _check(self.L.adder_b200_comm_release_frames(self.c, upto_seq))
+
+    def frame_ptrs(self, frame_seq):
+        e, o = C.c_void_p(), C.c_void_p()
+        _check(self.L.adder_b200_comm_frame(self.c, frame_seq, C.byref(e), C.byref(o)))
+        return e.value, o.value
+
+    def read_frame(self, frame_seq, total_chunks):
+        """Consumer, after wait_frames + sync: (events, chunk_offsets) of one whole frame as numpy arrays."""
+        e, o = self.frame_ptrs(frame_seq)
+        off = np.empty(total_chunks + 1, dtype=np.uint32)
+        _check(self.L.adder_b200_copy_to_host(self.video.v, off.ctypes.data, o, off.nbytes))
+        ev = np.empty(int(off[-1]), dtype=EVENT_DTYPE)
+        if len(ev):
+            _check(self.L.adder_b200_copy_to_host(self.video.v, ev.ctypes.data, e, ev.nbytes))
+        return ev, off
+
+    def sync(self):
+        _check(self.L.adder_b200_comm_sync(self.c))
+
+    def close(self):
+        if getattr(self, "c", None):
+            self.L.adder_b200_comm_destroy(self.c)
+            self.c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

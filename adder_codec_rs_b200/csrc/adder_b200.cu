@@ -21,6 +21,7 @@
 #include "feature_kernel.cuh"
 #include "framer_kernel.cuh"
 #include "raw_kernel.cuh"
+#include "exchange_kernel.cuh"
 #include "synth.cuh"
 
 namespace {
@@ -1631,5 +1632,282 @@ int adder_b200_framer_state(const adder_b200_framer* f, int64_t* frames_written,
   if (tpf) *tpf = f->tpf;
   return ADDER_OK;
 }
+
+}  /* extern "C" */
+
+/* ================================ event exchange between row bands (include/adder_b200.h, comm section) ================================ */
+
+struct adder_b200_comm {
+  adder_b200_video* v = nullptr; /* the band (or the consumer's video) whose device and stream order this object follows */
+  int device = 0;
+  bool owner = false;        /* allocated the ring (the consumer) */
+  bool ipc_mapped = false;   /* the ring was opened from another process's handle */
+  void* base = nullptr;      /* one allocation: records | chunk offsets | totals | arrived | released */
+  size_t bytes = 0;
+  adder::ExchangeRing ring{};
+  cudaStream_t stream = nullptr; /* pushes / waits run here, behind the video's stream, so that they overlap its next launch */
+  cudaEvent_t ev = nullptr;
+  cudaEvent_t ev_push[2] = {nullptr, nullptr}; /* completion of the last two push_frames calls */
+  uint64_t n_push = 0;
+  uint32_t* d_local_done = nullptr; /* [kMaxFramesPerLaunch] */
+  uint32_t* d_err = nullptr;
+  uint32_t* h_err = nullptr;
+  unsigned long long released = 0; /* consumer: frames released so far */
+};
+
+namespace {
+
+struct CommBlob { /* what crosses the process boundary: ADDER_COMM_BLOB_BYTES */
+  char magic[8];
+  cudaIpcMemHandle_t handle; /* 64 bytes */
+  uint64_t bytes, out_stride;
+  uint32_t slots, world, total_chunks, device;
+};
+static_assert(sizeof(CommBlob) <= ADDER_COMM_BLOB_BYTES, "blob too large");
+
+size_t align256(size_t x) { return (x + 255u) & ~(size_t)255u; }
+
+/* offsets of the ring's parts inside its one allocation */
+void ring_layout(void* base, uint32_t slots, uint32_t world, uint32_t total_chunks, uint64_t out_stride, adder::ExchangeRing* r, size_t* bytes) {
+  size_t o = 0;
+  uint8_t* b = (uint8_t*)base;
+  r->ev_words = (uint32_t*)(b + o);
+  o += align256((size_t)slots * out_stride * sizeof(adder_event_t));
+  r->chunk_off = (uint32_t*)(b + o);
+  o += align256((size_t)slots * (total_chunks + 1u) * sizeof(uint32_t));
+  r->totals = (unsigned long long*)(b + o);
+  o += align256((size_t)slots * world * sizeof(unsigned long long));
+  r->arrived = (unsigned long long*)(b + o);
+  o += align256((size_t)slots * sizeof(unsigned long long));
+  r->released = (unsigned long long*)(b + o);
+  o += 256;
+  r->slots = slots;
+  r->world = world;
+  r->total_chunks = total_chunks;
+  r->out_stride = out_stride;
+  if (bytes) *bytes = o;
+}
+
+int comm_common_init(adder_b200_comm* c) {
+  CU(cudaSetDevice(c->device));
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi)); /* small kernels that should not queue behind the persistent one */
+  CU(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_push[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_push[1], cudaEventDisableTiming));
+  CU(cudaMalloc(&c->d_local_done, kMaxFramesPerLaunch * sizeof(uint32_t)));
+  CU(cudaMalloc(&c->d_err, sizeof(uint32_t)));
+  CU(cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream));
+  CU(cudaHostAlloc(&c->h_err, sizeof(uint32_t), cudaHostAllocDefault));
+  return ADDER_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int adder_b200_comm_create(adder_b200_video* v, uint32_t world, uint32_t total_chunks, uint32_t slots, size_t out_stride,
+                           adder_b200_comm** out) {
+  return guarded([&]() -> int {
+    if (!v || !out || world == 0 || slots == 0 || total_chunks == 0 || out_stride == 0) return fail(ADDER_ERR_BAD_PARAMS, "bad argument");
+    *out = nullptr;
+    adder_b200_comm* c = new adder_b200_comm();
+    c->v = v;
+    c->device = v->device;
+    c->owner = true;
+    auto build = [&]() -> int {
+      if (int rc = comm_common_init(c)) return rc;
+      ring_layout(nullptr, slots, world, total_chunks, out_stride, &c->ring, &c->bytes);
+      CU(cudaMalloc(&c->base, c->bytes));
+      ring_layout(c->base, slots, world, total_chunks, out_stride, &c->ring, nullptr);
+      /* totals / arrived / released start at zero: no frame has been published */
+      CU(cudaMemsetAsync(c->ring.totals, 0, (uint8_t*)c->base + c->bytes - (uint8_t*)c->ring.totals, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      return ADDER_OK;
+    };
+    if (int rc = build()) {
+      adder_b200_comm_destroy(c);
+      return rc;
+    }
+    *out = c;
+    return ADDER_OK;
+  });
+}
+
+int adder_b200_comm_export(adder_b200_comm* c, uint8_t* blob, size_t cap) {
+  if (!c || !blob || cap < ADDER_COMM_BLOB_BYTES) return fail(ADDER_ERR_BAD_PARAMS, "blob must hold ADDER_COMM_BLOB_BYTES");
+  if (!c->owner) return fail(ADDER_ERR_BAD_PARAMS, "only the consumer's comm can be exported");
+  CU(cudaSetDevice(c->device));
+  CommBlob b{};
+  memcpy(b.magic, "ADDRXCH1", 8);
+  CU(cudaIpcGetMemHandle(&b.handle, c->base));
+  b.bytes = c->bytes;
+  b.out_stride = c->ring.out_stride;
+  b.slots = c->ring.slots;
+  b.world = c->ring.world;
+  b.total_chunks = c->ring.total_chunks;
+  b.device = (uint32_t)c->device;
+  memset(blob, 0, ADDER_COMM_BLOB_BYTES);
+  memcpy(blob, &b, sizeof(b));
+  return ADDER_OK;
+}
+
+int adder_b200_comm_open(adder_b200_video* v, const uint8_t* blob, size_t blob_bytes, adder_b200_comm** out) {
+  return guarded([&]() -> int {
+    if (!v || !blob || !out || blob_bytes < sizeof(CommBlob)) return fail(ADDER_ERR_BAD_PARAMS, "bad argument");
+    *out = nullptr;
+    CommBlob b;
+    memcpy(&b, blob, sizeof(b));
+    if (memcmp(b.magic, "ADDRXCH1", 8) != 0) return fail(ADDER_ERR_BAD_PARAMS, "not an exchange blob");
+    adder_b200_comm* c = new adder_b200_comm();
+    c->v = v;
+    c->device = v->device;
+    auto build = [&]() -> int {
+      if (int rc = comm_common_init(c)) return rc;
+      CU(cudaIpcOpenMemHandle(&c->base, b.handle, cudaIpcMemLazyEnablePeerAccess)); /* maps the consumer's ring over NVLink */
+      c->ipc_mapped = true;
+      c->bytes = b.bytes;
+      ring_layout(c->base, b.slots, b.world, b.total_chunks, b.out_stride, &c->ring, nullptr);
+      return ADDER_OK;
+    };
+    if (int rc = build()) {
+      adder_b200_comm_destroy(c);
+      return rc;
+    }
+    *out = c;
+    return ADDER_OK;
+  });
+}
+
+int adder_b200_comm_attach(adder_b200_video* v, adder_b200_comm* consumer, adder_b200_comm** out) {
+  return guarded([&]() -> int {
+    if (!v || !consumer || !out || !consumer->owner) return fail(ADDER_ERR_BAD_PARAMS, "bad argument");
+    *out = nullptr;
+    adder_b200_comm* c = new adder_b200_comm();
+    c->v = v;
+    c->device = v->device;
+    auto build = [&]() -> int {
+      if (int rc = comm_common_init(c)) return rc;
+      if (c->device != consumer->device) { /* same process, another GPU: plain peer access */
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, c->device, consumer->device));
+        if (!can) return fail(ADDER_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", c->device, consumer->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(consumer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        (void)cudaGetLastError();
+      }
+      c->base = consumer->base;
+      c->bytes = consumer->bytes;
+      c->ring = consumer->ring;
+      return ADDER_OK;
+    };
+    if (int rc = build()) {
+      adder_b200_comm_destroy(c);
+      return rc;
+    }
+    *out = c;
+    return ADDER_OK;
+  });
+}
+
+void adder_b200_comm_destroy(adder_b200_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->ipc_mapped && c->base) cudaIpcCloseMemHandle(c->base);
+  if (c->owner) cudaFree(c->base);
+  cudaFree(c->d_local_done);
+  cudaFree(c->d_err);
+  if (c->h_err) cudaFreeHost(c->h_err);
+  if (c->ev) cudaEventDestroy(c->ev);
+  if (c->ev_push[0]) cudaEventDestroy(c->ev_push[0]);
+  if (c->ev_push[1]) cudaEventDestroy(c->ev_push[1]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int adder_b200_comm_push_frames(adder_b200_comm* c, uint32_t band, uint32_t chunk0, const adder_event_t* d_events, size_t events_stride,
+                                const uint32_t* d_chunk_offsets, uint32_t n_frames, uint64_t frame_seq0) {
+  return guarded([&]() -> int {
+    if (!c || !d_chunk_offsets || (!d_events && events_stride)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (band >= c->ring.world) return fail(ADDER_ERR_BAD_PARAMS, "band %u of %u", band, c->ring.world);
+    if (chunk0 + c->v->n_chunks > c->ring.total_chunks) return fail(ADDER_ERR_BAD_PARAMS, "the band's chunks do not fit the frame's");
+    CU(cudaSetDevice(c->device));
+    /* behind whatever the band's stream has queued (the integrate launch that produces these frames) */
+    CU(cudaEventRecord(c->ev, c->v->stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev, 0));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += kMaxFramesPerLaunch) {
+      const uint32_t n = std::min<uint32_t>(kMaxFramesPerLaunch, n_frames - f0);
+      CU(cudaMemsetAsync(c->d_local_done, 0, n * sizeof(uint32_t), c->stream));
+      adder::PushArgs a{};
+      a.ring = c->ring;
+      a.ev_words = reinterpret_cast<const uint32_t*>(d_events) + (size_t)f0 * events_stride * 3u;
+      a.ev_stride = events_stride;
+      a.chunk_off = d_chunk_offsets + (size_t)f0 * (c->v->n_chunks + 1u);
+      a.n_chunks = c->v->n_chunks;
+      a.chunk0 = chunk0;
+      a.band = band;
+      a.n_frames = n;
+      a.seq0 = frame_seq0 + f0;
+      a.local_done = c->d_local_done;
+      a.err = c->d_err;
+      /* a quarter of the SMs' worth of CTAs moves a band at NVLink rate and leaves room for the next integrate launch */
+      adder::exchange_push_kernel<<<std::max(sms / 4, 8), 256, 0, c->stream>>>(a);
+      CU(cudaGetLastError());
+    }
+    /* Two batches may be outstanding (the caller alternates two sets of buffers): whatever the band's stream is given
+     * after this call — the integrate launch that overwrites the buffers of the call before this one — waits for that
+     * earlier push, while this one still overlaps it. */
+    CU(cudaEventRecord(c->ev_push[c->n_push & 1u], c->stream));
+    if (c->n_push >= 1) CU(cudaStreamWaitEvent(c->v->stream, c->ev_push[(c->n_push - 1u) & 1u], 0));
+    c->n_push++;
+    return ADDER_OK;
+  });
+}
+
+int adder_b200_comm_wait_frames(adder_b200_comm* c, uint64_t frame_seq0, uint32_t n_frames) {
+  if (!c || !c->owner) return fail(ADDER_ERR_BAD_PARAMS, "only the consumer waits for frames");
+  if (n_frames > c->ring.slots) return fail(ADDER_ERR_BAD_PARAMS, "more frames than ring slots");
+  CU(cudaSetDevice(c->device));
+  adder::exchange_wait_kernel<<<1, 1, 0, c->stream>>>(c->ring, frame_seq0, n_frames, c->d_err);
+  CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
+int adder_b200_comm_release_frames(adder_b200_comm* c, uint64_t upto_seq) {
+  if (!c || !c->owner) return fail(ADDER_ERR_BAD_PARAMS, "only the consumer releases frames");
+  if (upto_seq < c->released) return fail(ADDER_ERR_BAD_PARAMS, "frames up to %llu were already released", (unsigned long long)c->released);
+  if (upto_seq - c->released > c->ring.slots) return fail(ADDER_ERR_BAD_PARAMS, "more frames than ring slots");
+  CU(cudaSetDevice(c->device));
+  adder::exchange_release_kernel<<<1, 1, 0, c->stream>>>(c->ring, c->released, upto_seq);
+  CU(cudaGetLastError());
+  c->released = upto_seq;
+  return ADDER_OK;
+}
+
+int adder_b200_comm_frame(adder_b200_comm* c, uint64_t frame_seq, adder_event_t** d_events, uint32_t** d_chunk_offsets) {
+  if (!c || !c->owner) return fail(ADDER_ERR_BAD_PARAMS, "only the consumer holds frames");
+  const size_t slot = (size_t)(frame_seq % c->ring.slots);
+  if (d_events) *d_events = reinterpret_cast<adder_event_t*>(c->ring.ev_words) + slot * c->ring.out_stride;
+  if (d_chunk_offsets) *d_chunk_offsets = c->ring.chunk_off + slot * (c->ring.total_chunks + 1u);
+  return ADDER_OK;
+}
+
+int adder_b200_comm_sync(adder_b200_comm* c) {
+  if (!c) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const uint32_t e = *c->h_err;
+  if (e) CU(cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream));
+  if (e & 4u) return fail(ADDER_ERR_INTERNAL, "event exchange: a peer did not show up within the time limit");
+  if (e & 1u) return fail(ADDER_ERR_CAPACITY, "event exchange: a frame's events do not fit the consumer's slot");
+  return ADDER_OK;
+}
+
+void* adder_b200_comm_stream(adder_b200_comm* c) { return c ? (void*)c->stream : nullptr; }
 
 }  /* extern "C" */

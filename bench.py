@@ -377,6 +377,59 @@ def bind_to_gpu_numa_node(local):
         return 0
 
 
+def gather_leg(A, dist, wl, rank, world, total_chunks, out_stride, gb, steps, barrier):
+    """The step of `wl` with the exchange on: after every integrate launch of gb frames each band pushes its records into
+    rank 0's whole-frame ring (adder_b200_comm_push_frames); rank 0 waits for the frames and releases the slots.
+    Two batches in flight (two sets of band buffers), host wall clock with all streams drained, max over ranks."""
+    import torch
+
+    v, P = wl.v, wl.P
+    d_ev2 = [v.device_alloc(wl.ev_stride * 12 * gb) for _ in range(2)]
+    d_off2 = [v.device_alloc((v.n_chunks + 1) * 4 * gb) for _ in range(2)]
+    cons = A.Exchange.consumer(v, world, total_chunks, 2 * gb, out_stride) if rank == 0 else None
+    blob = [cons.export() if rank == 0 else None]
+    dist.broadcast_object_list(blob, src=0)
+    prod = cons.attach(v) if rank == 0 else A.Exchange.open(v, blob[0])
+    seq = [0]
+
+    def step():
+        v.reset_state()
+        wl.quality()
+        for k, f0 in enumerate(range(0, wl.nf, gb)):
+            n = min(gb, wl.nf - f0)
+            b = k & 1
+            v.integrate_frames_device(wl.d_frames.ptr + f0 * P, P, n, float(wl.ref), d_ev2[b].ptr, wl.ev_stride, d_off2[b].ptr)
+            prod.push_frames(rank, wl.row0, d_ev2[b].ptr, wl.ev_stride, d_off2[b].ptr, n, seq[0])
+            if cons is not None:  # the consumer: wait for the whole frames, "consume" them, give the slots back
+                cons.wait_frames(seq[0], n)
+                cons.release_frames(seq[0] + n)
+            seq[0] += n
+
+    def drain():
+        v.sync()
+        prod.sync()
+        if cons is not None:
+            cons.sync()
+
+    step()
+    drain()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    drain()
+    secs = time.perf_counter() - t0
+    barrier()
+    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for b in d_ev2 + d_off2:
+        b.free()
+    prod.close()
+    if cons is not None:
+        cons.close()
+    return {"seconds": t[0].item(), "steps": steps, "frames_per_push": gb}
+
+
 def run_ours(args):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     nf = args.frames or NF
@@ -459,6 +512,31 @@ def run_ours(args):
     barrier()
     assert tot == events_per_step * e2e_steps, (tot, events_per_step)
 
+    # ---- gather legs (N > 1): the whole frame's events, in order, into rank 0's HBM after every batch of frames ---------
+    gather = gather4 = None
+    if dist is not None and not args.no_gather:
+        host_events = None
+        gather = gather_leg(A, dist, wl, rank, world, H, int(W * H * C * EV_PER_PX), min(50, nf), max(1, min(args.steps, 3)), barrier)
+        # BASELINE configs[3] — the one that names the event all-gather: 3840x2160 RGB noise, row bands, dense event stream
+        nf4 = min(200, nf)
+        wl4 = DeviceWorkload(A, S, w=3840, h=2160, c=3, kind=KIND_NOISE, frames=nf4, ref=255, dtm=7650, crf=3, rank=rank, world=world,
+                             device=local, batch=min(100, nf4), ev_per_px=1.25)
+        ms4, _ = wl4.timed(2, 1, barrier)
+        wl4.d_events.free()
+        wl4.d_events = None
+        g4 = gather_leg(A, dist, wl4, rank, world, 2160, int(3840 * 2160 * 3 * 1.25), min(20, nf4), 2, barrier)
+        import torch
+
+        t4 = torch.tensor([ms4], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        px4 = 3840 * 2160 * 3 * nf4
+        gather4 = {"workload": f"cfg4: 3840x2160 RGB noise, {nf4} frames, crf 3, {world} row bands (dense event stream: ~0.93 events per px-frame)",
+                   "value_gather_off": px4 * 2 / (t4[0].item() * 1e-3) / 1e6, "value_gather_on": px4 * g4["steps"] / g4["seconds"] / 1e6, "unit": "Mpx/s",
+                   "frames_per_push": g4["frames_per_push"],
+                   "limiter": "rank 0's NVLink ingress: ~280 MB of records per frame land on one GPU (~900 GB/s per direction), against "
+                              f"{490 / world:.0f} us per frame for the band kernels"}
+        wl4.free()
+
     # ---- reduce over ranks -----------------------------------------------------------------------------------
     if dist is not None:
         import torch
@@ -515,6 +593,15 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
         }
+        if gather is not None:
+            line["gather"] = {"on": True, "value": px_step * gather["steps"] / gather["seconds"] / 1e6, "unit": "Mpx/s", "steps": gather["steps"],
+                              "consumer_rank": 0, "event_bytes_per_step": int(events_all * 12), "frames_per_push": gather["frames_per_push"],
+                              "api": "adder_b200_comm_push_frames after every integrate launch: each band stores its compacted records at its offset in rank 0's "
+                                     "whole-frame ring over NVLink peer memory (offset = inter-GPU look-back over the lower bands' totals); rank 0 waits and releases; "
+                                     "host wall clock, streams drained, max over ranks",
+                              "limiter": "rank 0's NVLink ingress (~900 GB/s) for dense event streams; this workload's stream is sparse, so the leg runs at the kernels' pace"}
+        if gather4 is not None:
+            line["gather_cfg4"] = gather4
         if workloads is not None:
             line["workloads"] = workloads
         # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------------------
@@ -548,6 +635,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-workloads", action="store_true", help="skip the table of the other BASELINE configs (N = 1)")
     ap.add_argument("--traffic", default="some", choices=["off", "some", "all"], help="ncu side passes for measured DRAM traffic: headline + cfg 2 + cfg 3 c in {0,5,10} (some), every workload (all)")
+    ap.add_argument("--no-gather", action="store_true", help="skip the gather leg (N > 1)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind each rank to the CPUs next to its GPU (N > 1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

@@ -351,6 +351,63 @@ int adder_b200_video_timer_stop(adder_b200_video* v, float* ms);
 int adder_b200_synth_frames(adder_b200_video* v, uint8_t* d_frames, size_t frame_stride, uint32_t f0,
                             uint32_t n_frames, int kind, uint64_t seed);
 
+/* ================================================================================================
+ * Event exchange between row bands.
+ *
+ * The path shards by rows: band g of a frame is a video of its own (adder_b200_video_set_row_offset) on its own GPU,
+ * and rank-order concatenation of the bands' streams IS the reference's stream.  Nothing has to be exchanged unless ONE
+ * downstream consumer needs the whole frame's events in order — which is what the reference's encoder loop does
+ * (video.rs:736-740, serial ingest_event over the Vec<Vec<Event>> of the whole frame; the compressed encoder cuts ADUs
+ * out of that ordered stream, adder-codec-core/src/codec/compressed/stream.rs:264-313).  For that case the consumer GPU
+ * owns a ring of whole-frame buffers and every band stores its compacted records straight into its place in the
+ * frame over NVLink (peer memory: CUDA IPC between processes, plain peer access inside one): the band's offset is the
+ * sum of the lower bands' totals, read from a small table in the consumer's memory (an inter-GPU look-back).  No host
+ * round trip, no staging copy; pushes run on the comm's own stream behind the band's integrate launch and overlap the
+ * next one.  Frames are numbered by the caller (`frame_seq`, the same on all bands); frame s uses ring slot s % slots.
+ *
+ * One process per GPU (the usual layout):
+ *   consumer rank:  comm_create -> comm_export -> (send the blob to the other ranks by any means: it is 256 bytes)
+ *                   comm_attach(own band video, consumer comm) for its own band
+ *   other ranks:    comm_open(band video, blob)
+ *   every frame / batch of frames, every rank:   integrate_frames_device(...); comm_push_frames(...)
+ *   consumer:       comm_wait_frames(seq0, n); read comm_frame(seq) on the comm's stream; comm_release_frames(seq0 + n)
+ */
+typedef struct adder_b200_comm adder_b200_comm;
+#define ADDER_COMM_BLOB_BYTES 256u
+
+/* Consumer side.  On `v`'s device: `slots` whole-frame buffers of `out_stride` records and total_chunks + 1 chunk
+ * offsets each (total_chunks = ceil(H / chunk_rows) of the undivided frame), for `world` bands. */
+int adder_b200_comm_create(adder_b200_video* v, uint32_t world, uint32_t total_chunks, uint32_t slots, size_t out_stride,
+                           adder_b200_comm** out);
+/* The consumer's ring as bytes another process can open (cap >= ADDER_COMM_BLOB_BYTES). */
+int adder_b200_comm_export(adder_b200_comm* c, uint8_t* blob, size_t cap);
+/* Producer side in another process: maps the consumer's ring into the device of the band video `v`. */
+int adder_b200_comm_open(adder_b200_video* v, const uint8_t* blob, size_t blob_bytes, adder_b200_comm** out);
+/* Producer side in the consumer's own process (its own band, or bands on other GPUs of the same process). */
+int adder_b200_comm_attach(adder_b200_video* v, adder_b200_comm* consumer, adder_b200_comm** out);
+void adder_b200_comm_destroy(adder_b200_comm* c);
+/* Deliver n_frames frames of this band — the buffers an adder_b200_video_integrate_frames_device call on the band's
+ * video has just been given (same d_events / events_stride / d_chunk_offsets, which is required here) — as frames
+ * frame_seq0 .. frame_seq0 + n_frames - 1 of the consumer's ring.  band = this band's rank, chunk0 = index of its
+ * first chunk in the undivided frame.  Asynchronous: queued on the comm's stream behind the band's stream.
+ * Two pushes may be outstanding: work given to the band's stream after call k+1 waits for push k, so a band that
+ * alternates two sets of buffers overlaps push k+1 with the integrate launch k+2 without further synchronisation
+ * (with one set of buffers, adder_b200_comm_sync before reusing it). */
+int adder_b200_comm_push_frames(adder_b200_comm* c, uint32_t band, uint32_t chunk0, const adder_event_t* d_events, size_t events_stride,
+                                const uint32_t* d_chunk_offsets, uint32_t n_frames, uint64_t frame_seq0);
+/* Consumer: queue a wait on the comm's stream until all bands have delivered frames frame_seq0 .. +n_frames-1. */
+int adder_b200_comm_wait_frames(adder_b200_comm* c, uint64_t frame_seq0, uint32_t n_frames);
+/* Consumer: where frame frame_seq lies: its events (raster order of the whole frame) and its total_chunks + 1
+ * exclusive chunk offsets (the last one is the frame's event count) [device pointers]. */
+int adder_b200_comm_frame(adder_b200_comm* c, uint64_t frame_seq, adder_event_t** d_events, uint32_t** d_chunk_offsets);
+/* Consumer: frames below upto_seq have been read (by work queued on the comm's stream): their slots may be reused. */
+int adder_b200_comm_release_frames(adder_b200_comm* c, uint64_t upto_seq);
+/* Wait for everything queued on the comm's stream; reports a frame that did not fit its slot (ADDER_ERR_CAPACITY) or a
+ * peer that did not show up within 20 s (ADDER_ERR_INTERNAL). */
+int adder_b200_comm_sync(adder_b200_comm* c);
+/* The comm's CUDA stream (cudaStream_t), for the consumer's own kernels that read the frames. */
+void* adder_b200_comm_stream(adder_b200_comm* c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,3 +64,30 @@ def test_product_never_imports_the_oracle():
                 for pat in (r"^\s*(from|import)\s+oracle", r"oracle_py", r"#include.*oracle", r"libadder_oracle", r"libpx_sim",
                             r"^\s*(from|import)\s+tests"):
                     assert not re.search(pat, text, flags=re.M), f"{f} reaches into test infrastructure ({pat})"
+
+
+def _header_prototypes():
+    h = open(os.path.join(ROOT, "include", "adder_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(adder_b200_\w+)\s*\(([^;{]*?)\)\s*;", h):
+        args = " ".join(m.group(2).split())
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_rust_bindings_cover_the_header():
+    """rust/adder_b200-sys/src/lib.rs (source only: no rustc in this image) declares every entry point of the header
+    with the same number of arguments, and its event record is the 12-byte layout."""
+    src = open(os.path.join(ROOT, "rust", "adder_b200-sys", "src", "lib.rs")).read()
+    rust = {}
+    for m in re.finditer(r"pub fn (adder_b200_\w+)\(([^)]*)\)", src):
+        args = m.group(2).strip()
+        rust[m.group(1)] = 0 if not args else args.count(":")
+    protos = _header_prototypes()
+    assert set(rust) == set(protos), sorted(set(rust) ^ set(protos))
+    for name, n in protos.items():
+        assert rust[name] == n, f"{name}: header has {n} arguments, lib.rs {rust[name]}"
+    ev = re.search(r"pub struct adder_event_t \{(.*?)\}", src, flags=re.S).group(1)
+    fields = re.findall(r"pub (\w+): (\w+)", ev)
+    assert fields == [("x", "u16"), ("y", "u16"), ("c", "u8"), ("d", "u8"), ("reserved", "u16"), ("t", "u32")]
