@@ -24,6 +24,8 @@ from .binding import (  # noqa: F401
     VIEW_SAE,
     Video,
     build,
+    compact_frame_bytes,
+    expand_compact,
     crf_parameters,
     device_count,
     lib,

@@ -48,6 +48,7 @@ SYMBOLS = [
     "adder_b200_comm_create", "adder_b200_comm_export", "adder_b200_comm_open", "adder_b200_comm_attach", "adder_b200_comm_destroy",
     "adder_b200_comm_push_frames", "adder_b200_comm_wait_frames", "adder_b200_comm_frame", "adder_b200_comm_release_frames",
     "adder_b200_comm_sync", "adder_b200_comm_stream",
+    "adder_b200_video_integrate_frames_host_compact", "adder_b200_compact_frame_bytes", "adder_b200_expand_compact",
 ]
 COMM_BLOB_BYTES = 256
 
@@ -182,6 +183,9 @@ def lib() -> C.CDLL:
         "adder_b200_comm_release_frames": (i32, [vp, u64]),
         "adder_b200_comm_sync": (i32, [vp]),
         "adder_b200_comm_stream": (vp, [vp]),
+        "adder_b200_video_integrate_frames_host_compact": (i32, [vp, vp, sz, u32, f32, vp, sz, vp, vp, P(u64), P(u32)]),
+        "adder_b200_compact_frame_bytes": (u64, [u64, u64]),
+        "adder_b200_expand_compact": (i32, [u16, u16, u8, u16, vp, u64, vp, u32]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -208,6 +212,20 @@ def raw_eof() -> bytes:
     n = C.c_size_t()
     _check(lib().adder_b200_raw_eof(buf, 16, C.byref(n)))
     return bytes(buf[: n.value])
+
+
+def compact_frame_bytes(n_px: int, n_events: int) -> int:
+    return lib().adder_b200_compact_frame_bytes(n_px, n_events)
+
+
+def expand_compact(width, rows, channels, row0, block: np.ndarray, n_events: int, out: np.ndarray = None, n_threads: int = 0) -> np.ndarray:
+    """One frame's compact block -> its 12-byte records (host threads; no device involved)."""
+    block = np.ascontiguousarray(block, dtype=np.uint8)
+    if out is None:
+        out = np.empty(n_events, dtype=EVENT_DTYPE)
+    assert len(out) >= n_events
+    _check(lib().adder_b200_expand_compact(width, rows, channels, row0, block.ctypes.data, n_events, out.ctypes.data, n_threads or (os.cpu_count() or 1)))
+    return out[:n_events]
 
 
 def crf_parameters(crf, w, h) -> CrfParameters:
@@ -484,6 +502,20 @@ class Video:
         _check(self.L.adder_b200_video_integrate_frames_host_raw(self.v, frames.ctypes.data, frames[0].size, nf, time_spanned,
                                                                  bytes_out.ctypes.data, bytes_out.size, fc.ctypes.data,
                                                                  cc.ctypes.data, C.byref(n), C.byref(done)))
+        return bytes_out[: n.value], fc, cc
+
+    def integrate_frames_host_compact(self, frames: np.ndarray, time_spanned: float, bytes_out: np.ndarray):
+        """integrate_frames_host delivering the compact form (include/adder_b200.h): per frame either count bytes + {d, t}
+        or {index, d, t}.  Returns (bytes, frame_counts, chunk_counts); split with compact_frame_bytes, expand with expand_compact."""
+        assert frames.dtype == np.uint8 and frames.flags.c_contiguous and bytes_out.dtype == np.uint8
+        nf = frames.shape[0]
+        assert frames[0].size == self.w * self.h * self.src_c
+        fc = np.zeros(nf, dtype=np.uint64)
+        cc = np.zeros((nf, self.n_chunks), dtype=np.uint32)
+        n, done = C.c_uint64(), C.c_uint32()
+        _check(self.L.adder_b200_video_integrate_frames_host_compact(self.v, frames.ctypes.data, frames[0].size, nf, time_spanned,
+                                                                     bytes_out.ctypes.data, bytes_out.size, fc.ctypes.data,
+                                                                     cc.ctypes.data, C.byref(n), C.byref(done)))
         return bytes_out[: n.value], fc, cc
 
     def running_intensities(self) -> np.ndarray:

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/adder_b200.h"
@@ -152,7 +153,7 @@ struct adder_b200_video {
   int last_slot = -1;                                         /* slot holding the last single-frame call's events */
   /* frames integrated by integrate_frames_host[_raw] whose events did not fit the caller's buffer (frames_host_impl) */
   uint32_t pend_n = 0, pend_slot0 = 0;
-  bool pend_raw = false;
+  int pend_form = 0;
 
   cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
   cudaEvent_t ev_in[kRing] = {}, ev_k[kRing] = {}, ev_out[kRing] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -189,9 +190,11 @@ int set_device(const adder_b200_video* v) {
 int ensure_depth(adder_b200_video* v, uint32_t need) {
   if (need <= v->depth) return ADDER_OK;
   uint4* nn = nullptr;
-  CU(cudaMalloc(&nn, (size_t)need * v->Ppad * sizeof(uint4)));
+  /* two levels to a record (state_layout.h): the records of levels (2j, 2j+1) of all pixels are contiguous, so a deeper
+   * allocation keeps the old one as its prefix */
+  CU(cudaMalloc(&nn, (size_t)NODE_LEVELS_ALLOC(need) * v->Ppad * sizeof(uint4)));
   if (v->d_nodes) {
-    CU(cudaMemcpyAsync(nn, v->d_nodes, (size_t)v->depth * v->Ppad * sizeof(uint4), cudaMemcpyDeviceToDevice, v->stream));
+    CU(cudaMemcpyAsync(nn, v->d_nodes, (size_t)NODE_LEVELS_ALLOC(v->depth) * v->Ppad * sizeof(uint4), cudaMemcpyDeviceToDevice, v->stream));
     CU(cudaStreamSynchronize(v->stream));
     CU(cudaFree(v->d_nodes));
   }
@@ -389,7 +392,7 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   a.nodes = v->d_nodes;
   a.park_arena = v->d_park_arena;
   a.arena_slots = v->arena_slots;
-  a.level_stride = v->Ppad;
+  a.pair_stride = 2ull * v->Ppad;
   a.running = v->d_running;
   a.ev_words = reinterpret_cast<uint32_t*>(d_events);
   a.ev_cap = cap;
@@ -581,6 +584,10 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
 
     auto build = [&]() -> int {
       CU(cudaSetDevice(device));
+      if (const char* e = getenv("ADDER_B200_L2_FETCH")) { /* experiment: L2 fetch granularity in bytes (32 / 64 / 128) */
+        const int g = atoi(e);
+        if (g == 32 || g == 64 || g == 128) CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
+      }
       CU(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
       CU(cudaStreamCreateWithFlags(&v->stream_in, cudaStreamNonBlocking));
       CU(cudaStreamCreateWithFlags(&v->stream_out, cudaStreamNonBlocking));
@@ -893,7 +900,7 @@ int adder_b200_video_get_info(const adder_b200_video* v, adder_b200_video_info_t
   out->crf = v->crf;
   out->max_depth = v->depth;
   out->device = (uint32_t)v->device;
-  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)v->depth * sizeof(uint4)); /* the park arena is scratch, not state */
+  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)NODE_LEVELS_ALLOC(v->depth) * sizeof(uint4)); /* the park arena is scratch, not state */
   out->events_capacity = v->events_capacity;
   return ADDER_OK;
 }
@@ -985,6 +992,22 @@ int launch_raw_encode(adder_b200_video* v, cudaStream_t stream, const adder_even
   return ADDER_OK;
 }
 
+/* bytes of one frame in the compact host form (raw_kernel.cuh): dense P + 5 E when 4 E > P, else sparse 9 E */
+uint64_t compact_frame_bytes(uint64_t P, uint64_t n_events) { return 4ull * n_events > P ? P + 5ull * n_events : 9ull * n_events; }
+
+int launch_compact_encode(adder_b200_video* v, cudaStream_t stream, const adder_event_t* d_events, const uint32_t* d_n, uint64_t n_max, uint8_t* d_out) {
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v->device));
+  CU(cudaMemsetAsync(d_out, 0, v->P, stream)); /* the dense form's count bytes: pixels without events stay 0 */
+  const uint64_t want = (n_max + adder::kRawThreads - 1) / adder::kRawThreads;
+  const uint32_t blocks = (uint32_t)std::max<uint64_t>(std::min<uint64_t>(want, (uint64_t)sms * 8u), 1u);
+  adder::compact_encode_kernel<<<blocks, adder::kRawThreads, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_events), d_n, n_max, v->P,
+                                                                          (uint32_t)v->w * v->c, v->c, v->row0, d_out);
+  v->launches++;
+  CU(cudaGetLastError());
+  return ADDER_OK;
+}
+
 /* n_frames consecutive calls of integrate_matrix with H2D / kernels / D2H overlapped on three streams.
  * raw = false: 12-byte records to out; raw = true: the wire bytes of the same events.
  *
@@ -994,20 +1017,25 @@ int launch_raw_encode(adder_b200_video* v, cudaStream_t stream, const adder_even
  * the frames delivered, and the next call — which the caller makes with frames + frames_done * stride, as documented —
  * delivers the pending frames first and skips integrating them. */
 int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_stride, uint32_t n_frames, float time_spanned,
-                     void* out, size_t out_cap /* records, or bytes when raw */, bool raw, uint64_t* frame_counts,
+                     void* out, size_t out_cap /* records, or bytes when form != 0 */, int form /* 0 records, 1 raw wire bytes, 2 compact */, uint64_t* frame_counts,
                      uint32_t* chunk_counts, uint64_t* n_out, uint32_t* frames_done) {
   if (!v || (!frames && n_frames)) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
   if (n_out) *n_out = 0;
   if (frames_done) *frames_done = 0;
-  if (v->pend_n && v->pend_raw != raw)
+  const bool raw = form != 0; /* the frame leaves through d_raw (wire bytes or the compact form) */
+  static const char* const kFormName[3] = {"record", "raw", "compact"};
+  if (v->pend_n && v->pend_form != form)
     return fail(ADDER_ERR_BAD_PARAMS, "%u integrated frames are waiting to be delivered in the %s form: resume with the same call",
-                v->pend_n, v->pend_raw ? "raw" : "record");
+                v->pend_n, kFormName[v->pend_form]);
   if (v->pend_n > n_frames)
     return fail(ADDER_ERR_BAD_PARAMS, "%u integrated frames are waiting to be delivered: resume with at least that many frames", v->pend_n);
   if (int rc = set_device(v)) return rc;
   if (int rc = ensure_depth(v, derive_depth(v))) return rc;
   if (int rc = ensure_host_form(v)) return rc;
-  const size_t unit = raw ? raw_event_size(v) : sizeof(adder_event_t);
+  const size_t unit = form == 1 ? raw_event_size(v) : sizeof(adder_event_t);
+  auto frame_units = [&](uint64_t total) -> uint64_t { /* what one frame takes of `out`, in its units */
+    return form == 0 ? total : form == 1 ? total * unit : compact_frame_bytes(v->P, total);
+  };
   if (raw)
     for (int s = 0; s < kRing; s++)
       if (!v->d_raw[s]) CU(cudaMalloc(&v->d_raw[s], v->events_capacity * 11u));
@@ -1033,13 +1061,13 @@ int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_st
     CU(cudaEventSynchronize(v->ev_k[s]));
     const uint32_t* off = v->h_chunk_off[s];
     const uint64_t total = off[v->n_chunks];
-    const uint64_t need = raw ? total * unit : total;
+    const uint64_t need = frame_units(total);
     if (written + need > out_cap)
       return fail(ADDER_ERR_CAPACITY, "output holds %zu %s; frame %u needs %llu more than fit (its events are kept: call again from frames_done)",
                   out_cap, raw ? "bytes" : "records", f, (unsigned long long)(written + need - out_cap));
     if (total) {
       const void* src = raw ? (const void*)v->d_raw[s] : (const void*)v->d_events[s];
-      CU(cudaMemcpyAsync((uint8_t*)out + written * (raw ? 1 : unit), src, total * unit, cudaMemcpyDeviceToHost, v->stream_out));
+      CU(cudaMemcpyAsync((uint8_t*)out + written * (raw ? 1 : unit), src, raw ? need : total * unit, cudaMemcpyDeviceToHost, v->stream_out));
     }
     CU(cudaEventRecord(v->ev_out[s], v->stream_out));
     if (frame_counts) frame_counts[f] = total;
@@ -1059,8 +1087,11 @@ int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_st
       if (int rc = launch_gray(v, v->stream, v->d_rgb[s], v->d_frame[s])) return rc;
     if (int rc = launch_frame(v, v->stream, v->d_frame[s], time_spanned, v->d_events[s], v->events_capacity, v->d_chunk_off[s]))
       return rc;
-    if (raw)
+    if (form == 1)
       if (int rc = launch_raw_encode(v, v->stream, v->d_events[s], v->d_chunk_off[s] + v->n_chunks, v->events_capacity, v->d_raw[s]))
+        return rc;
+    if (form == 2)
+      if (int rc = launch_compact_encode(v, v->stream, v->d_events[s], v->d_chunk_off[s] + v->n_chunks, v->events_capacity, v->d_raw[s]))
         return rc;
     CU(cudaMemcpyAsync(v->h_chunk_off[s], v->d_chunk_off[s], ((size_t)v->n_chunks + 1) * sizeof(uint32_t),
                        cudaMemcpyDeviceToHost, v->stream));
@@ -1086,7 +1117,7 @@ int frames_host_impl(adder_b200_video* v, const uint8_t* frames, size_t frame_st
   if (rc_final == ADDER_ERR_CAPACITY && delivered < submitted) { /* integrated, not delivered: kept for the resuming call */
     v->pend_n = submitted - delivered;
     v->pend_slot0 = (slot0 + delivered) % kRing;
-    v->pend_raw = raw;
+    v->pend_form = form;
   }
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
     return fail(ADDER_ERR_CUDA, "draining the streams: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
@@ -1101,7 +1132,7 @@ int adder_b200_video_integrate_frames_host(adder_b200_video* v, const uint8_t* f
                                            size_t events_cap, uint64_t* frame_counts, uint32_t* chunk_counts,
                                            uint64_t* n_events, uint32_t* frames_done) {
   return guarded([&]() -> int {
-    return frames_host_impl(v, frames, frame_stride, n_frames, time_spanned, events_out, events_cap, false, frame_counts,
+    return frames_host_impl(v, frames, frame_stride, n_frames, time_spanned, events_out, events_cap, 0, frame_counts,
                             chunk_counts, n_events, frames_done);
   });
 }
@@ -1111,8 +1142,85 @@ int adder_b200_video_integrate_frames_host_raw(adder_b200_video* v, const uint8_
                                                uint64_t* frame_counts, uint32_t* chunk_counts, uint64_t* n_bytes,
                                                uint32_t* frames_done) {
   return guarded([&]() -> int {
-    return frames_host_impl(v, frames, frame_stride, n_frames, time_spanned, bytes_out, bytes_cap, true, frame_counts,
+    return frames_host_impl(v, frames, frame_stride, n_frames, time_spanned, bytes_out, bytes_cap, 1, frame_counts,
                             chunk_counts, n_bytes, frames_done);
+  });
+}
+
+int adder_b200_video_integrate_frames_host_compact(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
+                                                   uint32_t n_frames, float time_spanned, uint8_t* bytes_out, size_t bytes_cap,
+                                                   uint64_t* frame_counts, uint32_t* chunk_counts, uint64_t* n_bytes,
+                                                   uint32_t* frames_done) {
+  return guarded([&]() -> int {
+    return frames_host_impl(v, frames, frame_stride, n_frames, time_spanned, bytes_out, bytes_cap, 2, frame_counts,
+                            chunk_counts, n_bytes, frames_done);
+  });
+}
+
+uint64_t adder_b200_compact_frame_bytes(uint64_t n_px, uint64_t n_events) { return compact_frame_bytes(n_px, n_events); }
+
+/* Host side of the compact form: the frame's 12-byte records back, on n_threads host threads (the work is a memory-bound
+ * scatter: 12 bytes written per event). */
+int adder_b200_expand_compact(uint16_t width, uint16_t rows, uint8_t channels, uint16_t row0, const uint8_t* block, uint64_t n_events,
+                              adder_event_t* events_out, uint32_t n_threads) {
+  return guarded([&]() -> int {
+    if (!width || !rows || !channels || (n_events && (!block || !events_out))) return fail(ADDER_ERR_BAD_PARAMS, "bad argument");
+    const uint64_t P = (uint64_t)width * rows * channels, WC = (uint64_t)width * channels;
+    const bool dense = 4ull * n_events > P;
+    const uint32_t T = std::max<uint32_t>(1u, std::min<uint32_t>(n_threads ? n_threads : 1u, 256u));
+    auto put = [&](adder_event_t& e, uint64_t idx, const uint8_t* dt) {
+      const uint64_t y = idx / WC, rem = idx - y * WC;
+      e.x = (uint16_t)(rem / channels);
+      e.y = (uint16_t)(y + row0);
+      e.c = channels == 1 ? (uint8_t)ADDER_C_NONE : (uint8_t)(rem % channels);
+      e.d = dt[0];
+      e.reserved = 0;
+      memcpy(&e.t, dt + 1, 4);
+    };
+    std::vector<std::thread> pool;
+    std::vector<int> bad(T, 0);
+    if (!dense) { /* E x {index, d, t}: any split of the events works */
+      auto work = [&](uint32_t t) {
+        const uint64_t a = n_events * t / T, b = n_events * (t + 1) / T;
+        for (uint64_t k = a; k < b; k++) {
+          uint32_t idx;
+          memcpy(&idx, block + 9ull * k, 4);
+          if (idx >= P) { bad[t] = 1; return; }
+          put(events_out[k], idx, block + 9ull * k + 4);
+        }
+      };
+      for (uint32_t t = 1; t < T; t++) pool.emplace_back(work, t);
+      work(0);
+      for (auto& th : pool) th.join();
+    } else { /* count bytes | E x {d, t}: a thread takes a run of pixels; its first event is the sum of the counts before it */
+      std::vector<uint64_t> first(T + 1, 0);
+      auto count = [&](uint32_t t) {
+        const uint64_t a = P * t / T, b = P * (t + 1) / T;
+        uint64_t sum = 0;
+        for (uint64_t i = a; i < b; i++) sum += block[i];
+        first[t + 1] = sum;
+      };
+      for (uint32_t t = 1; t < T; t++) pool.emplace_back(count, t);
+      count(0);
+      for (auto& th : pool) th.join();
+      pool.clear();
+      for (uint32_t t = 0; t < T; t++) first[t + 1] += first[t];
+      if (first[T] != n_events) return fail(ADDER_ERR_BAD_PARAMS, "compact block: the count bytes add up to %llu events, not %llu",
+                                            (unsigned long long)first[T], (unsigned long long)n_events);
+      const uint8_t* body = block + P;
+      auto work = [&](uint32_t t) {
+        const uint64_t a = P * t / T, b = P * (t + 1) / T;
+        uint64_t k = first[t];
+        for (uint64_t i = a; i < b; i++)
+          for (uint32_t j = block[i]; j; j--, k++) put(events_out[k], i, body + 5ull * k);
+      };
+      for (uint32_t t = 1; t < T; t++) pool.emplace_back(work, t);
+      work(0);
+      for (auto& th : pool) th.join(); /* before `first` and the closures go out of scope */
+    }
+    for (uint32_t t = 0; t < T; t++)
+      if (bad[t]) return fail(ADDER_ERR_BAD_PARAMS, "compact block: a pixel index lies outside the plane");
+    return ADDER_OK;
   });
 }
 
@@ -1267,7 +1375,7 @@ int adder_b200_video_read_px(adder_b200_video* v, size_t index, adder_b200_px_st
   out->time_mode = (uint8_t)v->time_mode;
   for (uint32_t k = 0; k < out->length && k < v->depth; k++) {
     uint4 n;
-    CU(cudaMemcpy(&n, v->d_nodes + (size_t)k * v->Ppad + index, sizeof(n), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&n, v->d_nodes + NODE_SLOT(k, index, v->Ppad), sizeof(n), cudaMemcpyDeviceToHost));
     memcpy(&out->nodes[k].integration, &n.x, 4);
     memcpy(&out->nodes[k].delta_t, &n.y, 4);
     memcpy(&out->nodes[k].best_delta_t, &n.z, 4);

@@ -58,7 +58,7 @@ struct FrameArgs {
   uint4* nodes;
   uint2* park_arena;               /* events beyond the shared-memory slots: [CTA][park buffer][slot][pixel-in-tile] */
   uint32_t arena_slots;            /* slots per pixel in the arena (allocated node depth + 2 - S covers the worst case) */
-  unsigned long long level_stride; /* uint4 elements between levels */
+  unsigned long long pair_stride;  /* uint4 elements between the records of levels (2j, 2j+1) and (2j+2, 2j+3): 2 * Ppad */
   uint8_t* running;
   uint32_t* ev_words;        /* output records as 3 u32 words each; frame f's start at f * ev_cap records */
   unsigned long long ev_cap; /* records per frame */
@@ -86,14 +86,33 @@ template <bool kCoherent>
 __device__ __forceinline__ uint4 ld_state(const uint4* p) { return kCoherent ? __ldcg(p) : *p; }
 template <bool kCoherent>
 __device__ __forceinline__ uint2 ld_state(const uint2* p) { return kCoherent ? __ldcg(p) : *p; }
+/* root and first child of a pixel: one 32-byte record, one 256-bit access */
+template <bool kCoherent>
+__device__ __forceinline__ void ld_state256(const uint4* p, uint4& a, uint4& b) {
+  if (kCoherent)
+    asm volatile("ld.relaxed.gpu.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p)
+                 : "memory");
+  else
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st_state256(uint4* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 template <bool kCoherent>
 struct GlobalNodes {
-  uint4* p; /* &nodes[i] */
-  unsigned long long stride;
+  uint4* p; /* the pixel's first record: &nodes[NODE_SLOT(0, i, Ppad)] */
+  unsigned long long stride; /* uint4 elements from one of the pixel's records to the next: 2 * Ppad */
   uint32_t n_loads, n_stores; /* only read by the counting variant of the kernel */
+  __device__ __forceinline__ uint4* at(uint32_t k) const { return p + (unsigned long long)(k >> 1) * stride + (k & 1u); }
   __device__ __forceinline__ Node load(uint32_t k) {
     n_loads++;
-    const uint4 v = ld_state<kCoherent>(p + (unsigned long long)k * stride);
+    const uint4 v = ld_state<kCoherent>(at(k));
     Node n;
     n.integ = __uint_as_float(v.x);
     n.dt = __uint_as_float(v.y);
@@ -103,15 +122,25 @@ struct GlobalNodes {
   }
   __device__ __forceinline__ void store(uint32_t k, const Node& n) {
     n_stores++;
-    p[(unsigned long long)k * stride] = make_uint4(__float_as_uint(n.integ), __float_as_uint(n.dt), __float_as_uint(n.best_dt), n.w);
+    *at(k) = make_uint4(__float_as_uint(n.integ), __float_as_uint(n.dt), __float_as_uint(n.best_dt), n.w);
+  }
+  /* A freshly spawned tail (PixelNode::new).  When it opens a new record (even level) the whole 32 bytes are written — the
+   * other half is beyond the pixel's length, so its content is free — and the sector needs no fill from DRAM. */
+  __device__ __forceinline__ void store_fresh(uint32_t k, const Node& n) {
+    n_stores++;
+    const uint4 v = make_uint4(__float_as_uint(n.integ), __float_as_uint(n.dt), __float_as_uint(n.best_dt), n.w);
+    if (k & 1u)
+      *at(k) = v;
+    else
+      st_state256(at(k), v, make_uint4(0u, 0u, 0u, 0u));
   }
   /* level 1 is fetched with the root, before the length is known: it counts as algorithmic traffic
    * only when the state machine needed it; a level requested ahead and then dropped does not count */
-  /* every level the walk will visit, requested at once (no register, no scoreboard) */
+  /* every record the walk will visit, requested at once (no register, no scoreboard) */
   __device__ __forceinline__ void prefetch_levels(uint32_t len) {
 #if ADDER_DEEP_PF
-    const uint4* q = p + 2ull * stride;
-    for (uint32_t k = 2; k < len; k++, q += stride) {
+    const uint4* q = p + stride;
+    for (uint32_t k = 2; k < len; k += 2, q += stride) {
 #if ADDER_DEEP_PF == 1
       asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
 #else
@@ -120,11 +149,28 @@ struct GlobalNodes {
     }
 #endif
   }
+  /* record j = levels 2j and 2j+1 in one 256-bit access; b_live: level 2j+1 belongs to the stack (it counts as traffic) */
+  __device__ __forceinline__ void load_pair(uint32_t j, Node& na, Node& nb, bool b_live) {
+    n_loads += b_live ? 2u : 1u;
+    uint4 a, b;
+    ld_state256<kCoherent>(p + (unsigned long long)j * stride, a, b);
+    na.integ = __uint_as_float(a.x), na.dt = __uint_as_float(a.y), na.best_dt = __uint_as_float(a.z), na.w = a.w;
+    nb.integ = __uint_as_float(b.x), nb.dt = __uint_as_float(b.y), nb.best_dt = __uint_as_float(b.z), nb.w = b.w;
+  }
+  /* the whole record is written (one sector, no fill); n_live of its two nodes belong to the stack */
+  __device__ __forceinline__ void store_pair(uint32_t j, const Node& na, const Node& nb, uint32_t n_live) {
+    n_stores += n_live;
+    st_state256(p + (unsigned long long)j * stride,
+                make_uint4(__float_as_uint(na.integ), __float_as_uint(na.dt), __float_as_uint(na.best_dt), na.w),
+                make_uint4(__float_as_uint(nb.integ), __float_as_uint(nb.dt), __float_as_uint(nb.best_dt), nb.w));
+  }
   __device__ __forceinline__ void used_preloaded() { n_loads++; }
   __device__ __forceinline__ void unused_load() { n_loads--; }
+  __device__ __forceinline__ void unused_loads(uint32_t n) { n_loads -= n; }
   /* px_frame falls back to px_step: root and level 1 again, as they are in memory (nothing has been stored yet) */
   __device__ __forceinline__ void reload(Node& n0, Node& n1) {
-    const uint4 a = ld_state<kCoherent>(p), b = ld_state<kCoherent>(p + stride);
+    uint4 a, b;
+    ld_state256<kCoherent>(p, a, b);
     n0.integ = __uint_as_float(a.x), n0.dt = __uint_as_float(a.y), n0.best_dt = __uint_as_float(a.z), n0.w = a.w;
     n1.integ = __uint_as_float(b.x), n1.dt = __uint_as_float(b.y), n1.best_dt = __uint_as_float(b.z), n1.w = b.w;
     n_loads = 1u; /* the root; level 1 counts when px_step uses it */
@@ -409,8 +455,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   auto fetch_px = [&](uint32_t i) {
     if (i < a.P) {
       h_next = ld_state<kMulti>(a.hdr + i);
-      n0_next = ld_state<kMulti>(a.nodes + i);
-      n1_next = ld_state<kMulti>(a.nodes + a.level_stride + i);
+      ld_state256<kMulti>(a.nodes + 2ull * i, n0_next, n1_next);
     }
   };
   /* First state load of tile t.  A launch spans n_frames frames; the tail of one frame overlaps the head of the
@@ -469,7 +514,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         if (r + 1u < my_rows) fetch_px(tile_start + 32u * row_of(r + 1u) + lane);
         uint32_t nev = 0;
         if (i < a.P) {
-          GlobalNodes<kMulti> mem{a.nodes + i, a.level_stride, 1u, 0u};
+          GlobalNodes<kMulti> mem{a.nodes + 2ull * i, a.pair_stride, 1u, 0u};
           EventPark<S> park{slot_t + q, slot_d + q, arena + (unsigned long long)b * a.arena_slots * TILE + q, TILE, a.arena_slots, 0u, 0u};
           PxHeader h{__uint_as_float(hraw.x), hraw.y};
           const Node n0{__uint_as_float(n0raw.x), __uint_as_float(n0raw.y), __uint_as_float(n0raw.z), n0raw.w};
@@ -630,10 +675,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
       const uint32_t i = (t_next - frame_of(t_next) * a.n_tiles) * TILE + 32u * row_of(0u) + lane;
       if (my_rows && i < a.P) { /* towards L2 now, into registers after the write-out */
         if ((lane & 15u) == 0u) prefetch_l2(a.hdr + i);
-        if ((lane & 7u) == 0u) {
-          prefetch_l2(a.nodes + i);
-          prefetch_l2(a.nodes + a.level_stride + i);
-        }
+        if ((lane & 3u) == 0u) prefetch_l2(a.nodes + 2ull * i); /* 128-byte lines: four 32-byte records each */
       }
     }
 
@@ -744,11 +786,12 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
 /* ---- small state kernels ---------------------------------------------------------------------- */
 
 /* Video::new (video.rs:364-382): every pixel = PixelArena::new(1.0, coord), event_pixel_tree.rs:69-87 */
-__global__ void init_state_kernel(uint2* hdr, uint4* level0, uint8_t* running, uint32_t P) {
+__global__ void init_state_kernel(uint2* hdr, uint4* nodes, uint8_t* running, uint32_t P) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   hdr[i] = make_uint2(0u, HDR_PACK(0, 10, 1, 1, 0, 0));
-  level0[i] = make_uint4(0u, 0u, 0u, NODE_PACK(0 /* get_d(1.0) */, 0, 0));
+  nodes[2ull * i] = make_uint4(0u, 0u, 0u, NODE_PACK(0 /* get_d(1.0) */, 0, 0)); /* the root: first half of the pixel's first record */
+  nodes[2ull * i + 1ull] = make_uint4(0u, 0u, 0u, 0u);
   running[i] = 0;
 }
 
@@ -775,12 +818,12 @@ __global__ void rect_c_kernel(uint2* hdr, uint32_t W, uint32_t C, uint32_t x0, u
 }
 
 /* set_initial_d (video.rs:780-801) */
-__global__ void set_initial_d_kernel(uint2* hdr, uint4* level0, const uint8_t* frame, uint32_t P) {
+__global__ void set_initial_d_kernel(uint2* hdr, uint4* nodes, const uint8_t* frame, uint32_t P) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   uint32_t v = frame[i];
   uint32_t d = v == 0u ? ADDER_D_ZERO_INTEGRATION : 31u - __clz(v); /* floor(log2(v)) */
-  level0[i].w = (level0[i].w & ~0xFFu) | d;
+  nodes[2ull * i].w = (nodes[2ull * i].w & ~0xFFu) | d;
   hdr[i].y = (hdr[i].y & ~0xFFu) | v;
 }
 

@@ -33,6 +33,9 @@
 
 #include "state_layout.h"
 
+#ifndef ADDER_PAIR_WALK
+#define ADDER_PAIR_WALK 0 /* 1: px_step walks an unshifted stack a 32-byte record (two levels) at a time */
+#endif
 #ifndef ADDER_D_MAX
 #define ADDER_D_MAX 127u
 #define ADDER_D_ZERO_INTEGRATION 128u
@@ -325,10 +328,10 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
     if (need_pop) {
       emit_abs(a, sink, lf, NODE_BEST_D(n0.w), n0.best_dt);
       popped = 1;
-      mem.store(0, fresh_node(intensity));
+      mem.store_fresh(0, fresh_node(intensity));
     } else {
       mem.store(0, n0);
-      if (a.depth > 1u) mem.store(1, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+      if (a.depth > 1u) mem.store_fresh(1, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
       new_len = 2;
       disp_has = true;
       disp_d = NODE_BEST_D(n0.w);
@@ -349,7 +352,7 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
         } else { /* :164-193 synthesise a best event, then pop it: the root becomes a fresh node */
           const uint32_t sd = n0.integ < 1.0f ? ADDER_D_ZERO_INTEGRATION : 31u - clz32(f2u(n0.integ));
           emit_abs(a, sink, lf, sd, n0.dt);
-          mem.store(0, fresh_node(intensity));
+          mem.store_fresh(0, fresh_node(intensity));
           cut = true;
         }
       } else {
@@ -372,6 +375,63 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
       const uint32_t k_end = (only_root && !shift) ? 1u : len;
       Node nk = n1; /* level 1 is already here; level k+1 is requested before level k is worked on */
       if (k_end > 1u) mem.used_preloaded(); /* n1 */
+#if ADDER_PAIR_WALK
+      /* The common walk (no arena shift, every level integrates): levels 2j and 2j+1 share one 32-byte record
+       * (state_layout.h), so the stack is walked a record at a time — one 256-bit load and one 256-bit store per two
+       * levels, the record after the one being worked on already requested.  Same results as the loop below. */
+      if (!shift && !only_root) {
+        if (len > 1u) {
+          Node ra, rb; /* the record requested ahead */
+          bool have = len > 2u;
+          if (have) mem.load_pair(1u, ra, rb, len > 3u);
+          if (len == 2u && nk.dt == 0.0f && nk.integ == 0.0f) nk.w = (nk.w & ~0xFFu) | get_d_from_intensity(intensity); /* :332-335 */
+          bool fired = integrate_main(nk, intensity, time);
+          mem.store(1u, nk);
+          uint32_t kf = 1; /* the level that fired, when one did */
+          uint32_t k = 2;
+          while (!fired && have) {
+            Node na = ra, nb = rb;
+            const bool b_live = k + 1u < len;
+            have = k + 2u < len;
+            if (have) mem.load_pair((k >> 1) + 1u, ra, rb, k + 3u < len);
+            if (k == len - 1u && na.dt == 0.0f && na.integ == 0.0f) na.w = (na.w & ~0xFFu) | get_d_from_intensity(intensity);
+            fired = integrate_main(na, intensity, time);
+            if (fired) { /* its child takes the record's other half; whatever lay deeper is dropped (:344-366) */
+              kf = k;
+              mem.unused_loads((b_live ? 1u : 0u) + (have ? 1u + (k + 3u < len ? 1u : 0u) : 0u));
+              if (k + 1u < a.depth) {
+                mem.store_pair(k >> 1, na, fresh_node(intensity), 2u);
+              } else {
+                mem.store_pair(k >> 1, na, fresh_node(intensity), 1u);
+                errbits |= ADDER_DEVERR_DEPTH;
+              }
+              break;
+            }
+            if (!b_live) { /* the stack ends here without a fire (a tail that was not fresh) */
+              mem.store_pair(k >> 1, na, fresh_node(intensity), 1u);
+              break;
+            }
+            if (k + 1u == len - 1u && nb.dt == 0.0f && nb.integ == 0.0f) nb.w = (nb.w & ~0xFFu) | get_d_from_intensity(intensity);
+            fired = integrate_main(nb, intensity, time);
+            mem.store_pair(k >> 1, na, nb, 2u);
+            if (fired) { /* the child opens the next record */
+              kf = k + 1u;
+              mem.unused_loads(have ? 1u + (k + 3u < len ? 1u : 0u) : 0u);
+              if (k + 2u < a.depth) mem.store_fresh(k + 2u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+              break;
+            }
+            k += 2u;
+          }
+          if (fired) {
+            if (kf == 1u) {
+              mem.unused_loads(have ? 1u + (len > 3u ? 1u : 0u) : 0u);
+              if (2u < a.depth) mem.store_fresh(2u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+            }
+            new_len = kf + 2u;
+          }
+        }
+      } else
+#endif
       for (uint32_t k = 1; k < k_end; k++) {
         Node nxt = nk;
         if (k + 1u < k_end) nxt = mem.load(k + 1u);
@@ -388,7 +448,7 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
           disp_dt = nk.best_dt;
         }
         if (fired) {
-          if (k + 1u - shift < a.depth) mem.store(k + 1u - shift, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+          if (k + 1u - shift < a.depth) mem.store_fresh(k + 1u - shift, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
           new_len = k + 2u;
           if (k + 1u < k_end) mem.unused_load(); /* the level requested ahead is dropped with the rest (:366) */
           break;
@@ -542,7 +602,7 @@ ADDER_HD bool px_frame(const PxParams& a, uint32_t v, PxHeader& h, const Node& n
       }
       if (lean) {
         mem.store(kf, cur);
-        if (kf + 1u < a.depth) mem.store(kf + 1u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+        if (kf + 1u < a.depth) mem.store_fresh(kf + 1u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
         new_len = kf + 2u;
         if (new_len > a.depth) new_len = a.depth;
       }

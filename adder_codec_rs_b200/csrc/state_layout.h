@@ -9,7 +9,11 @@
  *   hdr   : uint2[P]        .x = last_fired_t (f32 bits)                       event_pixel_tree.rs:56
  *                           .y = base_val | c_thresh<<8 | c_increase_counter<<16 | length<<24
  *                                | dtm_reached<<29 | popped_dtm<<30              :58-65
- *   nodes : uint4[K][Ppad]  level k of every pixel's node stack                  :41-49
+ *   nodes : uint4[ceil(K/2)][Ppad][2]   the node stacks, two levels to a 32-byte record        :41-49
+ *                           levels 2j and 2j+1 of pixel i are the two halves of record (j, i): a pixel's root and its
+ *                           first child arrive in one 256-bit access, and every record is one DRAM sector that belongs to
+ *                           ONE pixel (with level-major 16-byte nodes two neighbouring pixels shared a sector, and every
+ *                           level only some pixels reach cost up to twice its bytes: profiles/r02d, DRAM / counted 1.43-1.46)
  *                           .x = integration (f32)  .y = delta_t (f32)  .z = best_event.delta_t (f32)
  *                           .w = d | best_event.d<<8 | best_event.is_some()<<16
  *   running : u8[P]         VideoState.running_intensities                      video.rs:212
@@ -31,6 +35,9 @@
 #include <stdint.h>
 
 #define ADDER_TILE_PX 256u        /* pixels per tile = threads per CTA */
+/* uint4 index of level k of pixel i (ppad = padded pixel count): record (k/2, i), half k%2 */
+#define NODE_SLOT(k, i, ppad) ((((unsigned long long)((k) >> 1)) * (ppad) + (i)) * 2ull + ((k) & 1u))
+#define NODE_LEVELS_ALLOC(depth) ((((depth) + 1u) >> 1) << 1) /* levels the allocation holds for a depth */
 #define ADDER_MAX_DEPTH 31u       /* reference iteration guard, event_pixel_tree.rs:387 */
 
 #define HDR_BASE(y) ((y) & 0xFFu)

@@ -351,6 +351,24 @@ int adder_b200_video_timer_stop(adder_b200_video* v, float* ms);
 int adder_b200_synth_frames(adder_b200_video* v, uint8_t* d_frames, size_t frame_stride, uint32_t f0,
                             uint32_t n_frames, int kind, uint64_t seed);
 
+/* ---- compact host form: half the bytes across PCIe ---------------------------------------------
+ * The event records of a frame are in raster order, so their coordinates are redundant on the way to the host.
+ * integrate_frames_host_compact delivers, per frame, back to back in bytes_out:
+ *   dense  form, when 4 * E > P:   P count bytes (events of every pixel-channel, raster order), then E x {d:u8, t:u32 LE}
+ *   sparse form, otherwise:        E x {index:u32 LE (flat raster index (y*W + x)*C + c inside this plane), d:u8, t:u32 LE}
+ * with E = frame_counts[f] and P = W*H*C of this plane: adder_b200_compact_frame_bytes(P, E) bytes.  On uniform noise
+ * that is 5.7 instead of 11.3 bytes per pixel-frame.  Everything else (pipelining, capacity / resume contract,
+ * chunk_counts) is as for adder_b200_video_integrate_frames_host.  adder_b200_expand_compact turns one frame's block
+ * back into the 12-byte records on n_threads host threads (a host-side helper: it needs no device); a consumer that
+ * feeds an encoder can also walk the block directly. */
+int adder_b200_video_integrate_frames_host_compact(adder_b200_video* v, const uint8_t* frames, size_t frame_stride,
+                                                   uint32_t n_frames, float time_spanned, uint8_t* bytes_out, size_t bytes_cap,
+                                                   uint64_t* frame_counts, uint32_t* chunk_counts, uint64_t* n_bytes,
+                                                   uint32_t* frames_done);
+uint64_t adder_b200_compact_frame_bytes(uint64_t n_px, uint64_t n_events);
+int adder_b200_expand_compact(uint16_t width, uint16_t rows, uint8_t channels, uint16_t row0, const uint8_t* block, uint64_t n_events,
+                              adder_event_t* events_out, uint32_t n_threads);
+
 /* ================================================================================================
  * Event exchange between row bands.
  *
@@ -370,6 +388,8 @@ int adder_b200_synth_frames(adder_b200_video* v, uint8_t* d_frames, size_t frame
  *                   comm_attach(own band video, consumer comm) for its own band
  *   other ranks:    comm_open(band video, blob)
  *   every frame / batch of frames, every rank:   integrate_frames_device(...); comm_push_frames(...)
+ *     (several bands driven by ONE process: push them in rank order — a push waits, on the device, for the totals of the
+ *      lower bands, and kernels of one process can queue behind each other whatever their streams)
  *   consumer:       comm_wait_frames(seq0, n); read comm_frame(seq) on the comm's stream; comm_release_frames(seq0 + n)
  */
 typedef struct adder_b200_comm adder_b200_comm;

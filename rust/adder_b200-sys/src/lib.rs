@@ -182,6 +182,9 @@ extern "C" {
     pub fn adder_b200_video_timer_start(v: *mut adder_b200_video) -> c_int;
     pub fn adder_b200_video_timer_stop(v: *mut adder_b200_video, ms: *mut c_float) -> c_int;
     pub fn adder_b200_synth_frames(v: *mut adder_b200_video, d_frames: *mut u8, frame_stride: usize, f0: u32, n_frames: u32, kind: c_int, seed: u64) -> c_int;
+    pub fn adder_b200_video_integrate_frames_host_compact(v: *mut adder_b200_video, frames: *const u8, frame_stride: usize, n_frames: u32, time_spanned: c_float, bytes_out: *mut u8, bytes_cap: usize, frame_counts: *mut u64, chunk_counts: *mut u32, n_bytes: *mut u64, frames_done: *mut u32) -> c_int;
+    pub fn adder_b200_compact_frame_bytes(n_px: u64, n_events: u64) -> u64;
+    pub fn adder_b200_expand_compact(width: u16, rows: u16, channels: u8, row0: u16, block: *const u8, n_events: u64, events_out: *mut adder_event_t, n_threads: u32) -> c_int;
     pub fn adder_b200_comm_create(v: *mut adder_b200_video, world: u32, total_chunks: u32, slots: u32, out_stride: usize, out_: *mut *mut adder_b200_comm) -> c_int;
     pub fn adder_b200_comm_export(c: *mut adder_b200_comm, blob: *mut u8, cap: usize) -> c_int;
     pub fn adder_b200_comm_open(v: *mut adder_b200_video, blob: *const u8, blob_bytes: usize, out_: *mut *mut adder_b200_comm) -> c_int;

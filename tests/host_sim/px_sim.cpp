@@ -11,6 +11,9 @@
 #include <vector>
 
 #define ADDER_HOST_SIM 1
+#ifndef ADDER_PAIR_WALK
+#define ADDER_PAIR_WALK 1 /* the host build checks the record walk; the general loop is checked by building with 0 */
+#endif
 #include "../../include/adder_b200.h"
 #include "../../adder_codec_rs_b200/csrc/px_machine.cuh"
 #include "../../adder_codec_rs_b200/csrc/gray_math.h"
@@ -18,15 +21,20 @@
 namespace adder {
 int g_fast_div_ulps = 0;
 }
+static int g_entry = 0; /* 0: px_step (what the kernel calls by default), 1: px_frame (short path + fallback) */
 namespace {
 struct HostNodes {
   adder::Node* p;
   size_t stride;
   adder::Node load(uint32_t k) const { return p[(size_t)k * stride]; }
   void store(uint32_t k, const adder::Node& n) const { p[(size_t)k * stride] = n; }
+  void store_fresh(uint32_t k, const adder::Node& n) const { p[(size_t)k * stride] = n; }
   void used_preloaded() const {}
   void prefetch_levels(uint32_t) const {}
   void unused_load() const {}
+  void unused_loads(uint32_t) const {}
+  void load_pair(uint32_t j, adder::Node& a, adder::Node& b, bool) const { a = p[(size_t)(2 * j) * stride]; b = p[(size_t)(2 * j + 1) * stride]; }
+  void store_pair(uint32_t j, const adder::Node& a, const adder::Node& b, uint32_t) const { p[(size_t)(2 * j) * stride] = a; p[(size_t)(2 * j + 1) * stride] = b; }
   void reload(adder::Node& n0, adder::Node& n1) const { n0 = p[0]; n1 = p[stride]; }
 };
 struct VecSink {
@@ -112,12 +120,15 @@ size_t sim_integrate(sim_video* v, const uint8_t* frame, float time, uint32_t re
     uint8_t disp = 0;
     /* like the kernel: level 1 is fetched before the length is known */
     const adder::Node n1 = v->depth > 1 ? mem.load(1) : mem.load(0);
-    if (adder::px_frame(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)) v->running[i] = disp;
+    const bool show = g_entry ? adder::px_frame(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)
+                              : adder::px_step(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp);
+    if (show) v->running[i] = disp;
   }
   return v->events.size();
 }
 /* unit hooks for the two exact-by-construction shortcuts of px_machine.cuh */
 void sim_set_fast_div_ulps(int n) { adder::g_fast_div_ulps = n; }
+void sim_set_entry(int e) { g_entry = e; }
 uint32_t sim_div_ref(uint32_t u, uint32_t ref) {
   adder::PxParams p{};
   p.ref = ref;

@@ -37,6 +37,7 @@ def lib():
         L.sim_running.argtypes = [vp]
         L.sim_force_display.argtypes = [vp]
         L.sim_set_fast_div_ulps.argtypes = [i32]
+        L.sim_set_entry.argtypes = [i32]
         L.sim_gray_check.restype = C.c_uint64
         L.sim_gray_check.argtypes = [C.POINTER(C.c_uint64)]
         L.sim_gray_of.restype = u32

@@ -126,7 +126,8 @@ def test_exchange_in_one_process_delivers_the_whole_frame_in_order(name, world, 
     seq = 0
     for f0 in range(0, case.n_frames, batch):
         n = min(batch, case.n_frames - f0)
-        for r in reversed(range(world)):  # queue the higher bands first: their pushes must wait for the lower ones
+        for r in range(world):  # inside one process the bands are queued in rank order: a push waits only for pushes queued before it,
+            # so streams that share a hardware queue (CUDA_DEVICE_MAX_CONNECTIONS) cannot block each other
             b, (P, d_fr, d_ev, d_off) = bands[r], bufs[r]
             d_fr.from_host(np.ascontiguousarray(frames[f0:f0 + n, b.row0:b.row0 + b.rows]))
             b.integrate_frames_device(d_fr.ptr, P, n, case.time, d_ev.ptr, P * 4, d_off.ptr)

@@ -52,8 +52,12 @@ class _SimAdapter:
         self.in_interval = n
 
 
+@pytest.mark.parametrize("entry", [0, 1], ids=["px_step", "px_frame"])
 @pytest.mark.parametrize("case", [c for c in cases.CASES if not c.initial_d and c.roi is None], ids=lambda c: c.name)
-def test_machine_matches_oracle(case):
+def test_machine_matches_oracle(case, entry):
+    from tests import sim_py
+
+    sim_py.lib().sim_set_entry(entry)  # the general state machine (with the record walk), and the short path in front of it
     ov = O.Video(case.w, case.h, case.c, O.MODE_FRAME_PERFECT)
     cases.configure(ov, case)
     sa = _SimAdapter(case)
