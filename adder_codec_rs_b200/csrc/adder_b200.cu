@@ -1472,9 +1472,7 @@ struct adder_b200_framer {
   float practical_d_max = 0.0f;
   uint64_t frame_px = 0;
   cudaStream_t stream = nullptr;
-  unsigned long long* d_running_ts = nullptr;
-  long long* d_last_filled = nullptr;
-  uint8_t* d_last_intensity = nullptr;
+  uint4* d_px_state = nullptr; /* running timestamp | last filled frame << 8 | last intensity, framer_kernel.cuh */
   uint8_t *d_ring_val = nullptr, *d_ring_some = nullptr;
   long long *d_offset_max = nullptr, *d_forced = nullptr;
   uint8_t *d_tracker = nullptr, *d_status = nullptr;
@@ -1533,9 +1531,7 @@ int framer_ingest(adder_b200_framer* f, const adder_event_t* d_events, const uin
   a.practical_d_max = f->practical_d_max;
   a.exact_lut = f->d_exact_lut;
   a.buffer_limit = f->buffer_limit;
-  a.running_ts = f->d_running_ts;
-  a.last_filled = f->d_last_filled;
-  a.last_intensity = f->d_last_intensity;
+  a.px_state = f->d_px_state;
   a.ring_val = f->d_ring_val;
   a.ring_some = f->d_ring_some;
   a.ring_frames = f->ring_frames;
@@ -1596,9 +1592,7 @@ int adder_b200_framer_create(uint16_t width, uint16_t height, uint8_t channels, 
       CU(cudaSetDevice(device));
       CU(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
       const uint64_t P = f->frame_px;
-      CU(cudaMalloc(&f->d_running_ts, P * sizeof(unsigned long long)));
-      CU(cudaMalloc(&f->d_last_filled, P * sizeof(long long)));
-      CU(cudaMalloc(&f->d_last_intensity, P));
+      CU(cudaMalloc(&f->d_px_state, P * sizeof(uint4)));
       CU(cudaMalloc(&f->d_ring_val, P * f->ring_frames));
       CU(cudaMalloc(&f->d_ring_some, P * f->ring_frames));
       CU(cudaMalloc(&f->d_offset_max, f->n_chunks * sizeof(long long)));
@@ -1615,14 +1609,12 @@ int adder_b200_framer_create(uint16_t width, uint16_t height, uint8_t channels, 
         adder::build_exact_lut(ref_interval, lut);
         CU(cudaMemcpyAsync(f->d_exact_lut, lut, sizeof(lut), cudaMemcpyHostToDevice, f->stream)); /* the build ends with a stream sync */
       }
-      CU(cudaMemsetAsync(f->d_running_ts, 0, P * sizeof(unsigned long long), f->stream));
-      CU(cudaMemsetAsync(f->d_last_intensity, 0, P, f->stream));
       CU(cudaMemsetAsync(f->d_ring_val, 0, P * f->ring_frames, f->stream));
       CU(cudaMemsetAsync(f->d_ring_some, 0, P * f->ring_frames, f->stream));
       CU(cudaMemsetAsync(f->d_tracker, 0, f->n_chunks, f->stream));
       CU(cudaMemsetAsync(f->d_err, 0, sizeof(uint32_t), f->stream));
       const uint64_t nn = std::max<uint64_t>(P, f->n_chunks);
-      adder::framer_init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, f->stream>>>(f->d_last_filled, P, f->d_offset_max, f->d_forced, f->n_chunks);
+      adder::framer_init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, f->stream>>>(f->d_px_state, P, f->d_offset_max, f->d_forced, f->n_chunks);
       CU(cudaGetLastError());
       CU(cudaStreamSynchronize(f->stream));
       return ADDER_OK;
@@ -1641,9 +1633,7 @@ void adder_b200_framer_destroy(adder_b200_framer* f) {
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
   cudaFree(f->d_exact_lut);
-  cudaFree(f->d_running_ts);
-  cudaFree(f->d_last_filled);
-  cudaFree(f->d_last_intensity);
+  cudaFree(f->d_px_state);
   cudaFree(f->d_ring_val);
   cudaFree(f->d_ring_some);
   cudaFree(f->d_offset_max);
@@ -1725,7 +1715,7 @@ int adder_b200_framer_flush_frame_buffer(adder_b200_framer* f, int* frame_ready)
       int sms = 0;
       CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device));
       adder::framer_flush_kernel<<<sms * 4, 256, 0, f->stream>>>(f->d_ring_val, f->d_ring_some, f->ring_frames, f->frame_px, f->frames_written,
-                                                               f->d_last_intensity, f->d_last_filled);
+                                                               f->d_px_state);
       CU(cudaGetLastError());
     }
     if (int rc = framer_refresh(f, 2, f->d_off_stage)) return rc;

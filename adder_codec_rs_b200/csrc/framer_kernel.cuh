@@ -11,8 +11,8 @@
  * The reference keeps, per chunk, a VecDeque of frames of Option<u8> plus filled counts.  Here the frames of the
  * whole plane live in a ring indexed by ABSOLUTE output frame number (deque index i of a chunk is absolute frame
  * frames_written + i), one value byte and one is-some byte per pixel; "filled" is a reduction over the is-some
- * bytes instead of a counter, so the fill needs no atomics.  Per pixel-channel state: running timestamp (u64), last
- * filled frame (i64), last intensity (u8).
+ * bytes instead of a counter, so the fill needs no atomics.  Per pixel-channel state, packed into one 16-byte record:
+ * running timestamp (u64), last filled frame (56 bits, signed), last intensity (u8).
  *
  * One thread handles one RUN of consecutive events of the same pixel-channel (the transcoder's stream keeps a pixel's
  * events of a frame contiguous; that is the precondition of ingest_events): the thread whose event starts a run walks it
@@ -37,10 +37,9 @@ struct FramerArgs {
   uint32_t codec_version, framed_source, view_mode, absolute_t;
   float practical_d_max;
   long long buffer_limit; /* < 0: None */
-  /* per pixel-channel */
-  unsigned long long* running_ts;
-  long long* last_filled;
-  uint8_t* last_intensity;
+  /* per pixel-channel, one 16-byte record (one 128-bit load and store per run of events instead of three of each):
+   * .x/.y = running timestamp (u64), .z/.w = last filled frame (i64) << 8 | last intensity */
+  uint4* px_state;
   /* frame ring */
   uint8_t* ring_val;
   uint8_t* ring_some;
@@ -52,6 +51,16 @@ struct FramerArgs {
   uint32_t* err;           /* bit 0: an event reaches beyond the ring (the reference would grow its VecDeque) */
   const uint8_t* exact_lut; /* [257] build_exact_lut(ref_interval): the Intensity byte of exactly integral intensities */
 };
+
+__host__ __device__ __forceinline__ unsigned long long framer_state_ts(const uint4& s) { return (unsigned long long)s.x | ((unsigned long long)s.y << 32); }
+__host__ __device__ __forceinline__ long long framer_state_last_filled(const uint4& s) {
+  return (long long)((unsigned long long)s.z | ((unsigned long long)s.w << 32)) >> 8; /* arithmetic shift: -1 stays -1 */
+}
+__host__ __device__ __forceinline__ uint32_t framer_state_intensity(const uint4& s) { return s.z & 0xFFu; }
+__host__ __device__ __forceinline__ uint4 framer_state_pack(unsigned long long ts, long long last_filled, uint32_t intensity) {
+  const unsigned long long p = ((unsigned long long)last_filled << 8) | (intensity & 0xFFu);
+  return make_uint4((uint32_t)ts, (uint32_t)(ts >> 32), (uint32_t)p, (uint32_t)(p >> 32));
+}
 
 /* n / d and n % d for a 64-bit n that almost always fits 32 bits (timestamps, frame numbers): the 64-bit division is a
  * long dependent sequence, and this kernel is bound by latency */
@@ -105,9 +114,10 @@ __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) 
     const uint32_t channel = cc == ADDER_C_NONE ? 0u : cc;
     if (x >= a.W || y >= a.H || channel >= a.C) continue;
     const unsigned long long gi = ((unsigned long long)y * a.W + x) * a.C + channel;
-    unsigned long long running_ts = a.running_ts[gi];
-    long long last_filled = a.last_filled[gi];
-    uint32_t intensity = a.last_intensity[gi];
+    const uint4 st = a.px_state[gi];
+    unsigned long long running_ts = framer_state_ts(st);
+    long long last_filled = framer_state_last_filled(st);
+    uint32_t intensity = framer_state_intensity(st);
     long long reach = -1;
     bool force = false;
     uint32_t e1 = w1, e2 = w2;
@@ -167,9 +177,7 @@ __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) 
       e1 = n1;
       e2 = n2;
     }
-    a.running_ts[gi] = running_ts;
-    a.last_filled[gi] = last_filled;
-    a.last_intensity[gi] = (uint8_t)intensity;
+    a.px_state[gi] = framer_state_pack(running_ts, last_filled, intensity);
     /* every pixel of a chunk reaches about the same frame, so nearly all of these would be atomics that change nothing
      * on one contended word per chunk (they were 70 % of the kernel's time): look first.  The word only grows, so a
      * stale read can at worst cause an atomic that was not needed. */
@@ -249,21 +257,21 @@ __global__ void __launch_bounds__(256) framer_pop_kernel(uint8_t* __restrict__ r
 
 /* flush_frame_buffer (driver.rs:633-680): every empty pixel of the frame at the front takes its last intensity */
 __global__ void __launch_bounds__(256) framer_flush_kernel(uint8_t* __restrict__ ring_val, uint8_t* __restrict__ ring_some, uint32_t ring_frames,
-                                                           unsigned long long frame_px, long long front, const uint8_t* __restrict__ last_intensity,
-                                                           long long* __restrict__ last_filled) {
+                                                           unsigned long long frame_px, long long front, uint4* __restrict__ px_state) {
   const unsigned long long base = (unsigned long long)(front % (long long)ring_frames) * frame_px;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < frame_px; i += (unsigned long long)gridDim.x * blockDim.x) {
     if (!ring_some[base + i]) {
+      const uint4 st = px_state[i];
       ring_some[base + i] = 1;
-      ring_val[base + i] = last_intensity[i];
-      last_filled[i] += 1;
+      ring_val[base + i] = (uint8_t)framer_state_intensity(st);
+      px_state[i] = framer_state_pack(framer_state_ts(st), framer_state_last_filled(st) + 1, framer_state_intensity(st));
     }
   }
 }
 
-__global__ void framer_init_kernel(long long* last_filled, unsigned long long n, long long* offset_max, long long* forced_frame, uint32_t n_chunks) {
+__global__ void framer_init_kernel(uint4* px_state, unsigned long long n, long long* offset_max, long long* forced_frame, uint32_t n_chunks) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) last_filled[i] = -1; /* driver.rs:349-353 */
+  if (i < n) px_state[i] = framer_state_pack(0ull, -1, 0u); /* last_filled_frame_ref = -1, driver.rs:349-353 */
   if (i < n_chunks) {
     offset_max[i] = 0;
     forced_frame[i] = -1;
