@@ -1952,8 +1952,9 @@ int adder_b200_comm_push_frames(adder_b200_comm* c, uint32_t band, uint32_t chun
       a.seq0 = frame_seq0 + f0;
       a.local_done = c->d_local_done;
       a.err = c->d_err;
-      /* a quarter of the SMs' worth of CTAs moves a band at NVLink rate and leaves room for the next integrate launch */
-      adder::exchange_push_kernel<<<std::max(sms / 4, 8), 256, 0, c->stream>>>(a);
+      /* one CTA per SM, 16 loads in flight per thread: enough to fill an NVLink direction; the CTAs take a fifth of an
+       * SM's thread slots from the next integrate launch while they run */
+      adder::exchange_push_kernel<<<std::max(sms, 8), 256, 0, c->stream>>>(a);
       CU(cudaGetLastError());
     }
     /* Two batches may be outstanding (the caller alternates two sets of buffers): whatever the band's stream is given

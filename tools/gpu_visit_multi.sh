@@ -8,7 +8,7 @@ echo "== exchange between processes (CUDA IPC over NVLink), sharding tests"
 NCCL_DEBUG=WARN timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -6
 echo "== bench --gpus $N --frames $FR (strong scaling, gather legs)"
 NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --frames $FR --steps $ST --warmup 3 > gpurun_out/r02g_bench_n$N.json 2> gpurun_out/r02g_bench_n$N.err; echo "rc=$?"
-grep -E "NCCL INFO.*(nranks|Connected all|NVLS|comm 0x)" gpurun_out/r02g_bench_n$N.err | head -12 > gpurun_out/r02g_nccl_n$N.txt; wc -l gpurun_out/r02g_nccl_n$N.txt
+grep "NCCL INFO" gpurun_out/r02g_bench_n$N.json | grep -E "NCCL version|nranks|NVLS multicast|via P2P" | head -40 > gpurun_out/r02g_nccl_n$N.txt; wc -l gpurun_out/r02g_nccl_n$N.txt
 python - <<PY
 import json
 try:

@@ -5,7 +5,6 @@
   <tag>_kernel_metrics.txt  selected raw metrics of the integrate kernel from the --set full capture
   <tag>_hot_lines.txt       per-source-line shares of instructions and stall samples
   <tag>_bench.json          the bench line of the same visit (NOT taken under a profiler)
-  roofline_traffic.json     dram bytes per launch, read by bench.py for roofline.traffic
 usage: python tools/ncu_summary.py <tag>"""
 import collections
 import csv
@@ -85,12 +84,6 @@ if os.path.exists(rep):
         for r in rows[2:]:
             traffic.append(num(r[iR]) * scale[units[iR]] + num(r[iW]) * scale[units[iW]])
         iT = hdr.index("gpu__time_duration.sum")
-    if is_bench_workload:
-      json.dump({"tag": tag, "kernel": rows[2][iN], "dram_bytes_per_launch": sum(traffic) / len(traffic),
-                 "frames_per_launch": frames_per_launch, "dram_bytes_per_frame": sum(traffic) / len(traffic) / frames_per_launch,
-                 "launches_captured": len(traffic), "duration_under_ncu": [r[iT] + " " + units[iT] for r in rows[2:]],
-                 "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches"},
-                open(os.path.join(PR, "roofline_traffic.json"), "w"), indent=1)
     cs = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-id", ":::1"],
                         capture_output=True, text=True).stdout
     tmp = os.path.join("/tmp", f"{tag}_cs.csv")
