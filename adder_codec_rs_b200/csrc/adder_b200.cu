@@ -254,15 +254,28 @@ int realloc_chunks(adder_b200_video* v) {
   return ADDER_OK;
 }
 
-template <int R>
-void launch_r(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
+template <int R, bool kDeep>
+void launch_rd(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
   const size_t smem = adder::frame_kernel_smem(R);
   if (v->counting)
-    adder::integrate_frame_kernel<R, true, true><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, true, true, kDeep><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
   else if (a.n_frames > 1u)
-    adder::integrate_frame_kernel<R, false, true><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, false, true, kDeep><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
   else /* one frame: the variant compiled without the cross-frame dependency, fences and L2-only state loads */
-    adder::integrate_frame_kernel<R, false, false><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, false, false, kDeep><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+}
+template <int R>
+void launch_r(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
+  launch_rd<R, false>(v, a, stream);
+}
+/* The variant whose warps walk the levels below the first two together (kDeep).  Parity-green on every case
+ * (ADDER_B200_R=8 ADDER_B200_DEEP=1 pytest), but measured 33 % SLOWER than the per-lane walk on aged 8K stacks
+ * (1923 vs 1444 us per frame, profiles/r02i_ab_deep.txt): its passes are a chain of dependent L2 round trips with nothing
+ * requested ahead, where the per-lane loop always has the next level in flight.  Off unless ADDER_B200_DEEP=1. */
+bool use_deep(const adder_b200_video* v) {
+  if (v->R != 8) return false;
+  if (const char* e = getenv("ADDER_B200_DEEP")) return atoi(e) != 0;
+  return false;
 }
 template <int R>
 int occupancy_r(int* ctas_per_sm) {
@@ -282,6 +295,12 @@ int choose_grid(adder_b200_video* v) {
     default: rc = occupancy_r<8>(&per_sm); break;
   }
   if (rc) return rc;
+  if (v->R == 8) { /* the long-integration variant must fit as many CTAs: the grid is shared */
+    int deep_per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&deep_per_sm, adder::integrate_frame_kernel<8, false, true, true>, ADDER_TILE_PX,
+                                                     adder::frame_kernel_smem(8)));
+    per_sm = std::min(per_sm, deep_per_sm);
+  }
   if (per_sm < 1) return fail(ADDER_ERR_INTERNAL, "integrate_frame_kernel does not fit an SM");
   if (const char* e = getenv("ADDER_B200_CTAS_PER_SM")) {
     const int n = atoi(e);
@@ -295,7 +314,9 @@ void launch_variant(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t
     case 1: launch_r<1>(v, a, stream); break;
     case 2: launch_r<2>(v, a, stream); break;
     case 4: launch_r<4>(v, a, stream); break;
-    default: launch_r<8>(v, a, stream); break;
+    default:
+      if (use_deep(v)) launch_rd<8, true>(v, a, stream); else launch_rd<8, false>(v, a, stream);
+      break;
   }
 }
 template <int R>
@@ -303,6 +324,11 @@ int set_smem_attr() {
   CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
   CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
   CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  if (R == 8) {
+    CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
+    CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
+    CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
+  }
   return ADDER_OK;
 }
 /* rounds per tile: 8 (62 rows = 1984 pixels: with one shared-memory park slot per pixel the three park

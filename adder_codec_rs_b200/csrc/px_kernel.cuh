@@ -149,24 +149,8 @@ struct GlobalNodes {
     }
 #endif
   }
-  /* record j = levels 2j and 2j+1 in one 256-bit access; b_live: level 2j+1 belongs to the stack (it counts as traffic) */
-  __device__ __forceinline__ void load_pair(uint32_t j, Node& na, Node& nb, bool b_live) {
-    n_loads += b_live ? 2u : 1u;
-    uint4 a, b;
-    ld_state256<kCoherent>(p + (unsigned long long)j * stride, a, b);
-    na.integ = __uint_as_float(a.x), na.dt = __uint_as_float(a.y), na.best_dt = __uint_as_float(a.z), na.w = a.w;
-    nb.integ = __uint_as_float(b.x), nb.dt = __uint_as_float(b.y), nb.best_dt = __uint_as_float(b.z), nb.w = b.w;
-  }
-  /* the whole record is written (one sector, no fill); n_live of its two nodes belong to the stack */
-  __device__ __forceinline__ void store_pair(uint32_t j, const Node& na, const Node& nb, uint32_t n_live) {
-    n_stores += n_live;
-    st_state256(p + (unsigned long long)j * stride,
-                make_uint4(__float_as_uint(na.integ), __float_as_uint(na.dt), __float_as_uint(na.best_dt), na.w),
-                make_uint4(__float_as_uint(nb.integ), __float_as_uint(nb.dt), __float_as_uint(nb.best_dt), nb.w));
-  }
   __device__ __forceinline__ void used_preloaded() { n_loads++; }
   __device__ __forceinline__ void unused_load() { n_loads--; }
-  __device__ __forceinline__ void unused_loads(uint32_t n) { n_loads -= n; }
   /* px_frame falls back to px_step: root and level 1 again, as they are in memory (nothing has been stored yet) */
   __device__ __forceinline__ void reload(Node& n0, Node& n1) {
     uint4 a, b;
@@ -373,7 +357,11 @@ __device__ __forceinline__ uint32_t look_back(const unsigned long long* status, 
  * kCount = true is the instrumented twin used (untimed) to measure the algorithmic bytes of a
  * workload: it additionally sums node loads / stores, display writes and events into a.counters.
  */
-template <int R, bool kCount, bool kMulti>
+/* kDeep = the long-integration variant: the levels below the first two of an unchanged pixel's stack are walked by the
+ * lanes of the warp together (px_machine.cuh deep_item / deep_finish).  Stacks of neighbouring pixels differ in depth
+ * (2 .. 11 live nodes after a few hundred frames of a static scene), and a per-lane loop runs as long as the deepest of
+ * the 32: 36 warp-instructions per pixel on aged 8K stacks against 18 on two-node stacks (profiles/r02h_static_*). */
+template <int R, bool kCount, bool kMulti, bool kDeep = false>
 __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame_kernel(const FrameArgs a) {
   constexpr uint32_t ROWS = tile_rows(R), TILE = tile_px(R);
   constexpr uint32_t S = park_slots(R);
@@ -388,6 +376,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   __shared__ uint32_t s_wtot[kParkBufs][ROWS];
   __shared__ __align__(8) unsigned long long s_bar_a, s_bar_b;
   __shared__ uint8_t s_lut[260];
+  __shared__ uint32_t s_kf[kDeep ? kThreads : 1]; /* kDeep: per pixel of the row a warp is working on, the shallowest level that fired */
   __shared__ float s_running_t[kMaxLaunchFrames + 1]; /* a.running_t[], read once per tile */
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -420,6 +409,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
     mbar_init(&s_bar_b, 2u);
   }
   for (uint32_t j = tid; j < 257u; j += kThreads) s_lut[j] = a.px.exact_lut[j];
+  if (kDeep) s_kf[tid] = kNoFire;
   if (kMulti && a.running_t) {
     for (uint32_t j = tid; j <= n_frames; j += kThreads) s_running_t[j] = a.running_t[j];
   } else if (tid == 0) { /* a single frame: both values came with the arguments */
@@ -513,19 +503,21 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         const uint4 n0raw = n0_next, n1raw = n1_next;
         if (r + 1u < my_rows) fetch_px(tile_start + 32u * row_of(r + 1u) + lane);
         uint32_t nev = 0;
+        PxHeader h{__uint_as_float(hraw.x), hraw.y};
+        bool deferred = false; /* kDeep: the walk below level 1 is still to be done */
+        const uint32_t sample = samples[r * 32u + lane];
         if (i < a.P) {
           GlobalNodes<kMulti> mem{a.nodes + 2ull * i, a.pair_stride, 1u, 0u};
           EventPark<S> park{slot_t + q, slot_d + q, arena + (unsigned long long)b * a.arena_slots * TILE + q, TILE, a.arena_slots, 0u, 0u};
-          PxHeader h{__uint_as_float(hraw.x), hraw.y};
           const Node n0{__uint_as_float(n0raw.x), __uint_as_float(n0raw.y), __uint_as_float(n0raw.z), n0raw.w};
           const Node n1{__uint_as_float(n1raw.x), __uint_as_float(n1raw.y), __uint_as_float(n1raw.z), n1raw.w};
           uint8_t disp;
 #if ADDER_LEAN /* A/B: the short path of px_frame in front of the general state machine */
-          const bool show = px_frame(px, samples[r * 32u + lane], h, n0, n1, mem, park, errbits, &disp);
+          const bool show = px_frame(px, sample, h, n0, n1, mem, park, errbits, &disp);
 #else
-          const bool show = px_step(px, samples[r * 32u + lane], h, n0, n1, mem, park, errbits, &disp);
+          const bool show = px_step<kDeep>(px, sample, h, n0, n1, mem, park, errbits, &disp, &deferred);
 #endif
-          a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
+          if (!kDeep) a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
 #if ADDER_EV_STREAM >= 2
           if (show) __stcs(a.running + i, disp);
 #else
@@ -538,7 +530,62 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             c_stores += mem.n_stores;
             c_disp += show ? 1u : 0u;
             c_len_in += HDR_LENGTH(hraw.y);
-            c_len_out += HDR_LENGTH(h.y);
+            if (!kDeep) c_len_out += HDR_LENGTH(h.y);
+          }
+        }
+        if (kDeep) {
+          if (__ballot_sync(kFull, deferred)) { /* some pixel of this row has levels left to walk */
+            const uint32_t len_in = HDR_LENGTH(hraw.y);
+            const uint32_t my_len = deferred ? len_in : 0u;
+            const float my_i = (float)sample;
+            uint32_t* const kfw = s_kf + warp * 32u; /* all kNoFire between rows */
+            const uint32_t maxlen = __reduce_max_sync(kFull, my_len);
+            uint32_t k = 2;
+            while (k < maxlen) {
+              /* one pass = as many whole levels as fit the 32 lanes: level k's pixels, then level k+1's, ... (the number
+               * of pixels that reach a level falls with the level), each lane taking one (pixel, level) */
+              uint32_t used = 0, lvl = 0, src = lane;
+              bool active = false;
+              while (k < maxlen) {
+                const uint32_t m = __ballot_sync(kFull, my_len > k);
+                const uint32_t c = (uint32_t)__popc(m);
+                if (used + c > 32u) break;
+                if (lane >= used && lane < used + c) {
+                  active = true;
+                  lvl = k;
+                  src = __fns(m, 0u, (int)(lane - used) + 1); /* the (lane - used)-th pixel of the row that has level k */
+                }
+                used += c;
+                k++;
+              }
+              const float i_src = __shfl_sync(kFull, my_i, src);
+              const uint32_t len_src = __shfl_sync(kFull, my_len, src);
+              if (active && kfw[src] > lvl) { /* nothing shallower of that pixel has fired so far */
+                GlobalNodes<kMulti> dm{a.nodes + 2ull * (i - lane + src), a.pair_stride, 0u, 0u};
+                if (deep_item(dm, lvl, len_src, i_src, px.time)) atomicMin(&kfw[src], lvl);
+                if (kCount) {
+                  c_loads += dm.n_loads;
+                  c_stores += dm.n_stores;
+                }
+              }
+              __syncwarp();
+            }
+            if (deferred) { /* the pixel's own lane finishes the level that fired and learns the new length */
+              const uint32_t kf = kfw[lane];
+              kfw[lane] = kNoFire;
+              GlobalNodes<kMulti> fm{a.nodes + 2ull * i, a.pair_stride, 0u, 0u};
+              const uint32_t nl = deep_finish(px, fm, kf, len_in, my_i, errbits);
+              h.y = (h.y & ~(0x1Fu << 24)) | (nl << 24);
+              if (kCount) {
+                c_loads += fm.n_loads;
+                c_stores += fm.n_stores;
+              }
+            }
+            __syncwarp();
+          }
+          if (i < a.P) {
+            a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
+            if (kCount) c_len_out += HDR_LENGTH(h.y);
           }
         }
         /* place of this pixel's records inside its row's run: two ballots cover 0..2 events per

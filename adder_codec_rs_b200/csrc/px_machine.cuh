@@ -33,9 +33,6 @@
 
 #include "state_layout.h"
 
-#ifndef ADDER_PAIR_WALK
-#define ADDER_PAIR_WALK 0 /* 1: px_step walks an unshifted stack a 32-byte record (two levels) at a time */
-#endif
 #ifndef ADDER_D_MAX
 #define ADDER_D_MAX 127u
 #define ADDER_D_ZERO_INTEGRATION 128u
@@ -261,9 +258,12 @@ ADDER_HD bool pop_node(const PxParams& a, Sink& sink, float& lf, Node& nk) {
  * the kernel fetches both before it knows the length).  Returns true and sets *disp when
  * running_intensities must be written.
  */
-template <class Mem, class Sink>
+/* kDefer: an unshifted, fully integrating walk stops after level 1 and reports *deferred = true (header written with the
+ * old length): levels 2.. are then walked by deep_item / deep_finish below — in the kernel by the lanes of the warp
+ * together, because the lanes' stacks differ in depth and a per-lane loop runs as long as the deepest of 32. */
+template <bool kDefer = false, class Mem, class Sink>
 ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node n1, Mem& mem, Sink& sink, uint32_t& errbits,
-                      uint8_t* disp) {
+                      uint8_t* disp, bool* deferred = nullptr) {
   const float intensity = (float)v; /* matrix.mapv(f32::from), video.rs:665 */
   const float time = a.time;
   float lf = h.lf;
@@ -375,66 +375,14 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
       const uint32_t k_end = (only_root && !shift) ? 1u : len;
       Node nk = n1; /* level 1 is already here; level k+1 is requested before level k is worked on */
       if (k_end > 1u) mem.used_preloaded(); /* n1 */
-#if ADDER_PAIR_WALK
-      /* The common walk (no arena shift, every level integrates): levels 2j and 2j+1 share one 32-byte record
-       * (state_layout.h), so the stack is walked a record at a time — one 256-bit load and one 256-bit store per two
-       * levels, the record after the one being worked on already requested.  Same results as the loop below. */
-      if (!shift && !only_root) {
-        if (len > 1u) {
-          Node ra, rb; /* the record requested ahead */
-          bool have = len > 2u;
-          if (have) mem.load_pair(1u, ra, rb, len > 3u);
-          if (len == 2u && nk.dt == 0.0f && nk.integ == 0.0f) nk.w = (nk.w & ~0xFFu) | get_d_from_intensity(intensity); /* :332-335 */
-          bool fired = integrate_main(nk, intensity, time);
-          mem.store(1u, nk);
-          uint32_t kf = 1; /* the level that fired, when one did */
-          uint32_t k = 2;
-          while (!fired && have) {
-            Node na = ra, nb = rb;
-            const bool b_live = k + 1u < len;
-            have = k + 2u < len;
-            if (have) mem.load_pair((k >> 1) + 1u, ra, rb, k + 3u < len);
-            if (k == len - 1u && na.dt == 0.0f && na.integ == 0.0f) na.w = (na.w & ~0xFFu) | get_d_from_intensity(intensity);
-            fired = integrate_main(na, intensity, time);
-            if (fired) { /* its child takes the record's other half; whatever lay deeper is dropped (:344-366) */
-              kf = k;
-              mem.unused_loads((b_live ? 1u : 0u) + (have ? 1u + (k + 3u < len ? 1u : 0u) : 0u));
-              if (k + 1u < a.depth) {
-                mem.store_pair(k >> 1, na, fresh_node(intensity), 2u);
-              } else {
-                mem.store_pair(k >> 1, na, fresh_node(intensity), 1u);
-                errbits |= ADDER_DEVERR_DEPTH;
-              }
-              break;
-            }
-            if (!b_live) { /* the stack ends here without a fire (a tail that was not fresh) */
-              mem.store_pair(k >> 1, na, fresh_node(intensity), 1u);
-              break;
-            }
-            if (k + 1u == len - 1u && nb.dt == 0.0f && nb.integ == 0.0f) nb.w = (nb.w & ~0xFFu) | get_d_from_intensity(intensity);
-            fired = integrate_main(nb, intensity, time);
-            mem.store_pair(k >> 1, na, nb, 2u);
-            if (fired) { /* the child opens the next record */
-              kf = k + 1u;
-              mem.unused_loads(have ? 1u + (k + 3u < len ? 1u : 0u) : 0u);
-              if (k + 2u < a.depth) mem.store_fresh(k + 2u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
-              break;
-            }
-            k += 2u;
-          }
-          if (fired) {
-            if (kf == 1u) {
-              mem.unused_loads(have ? 1u + (len > 3u ? 1u : 0u) : 0u);
-              if (2u < a.depth) mem.store_fresh(2u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
-            }
-            new_len = kf + 2u;
-          }
-        }
-      } else
-#endif
+      const bool defer_deep = kDefer && !shift && !only_root;
       for (uint32_t k = 1; k < k_end; k++) {
+        if (defer_deep && k == 2u) { /* level 1 did not fire: the rest of the walk is done by deep_item / deep_finish */
+          *deferred = true;
+          break;
+        }
         Node nxt = nk;
-        if (k + 1u < k_end) nxt = mem.load(k + 1u);
+        if (k + 1u < k_end && !defer_deep) nxt = mem.load(k + 1u);
         bool fired = false;
         if (!only_root) {
           if (k == len - 1u && nk.dt == 0.0f && nk.integ == 0.0f) /* :332-335 */
@@ -450,7 +398,7 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
         if (fired) {
           if (k + 1u - shift < a.depth) mem.store_fresh(k + 1u - shift, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
           new_len = k + 2u;
-          if (k + 1u < k_end) mem.unused_load(); /* the level requested ahead is dropped with the rest (:366) */
+          if (k + 1u < k_end && !defer_deep) mem.unused_load(); /* the level requested ahead is dropped with the rest (:366) */
           break;
         }
         nk = nxt;
@@ -471,6 +419,39 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
   return false;
 }
 
+
+/* ---- the deferred part of a walk (px_step<true>): levels 2 .. len-1 of an unchanged, unshifted stack -------------------
+ * Each level is independent of the others until one fires (integrate_main reads only its own node, event_pixel_tree.rs:
+ * 418-479); the FIRST level that fires gets its fresh child and everything deeper is dropped (:344-366).  So the levels
+ * can be integrated in any order, by any lane: a level that does not fire is stored integrated (harmless if a shallower
+ * level turns out to have fired: it then lies beyond the new length), a level that fires is left untouched and reported;
+ * the owner of the pixel finishes the shallowest reported level.  Results are those of the sequential walk. */
+constexpr uint32_t kNoFire = 0xFFu;
+template <class Mem>
+ADDER_HD bool deep_item(Mem& mem, uint32_t k, uint32_t len, float intensity, float time) {
+  Node n = mem.load(k);
+  uint32_t w = n.w;
+  if (k == len - 1u && n.dt == 0.0f && n.integ == 0.0f) w = (w & ~0xFFu) | get_d_from_intensity(intensity); /* :332-335 */
+  const float sum = rn_add(n.integ, intensity);
+  if (sum >= d_shift_f32(NODE_D(w))) return true; /* fires: left as it is for deep_finish */
+  n.integ = sum;
+  n.dt = rn_add(n.dt, time);
+  n.w = w;
+  mem.store(k, n);
+  return false;
+}
+/* kf = the shallowest level deep_item reported, or kNoFire.  Returns the stack's new length. */
+template <class Mem>
+ADDER_HD uint32_t deep_finish(const PxParams& a, Mem& mem, uint32_t kf, uint32_t len, float intensity, uint32_t& errbits) {
+  if (kf == kNoFire) return len;
+  Node n = mem.load(kf);
+  if (kf == len - 1u && n.dt == 0.0f && n.integ == 0.0f) n.w = (n.w & ~0xFFu) | get_d_from_intensity(intensity);
+  integrate_main(n, intensity, a.time); /* fires: deep_item saw the same node and the same sum */
+  mem.store(kf, n);
+  if (kf + 1u < a.depth) mem.store_fresh(kf + 1u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+  const uint32_t new_len = kf + 2u;
+  return new_len > a.depth ? a.depth : new_len;
+}
 
 /*
  * px_frame — what the kernel calls: the common cases of px_step on a short path, everything else through px_step.

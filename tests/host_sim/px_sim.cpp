@@ -11,9 +11,6 @@
 #include <vector>
 
 #define ADDER_HOST_SIM 1
-#ifndef ADDER_PAIR_WALK
-#define ADDER_PAIR_WALK 1 /* the host build checks the record walk; the general loop is checked by building with 0 */
-#endif
 #include "../../include/adder_b200.h"
 #include "../../adder_codec_rs_b200/csrc/px_machine.cuh"
 #include "../../adder_codec_rs_b200/csrc/gray_math.h"
@@ -21,7 +18,7 @@
 namespace adder {
 int g_fast_div_ulps = 0;
 }
-static int g_entry = 0; /* 0: px_step (what the kernel calls by default), 1: px_frame (short path + fallback) */
+static int g_entry = 0; /* 0: px_step (what the kernel calls by default), 1: px_frame (short path + fallback), 2: px_step<true> + deferred deep walk */
 namespace {
 struct HostNodes {
   adder::Node* p;
@@ -32,9 +29,6 @@ struct HostNodes {
   void used_preloaded() const {}
   void prefetch_levels(uint32_t) const {}
   void unused_load() const {}
-  void unused_loads(uint32_t) const {}
-  void load_pair(uint32_t j, adder::Node& a, adder::Node& b, bool) const { a = p[(size_t)(2 * j) * stride]; b = p[(size_t)(2 * j + 1) * stride]; }
-  void store_pair(uint32_t j, const adder::Node& a, const adder::Node& b, uint32_t) const { p[(size_t)(2 * j) * stride] = a; p[(size_t)(2 * j + 1) * stride] = b; }
   void reload(adder::Node& n0, adder::Node& n1) const { n0 = p[0]; n1 = p[stride]; }
 };
 struct VecSink {
@@ -120,8 +114,22 @@ size_t sim_integrate(sim_video* v, const uint8_t* frame, float time, uint32_t re
     uint8_t disp = 0;
     /* like the kernel: level 1 is fetched before the length is known */
     const adder::Node n1 = v->depth > 1 ? mem.load(1) : mem.load(0);
-    const bool show = g_entry ? adder::px_frame(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)
-                              : adder::px_step(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp);
+    bool show;
+    if (g_entry == 2) { /* the kernel's long-integration variant: deferred deep walk, here visited deepest level first */
+      const uint32_t len_in = HDR_LENGTH(v->hdr[i].y);
+      bool deferred = false;
+      show = adder::px_step<true>(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp, &deferred);
+      if (deferred) {
+        uint32_t kf = adder::kNoFire;
+        for (uint32_t k = len_in; k-- > 2u;)
+          if (adder::deep_item(mem, k, len_in, (float)frame[i], p.time) && k < kf) kf = k;
+        const uint32_t nl = adder::deep_finish(p, mem, kf, len_in, (float)frame[i], v->err);
+        v->hdr[i].y = (v->hdr[i].y & ~(0x1Fu << 24)) | (nl << 24);
+      }
+    } else {
+      show = g_entry ? adder::px_frame(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)
+                     : adder::px_step(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp);
+    }
     if (show) v->running[i] = disp;
   }
   return v->events.size();
