@@ -82,14 +82,18 @@ constexpr uint32_t kFlagAggregate = 1u, kFlagPrefix = 2u;
 
 /* level k of pixel i: one 128-bit access, 512 contiguous bytes per warp.  kCoherent: the launch spans several frames,
  * so the state a tile reads may have been written by another SM a moment ago — read it where it is coherent (L2). */
+#ifndef ADDER_STATE_L1
+#define ADDER_STATE_L1 0 /* 1 (experiment): state loads of a multi-frame launch go through L1 as well — every tile acquires its
+                          * predecessor's status word first, and ld.acquire.gpu invalidates the SM's L1 (CCTL.IVALL in the SASS) */
+#endif
 template <bool kCoherent>
-__device__ __forceinline__ uint4 ld_state(const uint4* p) { return kCoherent ? __ldcg(p) : *p; }
+__device__ __forceinline__ uint4 ld_state(const uint4* p) { return (kCoherent && !ADDER_STATE_L1) ? __ldcg(p) : *p; }
 template <bool kCoherent>
-__device__ __forceinline__ uint2 ld_state(const uint2* p) { return kCoherent ? __ldcg(p) : *p; }
+__device__ __forceinline__ uint2 ld_state(const uint2* p) { return (kCoherent && !ADDER_STATE_L1) ? __ldcg(p) : *p; }
 /* root and first child of a pixel: one 32-byte record, one 256-bit access */
 template <bool kCoherent>
 __device__ __forceinline__ void ld_state256(const uint4* p, uint4& a, uint4& b) {
-  if (kCoherent)
+  if (kCoherent && !ADDER_STATE_L1)
     asm volatile("ld.relaxed.gpu.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(p)
