@@ -49,6 +49,7 @@ SYMBOLS = [
     "adder_b200_comm_push_frames", "adder_b200_comm_wait_frames", "adder_b200_comm_frame", "adder_b200_comm_release_frames",
     "adder_b200_comm_sync", "adder_b200_comm_stream",
     "adder_b200_video_integrate_frames_host_compact", "adder_b200_compact_frame_bytes", "adder_b200_expand_compact",
+    "adder_b200_framer_ingest_events_device_async", "adder_b200_framer_frame_ready",
 ]
 COMM_BLOB_BYTES = 256
 
@@ -186,6 +187,8 @@ def lib() -> C.CDLL:
         "adder_b200_video_integrate_frames_host_compact": (i32, [vp, vp, sz, u32, f32, vp, sz, vp, vp, P(u64), P(u32)]),
         "adder_b200_compact_frame_bytes": (u64, [u64, u64]),
         "adder_b200_expand_compact": (i32, [u16, u16, u8, u16, vp, u64, vp, u32]),
+        "adder_b200_framer_ingest_events_device_async": (i32, [vp, vp, vp]),
+        "adder_b200_framer_frame_ready": (i32, [vp, P(i32)]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -598,6 +601,16 @@ class Framer:
         """The transcoder's device-resident output (records + n_chunks+1 offsets in HBM)."""
         ready = C.c_int()
         _check(self.L.adder_b200_framer_ingest_events_device(self.f, d_events, d_chunk_offsets, C.byref(ready)))
+        return bool(ready.value)
+
+    def ingest_events_device_async(self, d_events, d_chunk_offsets):
+        """ingest_events_device without the wait; ask frame_ready() later."""
+        _check(self.L.adder_b200_framer_ingest_events_device_async(self.f, d_events, d_chunk_offsets))
+
+    def frame_ready(self) -> bool:
+        """is_frame_0_filled() as of the last ingest (the one synchronisation of the asynchronous form)."""
+        ready = C.c_int()
+        _check(self.L.adder_b200_framer_frame_ready(self.f, C.byref(ready)))
         return bool(ready.value)
 
     def ingest_event(self, x, y, c, d, t) -> bool:

@@ -1518,14 +1518,18 @@ int framer_set_device(const adder_b200_framer* f) {
   return ADDER_OK;
 }
 
-/* status of the front frame -> tracker update (mode) -> predicates on the host */
-int framer_refresh(adder_b200_framer* f, int mode, const uint32_t* d_chunk_off) {
+/* status of the front frame -> tracker update (mode): queued on the framer's stream, nothing waits */
+int framer_refresh_queue(adder_b200_framer* f, int mode, const uint32_t* d_chunk_off) {
   const uint64_t chunk_px = (uint64_t)f->chunk_rows * f->w * f->c;
   adder::framer_chunk_status_kernel<<<f->n_chunks, 256, 0, f->stream>>>(f->d_ring_some, f->ring_frames, f->frame_px, chunk_px, f->d_forced,
                                                                         f->frames_written, f->d_status);
   adder::framer_tracker_kernel<<<1, 256, 0, f->stream>>>(f->d_tracker, f->d_status, d_chunk_off, f->n_chunks, mode, f->d_offset_max,
                                                          f->frames_written, f->buffer_limit, f->d_result);
   CU(cudaGetLastError());
+  return ADDER_OK;
+}
+/* the predicates of the last refresh (and the error word) on the host: the one synchronisation */
+int framer_collect(adder_b200_framer* f) {
   CU(cudaMemcpyAsync(f->h_result, f->d_result, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
   CU(cudaMemcpyAsync(f->h_result + 3, f->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
   CU(cudaStreamSynchronize(f->stream));
@@ -1536,8 +1540,12 @@ int framer_refresh(adder_b200_framer* f, int mode, const uint32_t* d_chunk_off) 
   }
   return ADDER_OK;
 }
+int framer_refresh(adder_b200_framer* f, int mode, const uint32_t* d_chunk_off) {
+  if (int rc = framer_refresh_queue(f, mode, d_chunk_off)) return rc;
+  return framer_collect(f);
+}
 
-int framer_ingest(adder_b200_framer* f, const adder_event_t* d_events, const uint32_t* d_chunk_off, int* frame_ready) {
+int framer_ingest(adder_b200_framer* f, const adder_event_t* d_events, const uint32_t* d_chunk_off, int* frame_ready, bool wait = true) {
   adder::FramerArgs a{};
   a.ev_words = reinterpret_cast<const uint32_t*>(d_events);
   a.chunk_off = d_chunk_off;
@@ -1569,7 +1577,9 @@ int framer_ingest(adder_b200_framer* f, const adder_event_t* d_events, const uin
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device));
   adder::framer_ingest_kernel<<<sms * 8, 256, 0, f->stream>>>(a);
   CU(cudaGetLastError());
-  if (int rc = framer_refresh(f, 0, d_chunk_off)) return rc;
+  if (int rc = framer_refresh_queue(f, 0, d_chunk_off)) return rc;
+  if (!wait) return ADDER_OK; /* the caller asks later (adder_b200_framer_frame_ready) */
+  if (int rc = framer_collect(f)) return rc;
   if (frame_ready) *frame_ready = (int)f->h_result[0];
   return ADDER_OK;
 }
@@ -1681,6 +1691,24 @@ int adder_b200_framer_ingest_events_device(adder_b200_framer* f, const adder_eve
     if (!f || !d_chunk_offsets) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
     if (int rc = framer_set_device(f)) return rc;
     return framer_ingest(f, d_events, d_chunk_offsets, frame_ready);
+  });
+}
+
+int adder_b200_framer_ingest_events_device_async(adder_b200_framer* f, const adder_event_t* d_events, const uint32_t* d_chunk_offsets) {
+  return guarded([&]() -> int {
+    if (!f || !d_chunk_offsets) return fail(ADDER_ERR_BAD_PARAMS, "NULL argument");
+    if (int rc = framer_set_device(f)) return rc;
+    return framer_ingest(f, d_events, d_chunk_offsets, nullptr, false);
+  });
+}
+
+int adder_b200_framer_frame_ready(adder_b200_framer* f, int* frame_ready) {
+  return guarded([&]() -> int {
+    if (!f) return fail(ADDER_ERR_BAD_PARAMS, "NULL handle");
+    if (int rc = framer_set_device(f)) return rc;
+    if (int rc = framer_collect(f)) return rc;
+    if (frame_ready) *frame_ready = (int)f->h_result[0];
+    return ADDER_OK;
   });
 }
 

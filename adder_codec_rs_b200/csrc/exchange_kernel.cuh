@@ -63,40 +63,58 @@ struct PushArgs {
 __global__ void __launch_bounds__(256) exchange_push_kernel(const PushArgs a) {
   __shared__ unsigned long long s_prefix;
   __shared__ uint32_t s_total, s_ok;
+  __shared__ unsigned long long s_part[256];
   const ExchangeRing& g = a.ring;
-  for (uint32_t f = 0; f < a.n_frames; f++) {
+  /* The frames of a push are independent of each other, and a frame of a sparse stream is a few waits over NVLink and
+   * a small copy: latency, not bandwidth.  So the CTAs split into as many groups as there are frames (or one CTA per
+   * frame when there are fewer CTAs): group `way` takes frames way, way + ways, ...; `rank` of `gsize` is this CTA's
+   * share of a frame's copy.  (A frame at a time with all CTAs cost 35 % of the step at 8 GPUs, profiles/r02g n8.) */
+  const uint32_t ways = a.n_frames < gridDim.x ? a.n_frames : gridDim.x;
+  const uint32_t way = blockIdx.x % ways, rank = blockIdx.x / ways;
+  const uint32_t gsize = (gridDim.x - way + ways - 1u) / ways;
+  for (uint32_t f = way; f < a.n_frames; f += ways) {
     const unsigned long long seq = a.seq0 + f;
     const uint32_t slot = (uint32_t)(seq % g.slots);
     const uint32_t* off = a.chunk_off + (unsigned long long)f * (a.n_chunks + 1u);
+    const unsigned long long t0 = global_ns();
     if (threadIdx.x == 0) {
-      const unsigned long long t0 = global_ns();
       bool ok = true;
       while (ok && ld_acquire_sys(g.released) + g.slots <= seq) { /* the slot's previous frame is still being read */
         __nanosleep(200);
         ok = global_ns() - t0 < kExchangeTimeoutNs;
       }
       const uint32_t total = off[a.n_chunks];
-      if (ok && blockIdx.x == 0) st_release_sys(g.totals + (unsigned long long)slot * g.world + a.band, ((seq + 1ull) << 32) | total);
-      unsigned long long prefix = 0;
-      for (uint32_t b = 0; ok && b < a.band; b++) { /* look-back over the lower bands' totals */
-        unsigned long long t = 0;
-        while (ok && ((t = ld_acquire_sys(g.totals + (unsigned long long)slot * g.world + b)) >> 32) != seq + 1ull) {
-          __nanosleep(100);
-          ok = global_ns() - t0 < kExchangeTimeoutNs;
-        }
-        prefix += (uint32_t)t;
-      }
-      s_prefix = prefix;
+      if (ok && rank == 0u) st_release_sys(g.totals + (unsigned long long)slot * g.world + a.band, ((seq + 1ull) << 32) | total);
       s_total = total;
       s_ok = ok ? 1u : 0u;
+    }
+    /* look-back over the lower bands' totals, one thread per band (the polls overlap) */
+    unsigned long long mine = 0;
+    bool ok_t = true;
+    for (uint32_t b = threadIdx.x; b < a.band; b += blockDim.x) {
+      unsigned long long t = 0;
+      while (ok_t && ((t = ld_acquire_sys(g.totals + (unsigned long long)slot * g.world + b)) >> 32) != seq + 1ull) {
+        __nanosleep(100);
+        ok_t = global_ns() - t0 < kExchangeTimeoutNs;
+      }
+      mine += (uint32_t)t;
+    }
+    s_part[threadIdx.x] = mine;
+    const int all_ok = __syncthreads_and(ok_t ? 1 : 0);
+    if (threadIdx.x == 0) {
+      unsigned long long prefix = 0;
+      const uint32_t np = a.band < blockDim.x ? a.band : blockDim.x;
+      for (uint32_t b = 0; b < np; b++) prefix += s_part[b];
+      s_prefix = prefix;
+      if (!all_ok) s_ok = 0u;
     }
     __syncthreads();
     const unsigned long long prefix = s_prefix;
     const uint32_t total = s_total;
     if (!s_ok) {
-      if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.err, 4u /* ADDER_DEVERR_INTERNAL: a peer did not show up */);
+      if (threadIdx.x == 0 && rank == 0u) atomicOr(a.err, 4u /* ADDER_DEVERR_INTERNAL: a peer did not show up */);
     } else if (prefix + total > g.out_stride) {
-      if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.err, 1u /* ADDER_DEVERR_CAPACITY */);
+      if (threadIdx.x == 0 && rank == 0u) atomicOr(a.err, 1u /* ADDER_DEVERR_CAPACITY */);
     } else {
       /* the band's words [0, 3 * total) -> the slot's words [3 * prefix, ...): this CTA's share, 128-bit stores in the body */
       const uint32_t* src = a.ev_words + (unsigned long long)f * a.ev_stride * 3ull;
@@ -105,13 +123,13 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const PushArgs a) {
       const unsigned long long head = n_words ? ((4ull - ((reinterpret_cast<uintptr_t>(dst) >> 2) & 3ull)) & 3ull) : 0ull; /* words up to dst's 16-byte boundary */
       const unsigned long long h = head < n_words ? head : n_words;
       const unsigned long long n_vec = (n_words - h) >> 2;
-      if (blockIdx.x == 0 && threadIdx.x < h) dst[threadIdx.x] = src[threadIdx.x];
+      if (rank == 0u && threadIdx.x < h) dst[threadIdx.x] = src[threadIdx.x];
       uint4* dst4 = reinterpret_cast<uint4*>(dst + h);
       const uint32_t* s4 = src + h;
       /* the source is only word-aligned relative to dst: four 32-bit loads per 128-bit store; four stores' worth of loads
-       * are in flight per thread (a lone load-then-store chain moved 200 GB/s over NVLink, profiles/r02g) */
-      const unsigned long long T = (unsigned long long)gridDim.x * blockDim.x;
-      unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+       * are in flight per thread (a lone load-then-store chain moved 200 GB/s over NVLink, profiles/r02g n2) */
+      const unsigned long long T = (unsigned long long)gsize * blockDim.x;
+      unsigned long long i = (unsigned long long)rank * blockDim.x + threadIdx.x;
       for (; i + 3ull * T < n_vec; i += 4ull * T) {
         uint4 v[4];
 #pragma unroll
@@ -127,17 +145,17 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const PushArgs a) {
         dst4[i] = make_uint4(p[0], p[1], p[2], p[3]);
       }
       const unsigned long long tail0 = h + 4ull * n_vec;
-      if (blockIdx.x == 0 && tail0 + threadIdx.x < n_words) dst[tail0 + threadIdx.x] = src[tail0 + threadIdx.x];
+      if (rank == 0u && tail0 + threadIdx.x < n_words) dst[tail0 + threadIdx.x] = src[tail0 + threadIdx.x];
       /* chunk offsets of the whole frame: this band's rows, rebased; the last band closes the table */
       uint32_t* goff = g.chunk_off + (unsigned long long)slot * (g.total_chunks + 1u) + a.chunk0;
-      for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < a.n_chunks; k += gridDim.x * blockDim.x) goff[k] = (uint32_t)prefix + off[k];
-      if (a.band + 1u == g.world && blockIdx.x == 0 && threadIdx.x == 0) goff[a.n_chunks] = (uint32_t)prefix + total;
+      for (uint32_t k = rank * blockDim.x + threadIdx.x; k < a.n_chunks; k += gsize * blockDim.x) goff[k] = (uint32_t)prefix + off[k];
+      if (a.band + 1u == g.world && rank == 0u && threadIdx.x == 0) goff[a.n_chunks] = (uint32_t)prefix + total;
     }
-    /* arrival: the last CTA of this launch to finish the frame tells the consumer */
+    /* arrival: the last CTA of the frame's group to finish tells the consumer */
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-      if (atomicAdd(a.local_done + f, 1u) + 1u == gridDim.x) {
+      if (atomicAdd(a.local_done + f, 1u) + 1u == gsize) {
         __threadfence_system();
         atomicAdd_system(g.arrived + slot, 1ull);
       }

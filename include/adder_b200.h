@@ -303,6 +303,12 @@ void adder_b200_framer_destroy(adder_b200_framer* f);
  * is_frame_0_filled() (driver.rs:851-866). */
 int adder_b200_framer_ingest_events_device(adder_b200_framer* f, const adder_event_t* d_events, const uint32_t* d_chunk_offsets,
                                            int* frame_ready);
+/* The same without the wait: the kernels (events, front-frame status, chunk_filled_tracker) are queued on the framer's
+ * stream and the call returns; the d_events / d_chunk_offsets buffers must stay untouched until a later call of this
+ * library on the framer has synchronised.  adder_b200_framer_frame_ready then gives is_frame_0_filled() as of the last
+ * ingest — for callers that feed several transcoded frames before they look for an output frame. */
+int adder_b200_framer_ingest_events_device_async(adder_b200_framer* f, const adder_event_t* d_events, const uint32_t* d_chunk_offsets);
+int adder_b200_framer_frame_ready(adder_b200_framer* f, int* frame_ready);
 /* The same from host memory: `events` holds sum(chunk_counts) records, chunk after chunk. */
 int adder_b200_framer_ingest_events_host(adder_b200_framer* f, const adder_event_t* events, const uint32_t* chunk_counts,
                                          int* frame_ready);

@@ -167,6 +167,8 @@ extern "C" {
     pub fn adder_b200_framer_create(width: u16, height: u16, channels: u8, chunk_rows: u32, codec_version: u8, time_mode: c_int, tps: u32, ref_interval: u32, delta_t_max: u32, output_fps: c_float, view_mode: c_int, source_camera: u32, buffer_limit: i64, ring_frames: u32, device: c_int, out_: *mut *mut adder_b200_framer) -> c_int;
     pub fn adder_b200_framer_destroy(f: *mut adder_b200_framer);
     pub fn adder_b200_framer_ingest_events_device(f: *mut adder_b200_framer, d_events: *const adder_event_t, d_chunk_offsets: *const u32, frame_ready: *mut c_int) -> c_int;
+    pub fn adder_b200_framer_ingest_events_device_async(f: *mut adder_b200_framer, d_events: *const adder_event_t, d_chunk_offsets: *const u32) -> c_int;
+    pub fn adder_b200_framer_frame_ready(f: *mut adder_b200_framer, frame_ready: *mut c_int) -> c_int;
     pub fn adder_b200_framer_ingest_events_host(f: *mut adder_b200_framer, events: *const adder_event_t, chunk_counts: *const u32, frame_ready: *mut c_int) -> c_int;
     pub fn adder_b200_framer_write_multi_frame_bytes(f: *mut adder_b200_framer, frames_out: *mut u8, max_frames: u32, n_frames: *mut u32) -> c_int;
     pub fn adder_b200_framer_flush_frame_buffer(f: *mut adder_b200_framer, frame_ready: *mut c_int) -> c_int;

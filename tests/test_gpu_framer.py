@@ -97,7 +97,11 @@ def test_transcoder_and_framer_in_lock_step(spec):
         gv.integrate_frames_device(d_frame.ptr, P, 1, case.time, d_events.ptr, cap, d_off.ptr)
         gv.sync()
         eo, co = ov.integrate_matrix(frames[f], case.time)
-        ready_g = gf.ingest_events_device(d_events.ptr, d_off.ptr)  # events never leave HBM
+        if f % 2:  # the asynchronous form: kernels queued, the predicate fetched by a separate call
+            gf.ingest_events_device_async(d_events.ptr, d_off.ptr)
+            ready_g = gf.frame_ready()
+        else:
+            ready_g = gf.ingest_events_device(d_events.ptr, d_off.ptr)  # events never leave HBM
         ready_o = of.ingest_events_events(eo, co)
         assert ready_g == ready_o, f"frame {f}"
         if ready_o:

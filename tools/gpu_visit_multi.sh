@@ -5,7 +5,7 @@ N=${1:-2}; FR=${2:-200}; ST=${3:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 echo "== exchange between processes (CUDA IPC over NVLink), sharding tests"
-NCCL_DEBUG=WARN timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -6
+NCCL_DEBUG=WARN timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -v 2>&1 | grep -E "PASSED|FAILED|SKIPPED|ERROR|passed|failed" | sed -e 's/^tests.test_gpu_multi.py:://' > gpurun_out/r02g_multi_tests_n$N.txt; tail -4 gpurun_out/r02g_multi_tests_n$N.txt
 echo "== bench --gpus $N --frames $FR (strong scaling, gather legs)"
 NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --frames $FR --steps $ST --warmup 3 > gpurun_out/r02g_bench_n$N.json 2> gpurun_out/r02g_bench_n$N.err; echo "rc=$?"
 grep "NCCL INFO" gpurun_out/r02g_bench_n$N.json | grep -E "NCCL version|nranks|NVLS multicast|via P2P" | head -40 > gpurun_out/r02g_nccl_n$N.txt; wc -l gpurun_out/r02g_nccl_n$N.txt

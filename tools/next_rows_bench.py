@@ -155,6 +155,28 @@ t0 = time.perf_counter(); fr.flush_frame_buffer(); out = fr.write_multi_frame_by
 n_frames_out += len(out)
 print(f"row 3 framer: ingest_events_device {ing / NF * 1e6:7.1f} us/frame (host clock, sync included; {n_events_in / NF:.0f} events/frame -> "
       f"{n_events_in / ing / 1e6:.0f} Mevents/s), write_multi_frame_bytes {wr / max(n_frames_out, 1) * 1e6:7.1f} us per output frame ({n_frames_out} frames, D2H included)")
+# the same frames' events ingested without a wait per call (adder_b200_framer_ingest_events_device_async): one buffer per frame
+vg.reset_state(); vg.update_crf(3)
+fr2 = A.Framer(W, H, 1, 1, 3, A.TIME_ABSOLUTE_T, REF * 30, REF, DTM, output_fps=30.0, ring_frames=160)
+d_evs = [vg.device_alloc(capg * 12) for _ in range(NF)]
+d_ofs = [vg.device_alloc((vg.n_chunks + 1) * 4) for _ in range(NF)]
+for f in range(NF):
+    vg.integrate_frames_device(d_gray.ptr + f * Pg, Pg, 1, float(REF), d_evs[f].ptr, capg, d_ofs[f].ptr)
+vg.sync()
+for rep in range(2):
+    t0 = time.perf_counter()
+    for f in range(NF if rep else 2):
+        fr2.ingest_events_device_async(d_evs[f].ptr, d_ofs[f].ptr)
+    ready = fr2.frame_ready()
+    dt_async = time.perf_counter() - t0
+    if not rep:  # a fresh framer for the timed pass
+        fr2 = A.Framer(W, H, 1, 1, 3, A.TIME_ABSOLUTE_T, REF * 30, REF, DTM, output_fps=30.0, ring_frames=160)
+ev_bytes = 12 * n_events_in / NF
+st_bytes = 2 * 16 * n_events_in / NF  # one 16-byte state record read and written per run of events (about one run per event here)
+print(f"      asynchronous ingest of {NF} frames, one wait at the end: {dt_async / NF * 1e6:7.1f} us/frame -> {(ev_bytes + st_bytes) / (dt_async / NF) / 1e9:6.0f} GB/s of records + pixel state "
+      f"({(ev_bytes + st_bytes) / (dt_async / NF) / 1e9 / PEAK:.2f} of the HBM roofline; the ring bytes it touches are not counted)")
+for b in d_evs + d_ofs:
+    b.free()
 if not quick:
     of = O.Framer(W, H, 1, 1, 3, O.TIME_ABSOLUTE_T, REF * 30, REF, DTM, output_fps=30.0)
     ov = O.Video(W, H, 1, O.MODE_FRAME_PERFECT)
