@@ -106,7 +106,8 @@ struct adder_b200_video {
   float running_t = 0.0f;
   uint32_t P = 0, n_tiles = 0;   /* n_tiles: tiles of the smallest shape (upper bound, sizes the status array) */
   uint32_t R = 1, n_tiles_r = 0; /* sub-tiles per tile and the number of tiles that goes with it */
-  uint32_t grid = 0;             /* persistent CTAs per launch */
+  uint32_t grid = 0;             /* persistent CTAs per launch (the kernel's full occupancy) */
+  uint32_t reserve_ctas = 0;     /* CTA slots the integrate launch leaves free for the event exchange's push kernel (set when a comm is bound) */
   uint32_t status_ring = 1;      /* frames of status words (power of two) */
   uint64_t status_words = 0;     /* status_ring * tiles */
   float* d_running_t[kRtSlots] = {}; /* running_t per frame of a launch (kMaxFramesPerLaunch + 1 floats each) */
@@ -254,15 +255,24 @@ int realloc_chunks(adder_b200_video* v) {
   return ADDER_OK;
 }
 
+/* The persistent grid fills every SM to the kernel's occupancy, and at 64 registers x 256 threads x 4 CTAs that is the
+ * whole register file: nothing else can start on an SM until a CTA of the launch exits, i.e. until the launch is over.
+ * The push kernel of the event exchange is meant to run BESIDE the next integrate launch, so a video with a comm bound
+ * to it launches a few CTAs fewer and the push kernel has exactly that many (measured without the reserve at 8 GPUs: the
+ * push ran after the next launch instead of beside it and the gather leg lost 35 %, profiles/r02g n8). */
+constexpr uint32_t kPushCtas = 16;
+uint32_t launch_grid(const adder_b200_video* v) { return v->grid > 8u * v->reserve_ctas ? v->grid - v->reserve_ctas : v->grid; }
+
 template <int R, bool kDeep>
 void launch_rd(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
   const size_t smem = adder::frame_kernel_smem(R);
+  const uint32_t grid = launch_grid(v);
   if (v->counting)
-    adder::integrate_frame_kernel<R, true, true, kDeep><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, true, true, kDeep><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
   else if (a.n_frames > 1u)
-    adder::integrate_frame_kernel<R, false, true, kDeep><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, false, true, kDeep><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
   else /* one frame: the variant compiled without the cross-frame dependency, fences and L2-only state loads */
-    adder::integrate_frame_kernel<R, false, false, kDeep><<<v->grid, ADDER_TILE_PX, smem, stream>>>(a);
+    adder::integrate_frame_kernel<R, false, false, kDeep><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
 }
 template <int R>
 void launch_r(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
@@ -470,7 +480,7 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
 
   v->d_last_input = d_frame + (size_t)(n_frames - 1u) * frame_stride;
   launch_variant(v, a, stream);
-  v->ticket_base += n_frames * v->n_tiles_r + v->grid; /* every CTA draws one ticket past the end */
+  v->ticket_base += n_frames * v->n_tiles_r + launch_grid(v); /* every CTA draws one ticket past the end */
   v->launches++;
   CU(cudaGetLastError());
   if (!v->feature_detection && v->d_n_new) CU(cudaMemsetAsync(v->d_n_new, 0, sizeof(uint32_t), stream)); /* this frame found none */
@@ -1842,6 +1852,7 @@ void ring_layout(void* base, uint32_t slots, uint32_t world, uint32_t total_chun
 
 int comm_common_init(adder_b200_comm* c) {
   CU(cudaSetDevice(c->device));
+  c->v->reserve_ctas = kPushCtas; /* from now on this video's integrate launches leave room for the push kernel */
   int lo = 0, hi = 0;
   CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi)); /* small kernels that should not queue behind the persistent one */
@@ -1989,8 +2000,6 @@ int adder_b200_comm_push_frames(adder_b200_comm* c, uint32_t band, uint32_t chun
     /* behind whatever the band's stream has queued (the integrate launch that produces these frames) */
     CU(cudaEventRecord(c->ev, c->v->stream));
     CU(cudaStreamWaitEvent(c->stream, c->ev, 0));
-    int sms = 0;
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     for (uint32_t f0 = 0; f0 < n_frames; f0 += kMaxFramesPerLaunch) {
       const uint32_t n = std::min<uint32_t>(kMaxFramesPerLaunch, n_frames - f0);
       CU(cudaMemsetAsync(c->d_local_done, 0, n * sizeof(uint32_t), c->stream));
@@ -2006,9 +2015,8 @@ int adder_b200_comm_push_frames(adder_b200_comm* c, uint32_t band, uint32_t chun
       a.seq0 = frame_seq0 + f0;
       a.local_done = c->d_local_done;
       a.err = c->d_err;
-      /* one CTA per SM, 16 loads in flight per thread: enough to fill an NVLink direction; the CTAs take a fifth of an
-       * SM's thread slots from the next integrate launch while they run */
-      adder::exchange_push_kernel<<<std::max(sms, 8), 256, 0, c->stream>>>(a);
+      /* as many CTAs as the band's integrate launches leave room for (launch_grid): they run beside the next launch */
+      adder::exchange_push_kernel<<<kPushCtas, 256, 0, c->stream>>>(a);
       CU(cudaGetLastError());
     }
     /* Two batches may be outstanding (the caller alternates two sets of buffers): whatever the band's stream is given

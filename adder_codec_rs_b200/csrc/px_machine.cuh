@@ -33,6 +33,9 @@
 
 #include "state_layout.h"
 
+#ifndef ADDER_HOIST_FIRE
+#define ADDER_HOIST_FIRE 1 /* the firing node's arithmetic after the level walk instead of inside it */
+#endif
 #ifndef ADDER_D_MAX
 #define ADDER_D_MAX 127u
 #define ADDER_D_ZERO_INTEGRATION 128u
@@ -177,6 +180,32 @@ ADDER_HD bool integrate_main(Node& n, float intensity, float time) {
   n.integ = sum;
   n.dt = rn_add(n.dt, time);
   return false;
+}
+
+/* integrate_main in two halves, for walks whose lanes fire at different levels: integrate_accumulate does the non-firing
+ * arm and only REPORTS a fire (node untouched); integrate_fire is the firing arm, run once after the walk by all lanes
+ * that reported one — inside the level loop a warp would run its division once per distinct firing level of its 32 pixels. */
+ADDER_HD bool integrate_accumulate(Node& n, float intensity, float time) {
+  const float sum = rn_add(n.integ, intensity);
+  if (sum >= d_shift_f32(NODE_D(n.w))) return true;
+  n.integ = sum;
+  n.dt = rn_add(n.dt, time);
+  return false;
+}
+ADDER_HD void integrate_fire(Node& n, float intensity, float time) {
+  const uint32_t d = NODE_D(n.w);
+  const float sum = rn_add(n.integ, intensity);
+  const uint32_t nd = get_d_from_intensity(sum);
+  float prop = rn_div(rn_sub(d_shift_f32(nd), n.integ), intensity);
+  if (nd == ADDER_D_ZERO_INTEGRATION || d == ADDER_D_ZERO_INTEGRATION || intensity < 1.1920929e-07f) prop = 1.0f;
+  n.best_dt = rn_add(n.dt, rn_mul(time, prop)); /* :445, two roundings */
+  uint32_t d_after = nd;
+  if (nd < ADDER_D_MAX) {
+    n.integ = sum;
+    n.dt = rn_add(n.dt, time);
+    d_after = nd + 1u;
+  }
+  n.w = NODE_PACK(d_after, nd, 1);
 }
 
 /* u8::get_frame_value, SourceType::U8 arm (scale_intensity.rs:58-104, :262-270) */
@@ -376,6 +405,7 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
       Node nk = n1; /* level 1 is already here; level k+1 is requested before level k is worked on */
       if (k_end > 1u) mem.used_preloaded(); /* n1 */
       const bool defer_deep = kDefer && !shift && !only_root;
+      uint32_t kf = 0; /* the level whose node fired (its arithmetic is done after the walk: ADDER_HOIST_FIRE) */
       for (uint32_t k = 1; k < k_end; k++) {
         if (defer_deep && k == 2u) { /* level 1 did not fire: the rest of the walk is done by deep_item / deep_finish */
           *deferred = true;
@@ -387,7 +417,15 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
         if (!only_root) {
           if (k == len - 1u && nk.dt == 0.0f && nk.integ == 0.0f) /* :332-335 */
             nk.w = (nk.w & ~0xFFu) | get_d_from_intensity(intensity);
+#if ADDER_HOIST_FIRE
+          if (integrate_accumulate(nk, intensity, time)) { /* fires: finished below, by all such lanes of the warp together */
+            kf = k;
+            if (k + 1u < k_end && !defer_deep) mem.unused_load(); /* the level requested ahead is dropped with the rest (:366) */
+            break;
+          }
+#else
           fired = integrate_main(nk, intensity, time);
+#endif
         }
         mem.store(k - shift, nk);
         if (k == 1u && shift && NODE_HAS_BEST(nk.w)) {
@@ -403,6 +441,19 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
         }
         nk = nxt;
       }
+#if ADDER_HOIST_FIRE
+      if (kf) { /* the node in nk fired at level kf: its best event, its fresh child, the rest of the stack dropped (:344-366) */
+        integrate_fire(nk, intensity, time);
+        mem.store(kf - shift, nk);
+        if (kf == 1u && shift) { /* it is the new root (always has a best event now) */
+          disp_has = true;
+          disp_d = NODE_BEST_D(nk.w);
+          disp_dt = nk.best_dt;
+        }
+        if (kf + 1u - shift < a.depth) mem.store_fresh(kf + 1u - shift, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+        new_len = kf + 2u;
+      }
+#endif
       new_len -= shift;
       if (new_len == 0u) new_len = 1u; /* flagged INTERNAL above */
       if (new_len > a.depth) new_len = a.depth;
