@@ -34,7 +34,8 @@
 #include "state_layout.h"
 
 #ifndef ADDER_HOIST_FIRE
-#define ADDER_HOIST_FIRE 1 /* the firing node's arithmetic after the level walk instead of inside it */
+#define ADDER_HOIST_FIRE 0 /* 1: the firing node's arithmetic after the level walk instead of inside it (+2 % on noise and
+                            * jitter c = 5, -3 % on aged 8K stacks, profiles/r02k_ab_hoist.txt: off) */
 #endif
 #ifndef ADDER_D_MAX
 #define ADDER_D_MAX 127u
