@@ -153,6 +153,25 @@ struct GlobalNodes {
     }
 #endif
   }
+  /* a running pointer through the pixel's levels (ADDER_FAST_WALK): level 1 is the second half of the first record; from an
+   * odd level the next one opens the next record, from an even level it is the record's other half */
+  __device__ __forceinline__ uint4* cursor_level1() const { return p + 1; }
+  __device__ __forceinline__ uint4* next_from_odd(uint4* q) const { return q + (stride - 1ull); }
+  __device__ __forceinline__ uint4* next_from_even(uint4* q) const { return q + 1; }
+  __device__ __forceinline__ Node load_at(const uint4* q) {
+    n_loads++;
+    const uint4 v = ld_state<kCoherent>(q);
+    Node n;
+    n.integ = __uint_as_float(v.x);
+    n.dt = __uint_as_float(v.y);
+    n.best_dt = __uint_as_float(v.z);
+    n.w = v.w;
+    return n;
+  }
+  __device__ __forceinline__ void store_at(uint4* q, const Node& n) {
+    n_stores++;
+    *q = make_uint4(__float_as_uint(n.integ), __float_as_uint(n.dt), __float_as_uint(n.best_dt), n.w);
+  }
   __device__ __forceinline__ void used_preloaded() { n_loads++; }
   __device__ __forceinline__ void unused_load() { n_loads--; }
   /* px_frame falls back to px_step: root and level 1 again, as they are in memory (nothing has been stored yet) */

@@ -33,6 +33,11 @@
 
 #include "state_layout.h"
 
+#ifndef ADDER_FAST_WALK
+#define ADDER_FAST_WALK 0 /* 1: the unshifted walk of px_step through a running pointer and two node registers used in turn:
+                           * half the instructions per level in the SASS, parity-green, and 7 % SLOWER on every workload
+                           * (profiles/r02m_ab_fastwalk.txt) — like every variant of this kernel that adds code */
+#endif
 #ifndef ADDER_HOIST_FIRE
 #define ADDER_HOIST_FIRE 0 /* 1: the firing node's arithmetic after the level walk instead of inside it (+2 % on noise and
                             * jitter c = 5, -3 % on aged 8K stacks, profiles/r02k_ab_hoist.txt: off) */
@@ -407,6 +412,64 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
       if (k_end > 1u) mem.used_preloaded(); /* n1 */
       const bool defer_deep = kDefer && !shift && !only_root;
       uint32_t kf = 0; /* the level whose node fired (its arithmetic is done after the walk: ADDER_HOIST_FIRE) */
+#if ADDER_FAST_WALK
+      /* The common walk — nothing moves up a level, every level integrates — written for the instruction count of one
+       * level (the general loop below costs 65-95 per level: address re-computation, a four-register rotation and the
+       * tail test on every level): a running pointer stepped by the record layout, two node registers used in turn so
+       * that nothing is copied, the next level requested before this one is worked on, the fresh-tail fix only at the
+       * tail, and the firing node finished once after the walk. */
+      if (!kDefer && !shift && !only_root) {
+        if (len > 1u) {
+          const uint32_t last = len - 1u;
+          Node na = nk, nb = nk;
+          auto qa = mem.cursor_level1(), qb = qa, qf = qa;
+          uint32_t k = 1;
+          for (;;) {
+            /* an odd level, in na */
+            if (k != last) {
+              qb = mem.next_from_odd(qa);
+              nb = mem.load_at(qb);
+            } else if (na.dt == 0.0f && na.integ == 0.0f) {
+              na.w = (na.w & ~0xFFu) | get_d_from_intensity(intensity); /* :332-335 */
+            }
+            if (integrate_accumulate(na, intensity, time)) {
+              kf = k;
+              nk = na;
+              qf = qa;
+              if (k != last) mem.unused_load();
+              break;
+            }
+            mem.store_at(qa, na);
+            if (k == last) break;
+            k++;
+            /* an even level, in nb */
+            if (k != last) {
+              qa = mem.next_from_even(qb);
+              na = mem.load_at(qa);
+            } else if (nb.dt == 0.0f && nb.integ == 0.0f) {
+              nb.w = (nb.w & ~0xFFu) | get_d_from_intensity(intensity);
+            }
+            if (integrate_accumulate(nb, intensity, time)) {
+              kf = k;
+              nk = nb;
+              qf = qb;
+              if (k != last) mem.unused_load();
+              break;
+            }
+            mem.store_at(qb, nb);
+            if (k == last) break;
+            k++;
+          }
+          if (kf) { /* its best event, its fresh child; whatever lay deeper is dropped (:344-366) */
+            integrate_fire(nk, intensity, time);
+            mem.store_at(qf, nk);
+            if (kf + 1u < a.depth) mem.store_fresh(kf + 1u, fresh_node(intensity)); else errbits |= ADDER_DEVERR_DEPTH;
+            new_len = kf + 2u;
+            kf = 0;
+          }
+        }
+      } else
+#endif
       for (uint32_t k = 1; k < k_end; k++) {
         if (defer_deep && k == 2u) { /* level 1 did not fire: the rest of the walk is done by deep_item / deep_finish */
           *deferred = true;

@@ -29,6 +29,11 @@ struct HostNodes {
   void used_preloaded() const {}
   void prefetch_levels(uint32_t) const {}
   void unused_load() const {}
+  adder::Node* cursor_level1() const { return p + stride; }
+  adder::Node* next_from_odd(adder::Node* q) const { return q + stride; }
+  adder::Node* next_from_even(adder::Node* q) const { return q + stride; }
+  adder::Node load_at(const adder::Node* q) const { return *q; }
+  void store_at(adder::Node* q, const adder::Node& n) const { *q = n; }
   void reload(adder::Node& n0, adder::Node& n1) const { n0 = p[0]; n1 = p[stride]; }
 };
 struct VecSink {
