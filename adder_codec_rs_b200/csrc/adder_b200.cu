@@ -263,10 +263,23 @@ int realloc_chunks(adder_b200_video* v) {
 constexpr uint32_t kPushCtas = 16;
 uint32_t launch_grid(const adder_b200_video* v) { return v->grid > 8u * v->reserve_ctas ? v->grid - v->reserve_ctas : v->grid; }
 
+/* The default output configuration (TimeMode::AbsoluteT, FramedViewMode::Intensity) runs the instantiation that has both
+ * as compile-time constants (kPlain: the large tile, uncounted, per-lane walk); everything else the general one. */
+bool use_plain(const adder_b200_video* v) {
+  if (const char* e = getenv("ADDER_B200_PLAIN")) return atoi(e) != 0 && v->time_mode == ADDER_TIME_ABSOLUTE_T && v->view_mode == ADDER_VIEW_INTENSITY;
+  return v->time_mode == ADDER_TIME_ABSOLUTE_T && v->view_mode == ADDER_VIEW_INTENSITY;
+}
 template <int R, bool kDeep>
 void launch_rd(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
   const size_t smem = adder::frame_kernel_smem(R);
   const uint32_t grid = launch_grid(v);
+  if (R == 8 && !kDeep && !v->counting && use_plain(v)) {
+    if (a.n_frames > 1u)
+      adder::integrate_frame_kernel<8, false, true, false, true><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
+    else
+      adder::integrate_frame_kernel<8, false, false, false, true><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
+    return;
+  }
   if (v->counting)
     adder::integrate_frame_kernel<R, true, true, kDeep><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
   else if (a.n_frames > 1u)
@@ -338,6 +351,8 @@ int set_smem_attr() {
     CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
     CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
     CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
+    CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
+    CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
   }
   return ADDER_OK;
 }

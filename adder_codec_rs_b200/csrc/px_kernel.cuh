@@ -384,7 +384,7 @@ __device__ __forceinline__ uint32_t look_back(const unsigned long long* status, 
  * lanes of the warp together (px_machine.cuh deep_item / deep_finish).  Stacks of neighbouring pixels differ in depth
  * (2 .. 11 live nodes after a few hundred frames of a static scene), and a per-lane loop runs as long as the deepest of
  * the 32: 36 warp-instructions per pixel on aged 8K stacks against 18 on two-node stacks (profiles/r02h_static_*). */
-template <int R, bool kCount, bool kMulti, bool kDeep = false>
+template <int R, bool kCount, bool kMulti, bool kDeep = false, bool kPlain = false>
 __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame_kernel(const FrameArgs a) {
   constexpr uint32_t ROWS = tile_rows(R), TILE = tile_px(R);
   constexpr uint32_t S = park_slots(R);
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
 #if ADDER_LEAN /* A/B: the short path of px_frame in front of the general state machine */
           const bool show = px_frame(px, sample, h, n0, n1, mem, park, errbits, &disp);
 #else
-          const bool show = px_step<kDeep>(px, sample, h, n0, n1, mem, park, errbits, &disp, &deferred);
+          const bool show = px_step<kDeep, kPlain>(px, sample, h, n0, n1, mem, park, errbits, &disp, &deferred);
 #endif
           if (!kDeep) a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
 #if ADDER_EV_STREAM >= 2

@@ -18,7 +18,7 @@
 namespace adder {
 int g_fast_div_ulps = 0;
 }
-static int g_entry = 0; /* 0: px_step (what the kernel calls by default), 1: px_frame (short path + fallback), 2: px_step<true> + deferred deep walk */
+static int g_entry = 0; /* 0: px_step (what the kernel calls by default), 1: px_frame (short path + fallback), 2: px_step<true> + deferred deep walk, 3: px_step<false, true> where it applies */
 namespace {
 struct HostNodes {
   adder::Node* p;
@@ -131,9 +131,11 @@ size_t sim_integrate(sim_video* v, const uint8_t* frame, float time, uint32_t re
         const uint32_t nl = adder::deep_finish(p, mem, kf, len_in, (float)frame[i], v->err);
         v->hdr[i].y = (v->hdr[i].y & ~(0x1Fu << 24)) | (nl << 24);
       }
+    } else if (g_entry == 3 && abs_time && view_mode == 0) { /* the kernel's kPlain instantiation (AbsoluteT + Intensity view as constants) */
+      show = adder::px_step<false, true>(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp);
     } else {
-      show = g_entry ? adder::px_frame(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)
-                     : adder::px_step(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp);
+      show = g_entry == 1 ? adder::px_frame(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp)
+                          : adder::px_step(p, frame[i], v->hdr[i], mem.load(0), n1, mem, sink, v->err, &disp);
     }
     if (show) v->running[i] = disp;
   }
