@@ -40,6 +40,9 @@
 #ifndef ADDER_WO_PIPE
 #define ADDER_WO_PIPE 1 /* write-out: the read of record e+1 overlaps the store of record e */
 #endif
+#ifndef ADDER_PF_ROLLED
+#define ADDER_PF_ROLLED 0 /* 1: -128 instructions of code, more spills, -2 % .. +2 % (profiles/r02p_ab_pfrolled.txt): off */
+#endif
 #ifndef ADDER_DEEP_PF
 #define ADDER_DEEP_PF 2 /* px_step entry: pull levels 2..length-1 towards L1 (1) or L2 (2); 0 = off */
 #endif
@@ -144,6 +147,9 @@ struct GlobalNodes {
   __device__ __forceinline__ void prefetch_levels(uint32_t len) {
 #if ADDER_DEEP_PF
     const uint4* q = p + stride;
+#if ADDER_PF_ROLLED
+#pragma unroll 1 /* the compiler unrolls this fifteen times at every place px_step is inlined: 160 instructions of the 47 KB kernel */
+#endif
     for (uint32_t k = 2; k < len; k += 2, q += stride) {
 #if ADDER_DEEP_PF == 1
       asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
