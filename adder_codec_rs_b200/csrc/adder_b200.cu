@@ -89,6 +89,7 @@ uint32_t f32_as_u32(float x) { /* Rust `as u32` */
 
 constexpr int kRing = 3; /* host-form pipeline depth */
 constexpr uint32_t kMaxFramesPerLaunch = adder::kMaxLaunchFrames; /* frames one integrate launch may span */
+constexpr uint32_t kMaxTBlock = 16;           /* frames of one tile a CTA may run back to back (FrameArgs::tblock) */
 constexpr uint32_t kRtSlots = 8;              /* launches whose running_t tables may be in flight before one is reused */
 
 }  // namespace
@@ -117,6 +118,14 @@ struct adder_b200_video {
   uint8_t* d_exact_lut = nullptr; /* [257] display bytes of exactly integral intensities, for lut_ref */
   uint32_t lut_ref = 0;
   uint64_t Ppad = 0;
+
+  /* How the node stacks are stored (state_layout.h): 0 = eager (every level holds its own integration / delta_t), 1 = offset
+   * form (px_offset.cuh: levels below the root hold offsets against the root and are touched only when they fire).  A video
+   * whose state is pristine takes whichever form the launch's parameters allow; an offset-form state is converted to the
+   * eager form when a launch is not eligible any more, and an eager state that has integrated frames stays eager. */
+  int form = 0;
+  bool pristine = true;    /* nothing integrated since create / reset_state */
+  uint32_t records = 0;    /* 32-byte records allocated per pixel */
 
   uint2* d_hdr = nullptr;
   uint4* d_nodes = nullptr;
@@ -188,18 +197,27 @@ int set_device(const adder_b200_video* v) {
   return ADDER_OK;
 }
 
+/* 32-byte records per pixel: eager form two levels to a record, offset form one level to a record (record 0 = root + meta) */
+uint32_t records_for(int form, uint32_t depth) { return form == 1 ? depth : NODE_LEVELS_ALLOC(depth) / 2u; }
+
 int ensure_depth(adder_b200_video* v, uint32_t need) {
-  if (need <= v->depth) return ADDER_OK;
-  uint4* nn = nullptr;
-  /* two levels to a record (state_layout.h): the records of levels (2j, 2j+1) of all pixels are contiguous, so a deeper
-   * allocation keeps the old one as its prefix */
-  CU(cudaMalloc(&nn, (size_t)NODE_LEVELS_ALLOC(need) * v->Ppad * sizeof(uint4)));
-  if (v->d_nodes) {
-    CU(cudaMemcpyAsync(nn, v->d_nodes, (size_t)NODE_LEVELS_ALLOC(v->depth) * v->Ppad * sizeof(uint4), cudaMemcpyDeviceToDevice, v->stream));
-    CU(cudaStreamSynchronize(v->stream));
-    CU(cudaFree(v->d_nodes));
+  need = std::max(need, v->depth);
+  const uint32_t need_records = std::max(records_for(v->form, need), v->records);
+  if (need == v->depth && need_records == v->records) return ADDER_OK;
+  if (need_records > v->records) {
+    uint4* nn = nullptr;
+    /* the records of one level (pair) of all pixels are contiguous (state_layout.h), so a larger allocation keeps the old
+     * one as its prefix */
+    CU(cudaMalloc(&nn, (size_t)need_records * 2u * v->Ppad * sizeof(uint4)));
+    if (v->d_nodes) {
+      CU(cudaMemcpyAsync(nn, v->d_nodes, (size_t)v->records * 2u * v->Ppad * sizeof(uint4), cudaMemcpyDeviceToDevice, v->stream));
+      CU(cudaStreamSynchronize(v->stream));
+      CU(cudaFree(v->d_nodes));
+    }
+    v->d_nodes = nn;
+    v->records = need_records;
   }
-  v->d_nodes = nn;
+  if (need == v->depth) return ADDER_OK;
   const bool first = v->depth == 0;
   v->depth = need;
   { /* a pixel emits at most depth + 2 events in one frame (1 + max(L, 2) + 1): the arena takes what the slots do not */
@@ -273,6 +291,21 @@ template <int R, bool kDeep>
 void launch_rd(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t stream) {
   const size_t smem = adder::frame_kernel_smem(R);
   const uint32_t grid = launch_grid(v);
+  if (!kDeep && v->form == 1) { /* offset-form state: the kOff instantiations */
+    if (R == 8 && !v->counting && use_plain(v)) {
+      if (a.n_frames > 1u)
+        adder::integrate_frame_kernel<8, false, true, false, true, true><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
+      else
+        adder::integrate_frame_kernel<8, false, false, false, true, true><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
+    } else if (v->counting) {
+      adder::integrate_frame_kernel<R, true, true, false, false, true><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
+    } else if (a.n_frames > 1u) {
+      adder::integrate_frame_kernel<R, false, true, false, false, true><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
+    } else {
+      adder::integrate_frame_kernel<R, false, false, false, false, true><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
+    }
+    return;
+  }
   if (R == 8 && !kDeep && !v->counting && use_plain(v)) {
     if (a.n_frames > 1u)
       adder::integrate_frame_kernel<8, false, true, false, true><<<grid, ADDER_TILE_PX, smem, stream>>>(a);
@@ -296,7 +329,7 @@ void launch_r(adder_b200_video* v, const adder::FrameArgs& a, cudaStream_t strea
  * (1923 vs 1444 us per frame, profiles/r02i_ab_deep.txt): its passes are a chain of dependent L2 round trips with nothing
  * requested ahead, where the per-lane loop always has the next level in flight.  Off unless ADDER_B200_DEEP=1. */
 bool use_deep(const adder_b200_video* v) {
-  if (v->R != 8) return false;
+  if (v->R != 8 || v->form == 1) return false;
   if (const char* e = getenv("ADDER_B200_DEEP")) return atoi(e) != 0;
   return false;
 }
@@ -324,6 +357,16 @@ int choose_grid(adder_b200_video* v) {
                                                      adder::frame_kernel_smem(8)));
     per_sm = std::min(per_sm, deep_per_sm);
   }
+  { /* and so must the offset-form instantiations */
+    int off_per_sm = 0;
+    switch (v->R) {
+      case 1: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&off_per_sm, adder::integrate_frame_kernel<1, false, true, false, false, true>, ADDER_TILE_PX, adder::frame_kernel_smem(1))); break;
+      case 2: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&off_per_sm, adder::integrate_frame_kernel<2, false, true, false, false, true>, ADDER_TILE_PX, adder::frame_kernel_smem(2))); break;
+      case 4: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&off_per_sm, adder::integrate_frame_kernel<4, false, true, false, false, true>, ADDER_TILE_PX, adder::frame_kernel_smem(4))); break;
+      default: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&off_per_sm, adder::integrate_frame_kernel<8, false, true, false, false, true>, ADDER_TILE_PX, adder::frame_kernel_smem(8))); break;
+    }
+    per_sm = std::min(per_sm, off_per_sm);
+  }
   if (per_sm < 1) return fail(ADDER_ERR_INTERNAL, "integrate_frame_kernel does not fit an SM");
   if (const char* e = getenv("ADDER_B200_CTAS_PER_SM")) {
     const int n = atoi(e);
@@ -347,7 +390,12 @@ int set_smem_attr() {
   CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
   CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
   CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
+  CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<R, true, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(R)));
   if (R == 8) {
+    CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
+    CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
     CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
     CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
     CU(cudaFuncSetAttribute(adder::integrate_frame_kernel<8, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adder::frame_kernel_smem(8)));
@@ -370,6 +418,44 @@ uint32_t choose_r(uint32_t P) {
   return 1;
 }
 
+/* T of a multi-frame launch: how many consecutive frames of one tile a CTA runs before it draws another tile (px_kernel.cuh
+ * tile_of).  The tile's state then comes back from L2 instead of DRAM for T - 1 of T frames, provided one generation of
+ * tiles — what all CTAs touch while each works on one tile-frame — fits L2: about 150 bytes per pixel of the large tile,
+ * 89 MB for 592 CTAs against 126 MB.  ADDER_B200_TBLOCK overrides (1 = the frame-major order of round 1). */
+uint32_t tblock_of(const adder_b200_video* v, uint32_t n_frames) {
+  uint32_t t = 1u;
+  if (const char* e = getenv("ADDER_B200_TBLOCK")) {
+    const int n = atoi(e);
+    if (n >= 1) t = std::min<uint32_t>((uint32_t)n, kMaxTBlock);
+  }
+  return std::max(1u, std::min(t, n_frames));
+}
+
+/* The form of the node stacks for a launch with the handle's current parameters (see adder_b200_video::form).
+ * ADDER_B200_OFFSET=0 keeps everything in the eager form (A/B runs). */
+bool offset_wanted(const adder_b200_video* v, float time_spanned) {
+  if (const char* e = getenv("ADDER_B200_OFFSET"))
+    if (atoi(e) == 0) return false;
+  return adder::offset_form_eligible(v->multi_mode == ADDER_MULTI_COLLAPSE, time_spanned, v->delta_t_max);
+}
+int choose_form(adder_b200_video* v, cudaStream_t stream, float time_spanned) {
+  const int want = offset_wanted(v, time_spanned) ? 1 : 0;
+  if (want == v->form) return ADDER_OK;
+  if (v->pristine) { /* a fresh state reads the same in both forms (one root, no levels below it) */
+    v->form = want;
+    return ADDER_OK;
+  }
+  if (v->form == 1) { /* not eligible any more: back to the reference's own representation, in place */
+    if (stream != v->stream) CU(cudaStreamSynchronize(v->stream));
+    adder::offset_to_eager_kernel<<<(v->P + 255) / 256, 256, 0, stream>>>(v->d_hdr, v->d_nodes, v->P, 2ull * v->Ppad);
+    v->launches++;
+    CU(cudaGetLastError());
+    v->form = 0;
+  }
+  /* an eager state that has integrated frames stays eager: nothing guarantees the bounds the offset form needs */
+  return ADDER_OK;
+}
+
 /* Queue one frame on `stream`.  d_frame: P dense bytes on the device. */
 /* Queue n_frames consecutive frames (d_frame + f * frame_stride) as ONE launch: frame f's events go to
  * d_events + f * cap, its chunk offsets to d_chunk_off + f * (n_chunks + 1).  Tickets run frame-major over the
@@ -380,11 +466,12 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   if (v->tree_mode != ADDER_MODE_FRAME_PERFECT)
     return fail(ADDER_ERR_UNSUPPORTED, "Mode::Continuous is not on the framed path (framed.rs:67 always builds FramePerfect)");
   if (n_frames == 0) return ADDER_OK;
-  if (n_frames > 1 && (v->feature_detection || n_frames > kMaxFramesPerLaunch || (uint64_t)n_frames * v->n_tiles_r >= (1ull << 31)))
+  if (n_frames > 1 && (v->feature_detection || n_frames > kMaxFramesPerLaunch || ((uint64_t)n_frames + kMaxTBlock) * v->n_tiles_r >= (1ull << 31)))
     return fail(ADDER_ERR_INTERNAL, "launch_frames: batch not split by the caller");
   /* everything that can fail comes before the first side effect (host counters, queued kernels) */
   if (v->feature_detection && v->row0 != 0)
     return fail(ADDER_ERR_UNSUPPORTED, "feature detection on a row band: the FAST neighbourhood would cross bands");
+  if (int rc = choose_form(v, stream, time_spanned)) return rc;
   if (int rc = ensure_depth(v, derive_depth(v))) return rc;
   if (v->feature_detection) {
     if (!v->d_feat_mask) {
@@ -437,6 +524,8 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   a.frame_stride = frame_stride;
   a.n_frames = n_frames;
   a.status_ring = v->status_ring;
+  a.tblock = tblock_of(v, n_frames);
+  a.tblock_magic = adder::ref_magic_of(a.tblock);
   a.running_t = v->d_rt_cur;
   a.tiles_magic = adder::ref_magic_of(v->n_tiles_r);
   a.hdr = v->d_hdr;
@@ -494,8 +583,9 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   p.practical_d_max = log2_raw(255.0f * (float)(v->delta_t_max / v->ref_time)); /* :668-670 */
 
   v->d_last_input = d_frame + (size_t)(n_frames - 1u) * frame_stride;
+  v->pristine = false;
   launch_variant(v, a, stream);
-  v->ticket_base += n_frames * v->n_tiles_r + launch_grid(v); /* every CTA draws one ticket past the end */
+  v->ticket_base += ((n_frames + a.tblock - 1u) / a.tblock) * v->n_tiles_r + launch_grid(v); /* items of the launch; every CTA draws one past the end */
   v->launches++;
   CU(cudaGetLastError());
   if (!v->feature_detection && v->d_n_new) CU(cudaMemsetAsync(v->d_n_new, 0, sizeof(uint32_t), stream)); /* this frame found none */
@@ -668,7 +758,11 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       { /* Status words for as many frames as can be in flight at once: a CTA holds at most three tickets, so the
          * tickets being worked on span at most 3 * grid / tiles frames; + 3 for the frame being read by look-backs,
          * the one before it (dependencies) and rounding. */
-        uint32_t need = (3u * v->grid + v->n_tiles_r - 1u) / v->n_tiles_r + 3u, ring = 1u;
+        /* With T frames per item (tblock_of) a CTA's three tickets lie in at most two items, the items being worked on
+         * span at most 2 * grid / tiles + 1 blocks of T frames, and progress beyond the block after a lagging tile's is
+         * impossible (every later tile of its frame waits for its aggregate, every later frame of its tile for its state). */
+        uint32_t need = std::max((3u * v->grid + v->n_tiles_r - 1u) / v->n_tiles_r + 3u,
+                                 kMaxTBlock * ((2u * v->grid + v->n_tiles_r - 1u) / v->n_tiles_r + 2u) + 3u), ring = 1u;
         while (ring < need) ring <<= 1;
         v->status_ring = ring;
         v->status_words = (uint64_t)ring * v->n_tiles_r;
@@ -680,6 +774,7 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       CU(cudaMalloc(&v->d_counters, 6 * sizeof(unsigned long long)));
       CU(cudaMemsetAsync(v->d_counters, 0, 6 * sizeof(unsigned long long), v->stream));
       if (int rc = realloc_chunks(v)) return rc;
+      v->form = offset_wanted(v, (float)v->ref_time) ? 1 : 0; /* the defaults are eligible; a pristine state changes form for free */
       if (int rc = ensure_depth(v, derive_depth(v))) return rc;
       CU(cudaStreamSynchronize(v->stream));
       return ADDER_OK;
@@ -951,7 +1046,7 @@ int adder_b200_video_get_info(const adder_b200_video* v, adder_b200_video_info_t
   out->crf = v->crf;
   out->max_depth = v->depth;
   out->device = (uint32_t)v->device;
-  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)NODE_LEVELS_ALLOC(v->depth) * sizeof(uint4)); /* the park arena is scratch, not state */
+  out->state_bytes = (uint64_t)v->Ppad * (sizeof(uint2) + 1 + (uint64_t)v->records * 2u * sizeof(uint4)); /* the park arena is scratch, not state */
   out->events_capacity = v->events_capacity;
   return ADDER_OK;
 }
@@ -963,6 +1058,7 @@ int adder_b200_video_reset_state(adder_b200_video* v) {
   v->launches++;
   CU(cudaGetLastError());
   v->running_t = 0.0f;
+  v->pristine = true;
   v->in_interval_count = 1;
   v->display_force = true;
   v->pend_n = 0; /* events of frames integrated before the reset are dropped with the state */
@@ -1424,8 +1520,27 @@ int adder_b200_video_read_px(adder_b200_video* v, size_t index, adder_b200_px_st
   out->dtm_reached = HDR_DTM_REACHED(h.y);
   out->popped_dtm = HDR_POPPED(h.y);
   out->time_mode = (uint8_t)v->time_mode;
+  uint4 root = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t k = 0; k < out->length && k < v->depth; k++) {
     uint4 n;
+    if (v->form == 1) { /* offset form -> the reference's node (px_offset.cuh) */
+      if (k == 0u) {
+        CU(cudaMemcpy(&root, v->d_nodes + 2ull * index, sizeof(root), cudaMemcpyDeviceToHost));
+        n = root;
+      } else if (k + 1u >= out->length) {
+        n = make_uint4(0u, 0u, 0u, 0u); /* the tail is always a node that has not integrated yet, and is not stored */
+      } else {
+        CU(cudaMemcpy(&n, v->d_nodes + 2ull * index + (size_t)k * 2ull * v->Ppad, sizeof(n), cudaMemcpyDeviceToHost));
+        if (!out->popped_dtm) {
+          float rx, rdt;
+          memcpy(&rx, &root.x, 4);
+          memcpy(&rdt, &root.y, 4);
+          const float fx = (float)((uint32_t)rx - n.x), fdt = (float)((uint32_t)rdt - n.y);
+          memcpy(&n.x, &fx, 4);
+          memcpy(&n.y, &fdt, 4);
+        }
+      }
+    } else
     CU(cudaMemcpy(&n, v->d_nodes + NODE_SLOT(k, index, v->Ppad), sizeof(n), cudaMemcpyDeviceToHost));
     memcpy(&out->nodes[k].integration, &n.x, 4);
     memcpy(&out->nodes[k].delta_t, &n.y, 4);

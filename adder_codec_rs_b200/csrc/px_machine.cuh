@@ -383,6 +383,7 @@ ADDER_HD bool px_step(const PxParams& a, uint32_t v, PxHeader& h, Node n0, Node 
     bool cut = false;
     if (need_pop) {
       popped = 1;
+      mem.set_popped(); /* offset form (OffsetAdaptor below): the levels stored from here on are never integrated again under Collapse */
       root_new = true;
       if (!NODE_HAS_BEST(n0.w)) {
         if (n0.integ == 0.0f && n0.dt > 0.0f) { /* zero event, :155-160 */

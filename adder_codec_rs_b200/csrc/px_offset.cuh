@@ -1,0 +1,307 @@
+/*
+ * px_offset.cuh — the OFFSET FORM of a pixel's node stack, and the state machine that works on it.
+ *
+ * The reference integrates EVERY live node of a pixel every frame (PixelArena::integrate,
+ * adder-codec-rs/src/transcoder/event_pixel_tree.rs:340-390): `integration += intensity; delta_t += time` on each
+ * level until the first level that fires.  On a scene that changes rarely the stacks are deep (2..11 live nodes after a
+ * few hundred frames of a static pixel) and that walk IS the cost of the frame: 16 bytes read and written and ~80
+ * instructions per level per pixel, the warp running as long as its deepest stack.
+ *
+ * All levels of one pixel receive the same increments.  So a level below the root need not be touched while it does
+ * not fire: its values are the ROOT's values minus what the root had accumulated when the level was born,
+ *
+ *     integration_k = X - oi_k        delta_t_k = DT - od_k        (X, DT: the root's integration / delta_t)
+ *
+ * and the offsets (oi_k, od_k) are constants of the level.  Level k fires in the frame in which the root's new
+ * integration X reaches  thr_k = oi_k + 2^d_k  (integrate_main's test `integration + intensity >= D_SHIFT[d]`,
+ * :423, on exact integers).  The shallowest such level is what the reference's walk finds (:344-366): it gets its best
+ * event and a fresh child, everything deeper is dropped.  With
+ *
+ *     meta  = (tmin, kmin)    the smallest threshold among the pixel's stored levels and the shallowest level that has it
+ *     pmin_k, pk_k            the same over the levels ABOVE level k, kept in level k's record
+ *
+ * a frame of an unchanged pixel touches the root and ONE level record, whatever the depth: if X < tmin no stored level
+ * fires, so the walk reaches the tail, which is always a fresh node (see below) and always fires on its first
+ * integration; otherwise start at kmin and hop to pk while pmin <= X — the hop ends at the shallowest firing level.
+ *
+ * What makes this exact (bit-identical to the reference's f32 arithmetic):
+ *  - a u8 source gives integer intensities, `time` is an integer number of ticks, and every integration / delta_t is a
+ *    sum of those starting from 0 (PixelNode::new :502-514; integrate_main :418-479 never scales them): integers, exact
+ *    in f32 below 2^24, so sums, differences and comparisons agree with integer arithmetic;
+ *  - under PixelMultiMode::Collapse a root is popped when its delta_t reaches delta_t_max (:394-396), after which only
+ *    the root integrates (:360-362): while levels below the root are live, DT <= dtm + time and X <= 255 * DT / time.
+ *    The host selects this form only when those bounds are below 2^24 (offset_form_eligible, adder_b200.cu); everything
+ *    else (PixelMultiMode::Normal, fractional time_spanned, huge delta_t_max / ref ratios) runs the eager form and px_step.
+ *  - After a Δt_max pop under Collapse the levels below the root are never integrated again; they are stored with their
+ *    actual values ("frozen": the header's popped_dtm bit says which reading applies).
+ *
+ * The tail.  For length >= 2 the last node of the stack is always a node that has never integrated (all zero): every
+ * way the machine produces a stack of two or more levels ends with PixelNode::new (:344-355), and a fresh tail fires on
+ * its first integration (its d is set from the intensity just before, :332-335, and 2^floor(log2 v) <= v; v = 0 gives
+ * D_ZERO_INTEGRATION whose threshold is 0).  It is therefore not stored at all: level length-1 is implicit.
+ *
+ * What the machine relies on.  Starting from Video::new and running only this machine (or px_step on eligible parameters,
+ * which is the same function of the state), a root that has integrated at least once always holds a best event (a fresh
+ * node fires on its first integration, and every later root is either a fresh node or a level that has fired).  The
+ * reference's branches for a root WITHOUT a best event at a Δt_max pop (zero event / synthesised event, :155-193), for a
+ * popped root with children that has nothing to give (:249-265 looking further down) and for a root at D_MAX can
+ * therefore not be reached; px_offset raises ADDER_DEVERR_INTERNAL there instead of carrying a copy of px_step (inlined next to the short
+ * path, px_step cost 124 bytes of spills per thread and 25 % on every workload; as a __noinline__ function it crashes
+ * ptxas 12.9).  The host simulation runs every shared case and the long runs of tests/test_px_offset_host.py through
+ * this very function and checks that the flag stays clear.
+ *
+ * Layout (state_layout.h): record 0 of a pixel = root node (16 B, eager, as in the eager form) + meta (16 B);
+ * record k >= 1 = level k: { oi, od, best_event.delta_t, w, pmin, pk, -, - } (32 B = one DRAM sector, one 256-bit access).
+ */
+#pragma once
+#include "px_machine.cuh"
+
+namespace adder {
+
+constexpr uint32_t kThrNever = 0xFFFFFFFFu;
+
+/* The meta half of record 0.  Besides (tmin, kmin) it caches what is needed to FIRE level kmin without reading its record:
+ * its delta_t offset, its d (its integration offset is then tmin - 2^d), and its own (pmin, pk).  The level that fires is
+ * written as a whole record afterwards, so the common frames of an unchanged pixel read no level record at all:
+ *   - the tail fires (no stored level has reached its threshold): a new record is written;
+ *   - level kmin fires from the cache: its record is rewritten.
+ * A record is read only when the cache does not describe level kmin (valid = 0: it was left behind when kmin changed to a
+ * shallower level, and is filled when that level actually fires), when a shallower level fires in the same frame (the
+ * hop), when a changed pixel pops its stack, or in the one frame per delta_t_max in which the stack moves up a level. */
+struct OffMeta {
+  uint32_t tmin;  /* smallest threshold among the stored levels (kThrNever: none) */
+  uint32_t od;    /* cached: level kmin's delta_t offset */
+  uint32_t pmin;  /* cached: level kmin's pmin */
+  uint32_t info;  /* kmin | d << 8 | pk << 16 | valid << 31 */
+};
+ADDER_HD uint32_t meta_kmin(const OffMeta& m) { return m.info & 0xFFu; }
+ADDER_HD uint32_t meta_d(const OffMeta& m) { return (m.info >> 8) & 0xFFu; }
+ADDER_HD uint32_t meta_pk(const OffMeta& m) { return (m.info >> 16) & 0xFFu; }
+ADDER_HD bool meta_valid(const OffMeta& m) { return (m.info >> 31) != 0u; }
+/* the cache can stand for a level only if its integration offset follows from its threshold: d < 31 */
+ADDER_HD uint32_t meta_info(uint32_t k, uint32_t d, uint32_t pk) { return k | (d << 8) | (pk << 16) | (d < 31u ? 0x80000000u : 0u); }
+ADDER_HD void meta_clear(OffMeta& m) { m.tmin = kThrNever, m.od = 0u, m.pmin = kThrNever, m.info = 0u; }
+
+struct OffRec {
+  uint32_t oi, od; /* offsets (or, frozen: the f32 bits of integration and delta_t) */
+  float best_dt;
+  uint32_t w;
+  uint32_t pmin, pk;
+};
+
+/* the root integration at which a level with offset oi and decimation d (in w) fires */
+ADDER_HD uint32_t off_thr(uint32_t oi, uint32_t w) {
+  const uint32_t d = NODE_D(w);
+  if (d >= 128u) return 0u;        /* D_SHIFT[128..] = 0: fires whenever it is reached */
+  if (d >= 31u) return kThrNever;  /* 2^d beyond any integration this form admits */
+  return oi + (1u << d);
+}
+
+/* Host side: may a launch with these parameters keep the node stacks in offset form?  Every integration and delta_t
+ * that the form subtracts must be an integer below 2^24 (see above); the margins are a factor of two, so that calls with
+ * different (eligible) time_spanned values may follow each other. */
+inline bool offset_form_eligible(bool collapse, float time, uint32_t dtm) {
+  if (!collapse) return false;
+  if (!(time >= 1.0f) || !(time < 8388608.0f) || time != (float)(uint32_t)time) return false;
+  const uint64_t t = (uint64_t)time;
+  const uint64_t dt_max = (uint64_t)dtm + 2ull * t;  /* a live root's delta_t never exceeds dtm + time (:394-396) */
+  const uint64_t x_max = 255ull * (dt_max / t + 2ull); /* and it has integrated at most that many samples */
+  return dt_max < (1ull << 23) && x_max < (1ull << 23);
+}
+
+/* a stored level as the reference's node, given the root's integration / delta_t the offsets refer to */
+ADDER_HD Node off_node(const OffRec& q, uint32_t x, uint32_t dt) {
+  Node n;
+  n.integ = u2f(x - q.oi);
+  n.dt = u2f(dt - q.od);
+  n.best_dt = q.best_dt;
+  n.w = q.w;
+  return n;
+}
+
+/*
+ * One pixel, one frame, offset form (PixelMultiMode::Collapse: offset_form_eligible).  n0 = the root (in: as loaded, out:
+ * as to be stored), meta likewise; the caller stores header and record 0 afterwards.  Same contract as px_step otherwise.
+ */
+/* kDefer: the one level record a common frame writes is handed back (*st_k = its level, 0 = none; *st_q) instead of being
+ * stored, so that the kernel can store the records of a row's pixels together once the warp has reconverged. */
+template <bool kPlain = false, bool kDefer = false, class Mem, class Sink>
+ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, OffMeta& meta, Mem& mem, Sink& sink, uint32_t& errbits,
+                        uint8_t* disp, uint32_t* st_k = nullptr, OffRec* st_q = nullptr) {
+  const float intensity = (float)v;
+  const float time = a.time;
+  float lf = h.lf;
+  uint32_t base = HDR_BASE(h.y), cth = HDR_CTHRESH(h.y), cnt = HDR_COUNTER(h.y);
+  uint32_t len = HDR_LENGTH(h.y);
+  uint32_t popped = HDR_POPPED(h.y);
+  const uint32_t lo = base > cth ? base - cth : 0u;
+  const uint32_t hi = base + cth > 255u ? 255u : base + cth;
+  bool root_new = false;
+  Node r = n0;
+
+  if (v < lo || v > hi) { /* video.rs:1338-1358 -> pop_best_events (:213-287) */
+    const uint32_t x0 = f2u(r.integ), dt0 = f2u(r.dt); /* before pop_node: a zero event clears the root's delta_t */
+    const bool any = pop_node<kPlain>(a, sink, lf, r);
+    bool fresh_root = len > 1u; /* the fresh tail becomes the root (:267-270); a stack of one node keeps its root as it is */
+    if (popped) { /* Collapse after a Δt_max pop: the first event only, then D_EMPTY and PixelNode::new (:249-265) */
+      if (any) {
+        lf = a.running_t_prev; /* running_t before this frame's `+= time` (:337 runs later) */
+        sink.push(ADDER_D_EMPTY, f2u(a.running_t_prev));
+        fresh_root = true;
+      } else if (len > 1u) {
+        errbits |= ADDER_DEVERR_INTERNAL; /* (see the header: only a root that has never integrated has nothing to give,
+                                           * and such a root — put there by a Δt_max pop in the frame it fired — has no child) */
+      }
+    } else if (len > 2u) { /* the stored levels; the tail is fresh and has nothing to give (:223-247) */
+      OffRec q = mem.load_rec(1u);
+      for (uint32_t k = 1;;) { /* record k+1 is requested before record k is worked on */
+        OffRec nxt = q;
+        if (k + 2u < len) nxt = mem.load_rec(k + 1u);
+        Node nk = off_node(q, x0, dt0);
+        pop_node<kPlain>(a, sink, lf, nk);
+        if (++k + 1u >= len) break;
+        q = nxt;
+      }
+    }
+    if (fresh_root) r.integ = 0.0f, r.dt = 0.0f, r.best_dt = 0.0f, r.w = 0u;
+    len = 1;
+    popped = 0;
+    base = v;
+    root_new = true;
+  }
+
+  /* ---- integrate (:317-413): the root ------------------------------------------------------------------------------ */
+  if (len == 1u && r.dt == 0.0f && r.integ == 0.0f) r.w = (r.w & ~0xFFu) | get_d_from_intensity(intensity); /* :332-335 */
+  const uint32_t x_in = f2u(r.integ), dt_in = f2u(r.dt);
+  const bool fired0 = integrate_main(r, intensity, time);
+  const uint32_t dtm_reached = r.dt >= a.dtm_f ? 1u : 0u; /* :394 */
+  if (NODE_D(r.w) == ADDER_D_MAX) errbits |= ADDER_DEVERR_INTERNAL; /* needs an integration of 2^126 */
+  uint32_t new_len = len;
+
+  if (dtm_reached && !popped) {
+    /* ---- pop_top_event (video.rs:1371-1374, :139-210): the root's best event leaves ------------------------------- */
+    if (!NODE_HAS_BEST(r.w)) errbits |= ADDER_DEVERR_INTERNAL; /* (see the header) */
+    emit_abs<kPlain>(a, sink, lf, NODE_BEST_D(r.w), r.best_dt);
+    popped = 1;
+    root_new = true;
+    meta_clear(meta);
+    if (fired0 || len < 2u) { /* the root fired this very frame: it is replaced by a fresh node (:164-193 -> :195-199) */
+      if (!fired0) errbits |= ADDER_DEVERR_INTERNAL; /* a root with a best event that did not fire has a child */
+      r.integ = 0.0f, r.dt = 0.0f, r.best_dt = 0.0f;
+      r.w = get_d_from_intensity(intensity);
+      new_len = 1;
+    } else {
+      /* the stack moves up a level (:201-204) while every level integrates this frame (:340-390) up to the first one
+       * that fires.  What is stored below the new root is never integrated again under Collapse: frozen values. */
+      const uint32_t last = len - 1u;
+      OffRec q{0u, 0u, 0.0f, 0u, 0u, 0u};
+      if (last > 1u) q = mem.load_rec(1u);
+      for (uint32_t k = 1;; k++) {
+        OffRec nxt = q;
+        if (k + 1u < last) nxt = mem.load_rec(k + 1u);
+        Node nk;
+        if (k == last) { /* the fresh tail */
+          nk.integ = 0.0f, nk.dt = 0.0f, nk.best_dt = 0.0f;
+          nk.w = get_d_from_intensity(intensity);
+        } else {
+          nk = off_node(q, x_in, dt_in);
+        }
+        const bool fired = integrate_main(nk, intensity, time);
+        if (k == 1u) {
+          r = nk;
+        } else {
+          OffRec f;
+          f.oi = f_bits(nk.integ), f.od = f_bits(nk.dt), f.best_dt = nk.best_dt, f.w = nk.w, f.pmin = kThrNever, f.pk = 0u;
+          mem.store_rec(k - 1u, f);
+        }
+        if (fired || k == last) {
+          if (!fired) errbits |= ADDER_DEVERR_INTERNAL;
+          new_len = k + 1u; /* levels 0 .. k-1 and a fresh tail */
+          break;
+        }
+        q = nxt;
+      }
+    }
+  } else if (fired0) { /* :344-355: a fresh child, deeper nodes dropped */
+    if (a.depth > 1u) new_len = 2; else errbits |= ADDER_DEVERR_DEPTH;
+    meta_clear(meta);
+    root_new = true;
+  } else if (!popped && len > 1u) {
+    /* ---- the walk below the root (:340-390) in one step: the shallowest stored level whose threshold the root's
+     * integration has reached, else the fresh tail ------------------------------------------------------------------- */
+    const uint32_t x = f2u(r.integ), dt = f2u(r.dt);
+    if ((x | dt) >> 24) errbits |= ADDER_DEVERR_INTERNAL; /* beyond what offset_form_eligible admits */
+    uint32_t k;
+    OffRec q;
+    Node nk;
+    if (x >= meta.tmin) {
+      k = meta_kmin(meta);
+      if (meta_valid(meta) && meta.pmin > x) { /* level kmin fires, and everything about it is in the cache */
+        q.oi = meta.tmin - (1u << meta_d(meta));
+        q.od = meta.od;
+        q.best_dt = 0.0f; /* replaced by the firing */
+        q.w = meta_d(meta);
+        q.pmin = meta.pmin;
+        q.pk = meta_pk(meta);
+      } else {
+        q = mem.load_rec(k);
+        while (q.pmin <= x) { /* a shallower level has reached its threshold too: the walk stops there (:344-366) */
+          k = q.pk;
+          q = mem.load_rec(k);
+        }
+      }
+      nk = off_node(q, x_in, dt_in);
+    } else { /* the tail: PixelNode::new with its d from this intensity (:332-335) */
+      k = len - 1u;
+      q.pmin = meta.tmin;
+      q.pk = meta_kmin(meta);
+      nk.integ = 0.0f, nk.dt = 0.0f, nk.best_dt = 0.0f;
+      nk.w = get_d_from_intensity(intensity);
+    }
+    if (!integrate_main(nk, intensity, time)) errbits |= ADDER_DEVERR_INTERNAL;
+    q.oi = x - f2u(nk.integ);
+    q.od = dt - f2u(nk.dt);
+    q.best_dt = nk.best_dt;
+    q.w = nk.w;
+    if (kDefer) {
+      *st_k = k;
+      *st_q = q;
+    } else {
+      mem.store_rec(k, q);
+    }
+    const uint32_t thr = off_thr(q.oi, q.w);
+    if (thr < q.pmin) { /* this level is the next to fire (ties go to the shallower level, like the walk) */
+      meta.tmin = thr;
+      meta.od = q.od;
+      meta.pmin = q.pmin;
+      meta.info = meta_info(k, NODE_D(q.w), q.pk);
+    } else if (x >= meta.tmin) { /* a stored level fired and a level above it holds the minimum now; the cache is filled
+                                  * when that level fires (the tail leaves tmin / kmin and the cache as they are) */
+      meta.tmin = q.pmin;
+      meta.info = q.pk;
+    }
+    if (k + 1u >= a.depth) errbits |= ADDER_DEVERR_DEPTH;
+    new_len = k + 2u > a.depth ? a.depth : k + 2u;
+  }
+  /* (popped: Collapse integrates the root only, :360-362; a stack of one node has nothing below the root) */
+
+  if (cth < a.c_max) { /* :402-412 */
+    if (cnt >= a.vel_m1) {
+      cth = cth + 1u > 255u ? 255u : cth + 1u;
+      cnt = 0;
+    } else {
+      cnt = cnt + a.cnt_inc > 255u ? 255u : cnt + a.cnt_inc;
+    }
+  }
+  n0 = r;
+  h.lf = lf;
+  h.y = HDR_PACK(base, cth, cnt, new_len, dtm_reached, popped);
+  /* video.rs:713-730.  An unchanged root best event gives the byte already in running_intensities. */
+  if (NODE_HAS_BEST(r.w) && a.display && (root_new || a.display == 2u || ADDER_VIEW_OF(a) == 3u)) {
+    *disp = frame_value_u8<kPlain>(a, NODE_BEST_D(r.w), f2u(r.best_dt), lf);
+    return true;
+  }
+  return false;
+}
+
+}  // namespace adder

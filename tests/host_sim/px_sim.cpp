@@ -13,12 +13,13 @@
 #define ADDER_HOST_SIM 1
 #include "../../include/adder_b200.h"
 #include "../../adder_codec_rs_b200/csrc/px_machine.cuh"
+#include "../../adder_codec_rs_b200/csrc/px_offset.cuh"
 #include "../../adder_codec_rs_b200/csrc/gray_math.h"
 
 namespace adder {
 int g_fast_div_ulps = 0;
 }
-static int g_entry = 0; /* 0: px_step (what the kernel calls by default), 1: px_frame (short path + fallback), 2: px_step<true> + deferred deep walk, 3: px_step<false, true> where it applies */
+static int g_entry = 0; /* 4: px_offset on offset-form state where offset_form_eligible() allows it (else px_step); 0: px_step (what the kernel calls by default), 1: px_frame (short path + fallback), 2: px_step<true> + deferred deep walk, 3: px_step<false, true> where it applies */
 namespace {
 struct HostNodes {
   adder::Node* p;
@@ -27,6 +28,7 @@ struct HostNodes {
   void store(uint32_t k, const adder::Node& n) const { p[(size_t)k * stride] = n; }
   void store_fresh(uint32_t k, const adder::Node& n) const { p[(size_t)k * stride] = n; }
   void used_preloaded() const {}
+  void set_popped() const {}
   void prefetch_levels(uint32_t) const {}
   void unused_load() const {}
   adder::Node* cursor_level1() const { return p + stride; }
@@ -35,6 +37,14 @@ struct HostNodes {
   adder::Node load_at(const adder::Node* q) const { return *q; }
   void store_at(adder::Node* q, const adder::Node& n) const { *q = n; }
   void reload(adder::Node& n0, adder::Node& n1) const { n0 = p[0]; n1 = p[stride]; }
+};
+/* offset-form records of one pixel (px_offset.cuh): record k of pixel i at recs[k * P + i] */
+struct HostRecs {
+  adder::OffRec* p;
+  size_t stride;
+  uint32_t n_loads = 0, n_stores = 0;
+  adder::OffRec load_rec(uint32_t k) { n_loads++; return p[(size_t)k * stride]; }
+  void store_rec(uint32_t k, const adder::OffRec& r) { n_stores++; p[(size_t)k * stride] = r; }
 };
 struct VecSink {
   std::vector<adder_event_t>* out;
@@ -56,6 +66,11 @@ struct sim_video {
   std::vector<adder::PxHeader> hdr;
   std::vector<adder::Node> nodes;
   std::vector<uint8_t> running;
+  /* offset form (g_entry == 4): root nodes stay in nodes[0 * P + i] */
+  std::vector<adder::OffRec> recs;
+  std::vector<adder::OffMeta> meta;
+  int form = -1; /* -1 undecided, 0 eager, 1 offset */
+  uint64_t rec_loads = 0, rec_stores = 0, px_frames = 0;
   std::vector<adder_event_t> events;
   float running_t;
   uint32_t err;
@@ -112,7 +127,35 @@ size_t sim_integrate(sim_video* v, const uint8_t* frame, float time, uint32_t re
   adder::build_exact_lut(ref, lut);
   p.exact_lut = lut;
   v->events.clear();
+  if (g_entry == 4) {
+    const bool ok = adder::offset_form_eligible(collapse != 0, time, dtm);
+    if (v->form < 0) {
+      v->form = ok ? 1 : 0;
+      if (ok) {
+        v->recs.assign(v->P * v->depth, adder::OffRec{0, 0, 0.0f, 0, 0, 0});
+        v->meta.assign(v->P, adder::OffMeta{0, 0, 0, 0});
+      }
+    } else if (v->form == 1 && !ok) {
+      v->err |= 0x80000000u; /* the test cases never change eligibility mid-stream (the library converts the state) */
+    }
+  }
   for (size_t i = 0; i < v->P; i++) {
+    if (g_entry == 4 && v->form == 1) {
+      HostRecs mem{v->recs.data() + i, v->P};
+      const uint32_t ch = (uint32_t)(i % v->c), x = (uint32_t)((i / v->c) % v->w), y = (uint32_t)(i / ((size_t)v->c * v->w));
+      VecSink sink{&v->events, (uint16_t)x, (uint16_t)y, (uint8_t)(v->c == 1 ? ADDER_C_NONE : ch)};
+      uint8_t disp = 0;
+      bool show;
+      if (abs_time && view_mode == 0)
+        show = adder::px_offset<true>(p, frame[i], v->hdr[i], v->nodes[i], v->meta[i], mem, sink, v->err, &disp);
+      else
+        show = adder::px_offset<false>(p, frame[i], v->hdr[i], v->nodes[i], v->meta[i], mem, sink, v->err, &disp);
+      if (show) v->running[i] = disp;
+      v->rec_loads += mem.n_loads;
+      v->rec_stores += mem.n_stores;
+      v->px_frames++;
+      continue;
+    }
     HostNodes mem{v->nodes.data() + i, v->P};
     const uint32_t ch = (uint32_t)(i % v->c), x = (uint32_t)((i / v->c) % v->w), y = (uint32_t)(i / ((size_t)v->c * v->w));
     VecSink sink{&v->events, (uint16_t)x, (uint16_t)y, (uint8_t)(v->c == 1 ? ADDER_C_NONE : ch)};
@@ -186,9 +229,22 @@ void sim_force_display(sim_video* v) { v->force_display = 1; }
 const adder_event_t* sim_events(const sim_video* v) { return v->events.data(); }
 const uint8_t* sim_running(const sim_video* v) { return v->running.data(); }
 uint32_t sim_err(const sim_video* v) { return v->err; }
+int sim_form(const sim_video* v) { return v->form; }
+/* offset form: level records read / written and pixel-frames so far */
+void sim_rec_traffic(const sim_video* v, uint64_t out[3]) { out[0] = v->rec_loads; out[1] = v->rec_stores; out[2] = v->px_frames; }
 /* header words + node k of pixel i, for state comparison */
 void sim_px(const sim_video* v, size_t i, float* lf, uint32_t* y) { *lf = v->hdr[i].lf; *y = v->hdr[i].y; }
 void sim_node(const sim_video* v, size_t i, uint32_t k, float* integ, float* dt, float* best_dt, uint32_t* w) {
+  if (v->form == 1 && k > 0) { /* offset form -> the reference's node (what adder_b200_video_read_px does in the library) */
+    const uint32_t len = HDR_LENGTH(v->hdr[i].y);
+    if (k + 1u >= len) { *integ = 0.0f; *dt = 0.0f; *best_dt = 0.0f; *w = 0u; return; }
+    const adder::OffRec& r = v->recs[(size_t)k * v->P + i];
+    const adder::Node& root = v->nodes[i];
+    if (HDR_POPPED(v->hdr[i].y)) { *integ = adder::bits_f(r.oi); *dt = adder::bits_f(r.od); }
+    else { *integ = adder::u2f(adder::f2u(root.integ) - r.oi); *dt = adder::u2f(adder::f2u(root.dt) - r.od); }
+    *best_dt = r.best_dt; *w = r.w;
+    return;
+  }
   const adder::Node& n = v->nodes[(size_t)k * v->P + i];
   *integ = n.integ; *dt = n.dt; *best_dt = n.best_dt; *w = n.w;
 }

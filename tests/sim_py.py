@@ -12,6 +12,7 @@ _SO = os.path.join(_HERE, "libpx_sim.so")
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _DEPS = [os.path.join(_HERE, "px_sim.cpp"),
          os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "px_machine.cuh"),
+         os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "px_offset.cuh"),
          os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "state_layout.h"),
          os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "gray_math.h")]
 _lib = None
@@ -46,6 +47,9 @@ def lib():
         L.sim_div_ref.argtypes = [u32, u32]
         L.sim_frame_value_intensity.restype = u32
         L.sim_frame_value_intensity.argtypes = [u32, u32, u32]
+        L.sim_form.restype = i32
+        L.sim_form.argtypes = [vp]
+        L.sim_rec_traffic.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.sim_err.restype = u32
         L.sim_err.argtypes = [vp]
         L.sim_px.argtypes = [vp, sz, C.POINTER(f32), C.POINTER(u32)]
@@ -87,6 +91,16 @@ class SimVideo:
     def running(self):
         n = self.w * self.h * self.c
         return np.ctypeslib.as_array(self.L.sim_running(self.v), shape=(n,)).reshape(self.h, self.w, self.c).copy()
+
+    @property
+    def form(self):
+        """-1 undecided, 0 eager, 1 offset form (entry 4 only)."""
+        return self.L.sim_form(self.v)
+
+    def rec_traffic(self):
+        out = (C.c_uint64 * 3)()
+        self.L.sim_rec_traffic(self.v, out)
+        return tuple(out)
 
     @property
     def err(self):

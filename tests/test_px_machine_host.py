@@ -52,7 +52,7 @@ class _SimAdapter:
         self.in_interval = n
 
 
-@pytest.mark.parametrize("entry", [0, 1, 2, 3], ids=["px_step", "px_frame", "px_step_deferred_deep_walk", "px_step_plain"])
+@pytest.mark.parametrize("entry", [0, 1, 2, 3, 4], ids=["px_step", "px_frame", "px_step_deferred_deep_walk", "px_step_plain", "px_offset"])
 @pytest.mark.parametrize("case", [c for c in cases.CASES if not c.initial_d and c.roi is None], ids=lambda c: c.name)
 def test_machine_matches_oracle(case, entry):
     from tests import sim_py
