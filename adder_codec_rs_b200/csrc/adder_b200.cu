@@ -89,7 +89,6 @@ uint32_t f32_as_u32(float x) { /* Rust `as u32` */
 
 constexpr int kRing = 3; /* host-form pipeline depth */
 constexpr uint32_t kMaxFramesPerLaunch = adder::kMaxLaunchFrames; /* frames one integrate launch may span */
-constexpr uint32_t kMaxTBlock = 16;           /* frames of one tile a CTA may run back to back (FrameArgs::tblock) */
 constexpr uint32_t kRtSlots = 8;              /* launches whose running_t tables may be in flight before one is reused */
 
 }  // namespace
@@ -418,19 +417,6 @@ uint32_t choose_r(uint32_t P) {
   return 1;
 }
 
-/* T of a multi-frame launch: how many consecutive frames of one tile a CTA runs before it draws another tile (px_kernel.cuh
- * tile_of).  The tile's state then comes back from L2 instead of DRAM for T - 1 of T frames, provided one generation of
- * tiles — what all CTAs touch while each works on one tile-frame — fits L2: about 150 bytes per pixel of the large tile,
- * 89 MB for 592 CTAs against 126 MB.  ADDER_B200_TBLOCK overrides (1 = the frame-major order of round 1). */
-uint32_t tblock_of(const adder_b200_video* v, uint32_t n_frames) {
-  uint32_t t = 1u;
-  if (const char* e = getenv("ADDER_B200_TBLOCK")) {
-    const int n = atoi(e);
-    if (n >= 1) t = std::min<uint32_t>((uint32_t)n, kMaxTBlock);
-  }
-  return std::max(1u, std::min(t, n_frames));
-}
-
 /* The form of the node stacks for a launch with the handle's current parameters (see adder_b200_video::form).
  * ADDER_B200_OFFSET=0 keeps everything in the eager form (A/B runs). */
 bool offset_wanted(const adder_b200_video* v, float time_spanned) {
@@ -466,7 +452,7 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   if (v->tree_mode != ADDER_MODE_FRAME_PERFECT)
     return fail(ADDER_ERR_UNSUPPORTED, "Mode::Continuous is not on the framed path (framed.rs:67 always builds FramePerfect)");
   if (n_frames == 0) return ADDER_OK;
-  if (n_frames > 1 && (v->feature_detection || n_frames > kMaxFramesPerLaunch || ((uint64_t)n_frames + kMaxTBlock) * v->n_tiles_r >= (1ull << 31)))
+  if (n_frames > 1 && (v->feature_detection || n_frames > kMaxFramesPerLaunch || (uint64_t)n_frames * v->n_tiles_r >= (1ull << 31)))
     return fail(ADDER_ERR_INTERNAL, "launch_frames: batch not split by the caller");
   /* everything that can fail comes before the first side effect (host counters, queued kernels) */
   if (v->feature_detection && v->row0 != 0)
@@ -524,8 +510,6 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   a.frame_stride = frame_stride;
   a.n_frames = n_frames;
   a.status_ring = v->status_ring;
-  a.tblock = tblock_of(v, n_frames);
-  a.tblock_magic = adder::ref_magic_of(a.tblock);
   a.running_t = v->d_rt_cur;
   a.tiles_magic = adder::ref_magic_of(v->n_tiles_r);
   a.hdr = v->d_hdr;
@@ -585,7 +569,7 @@ int launch_frames(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_fra
   v->d_last_input = d_frame + (size_t)(n_frames - 1u) * frame_stride;
   v->pristine = false;
   launch_variant(v, a, stream);
-  v->ticket_base += ((n_frames + a.tblock - 1u) / a.tblock) * v->n_tiles_r + launch_grid(v); /* items of the launch; every CTA draws one past the end */
+  v->ticket_base += n_frames * v->n_tiles_r + launch_grid(v); /* every CTA draws one ticket past the end */
   v->launches++;
   CU(cudaGetLastError());
   if (!v->feature_detection && v->d_n_new) CU(cudaMemsetAsync(v->d_n_new, 0, sizeof(uint32_t), stream)); /* this frame found none */
@@ -758,11 +742,7 @@ int adder_b200_video_create(uint16_t width, uint16_t height, uint8_t channels, i
       { /* Status words for as many frames as can be in flight at once: a CTA holds at most three tickets, so the
          * tickets being worked on span at most 3 * grid / tiles frames; + 3 for the frame being read by look-backs,
          * the one before it (dependencies) and rounding. */
-        /* With T frames per item (tblock_of) a CTA's three tickets lie in at most two items, the items being worked on
-         * span at most 2 * grid / tiles + 1 blocks of T frames, and progress beyond the block after a lagging tile's is
-         * impossible (every later tile of its frame waits for its aggregate, every later frame of its tile for its state). */
-        uint32_t need = std::max((3u * v->grid + v->n_tiles_r - 1u) / v->n_tiles_r + 3u,
-                                 kMaxTBlock * ((2u * v->grid + v->n_tiles_r - 1u) / v->n_tiles_r + 2u) + 3u), ring = 1u;
+        uint32_t need = (3u * v->grid + v->n_tiles_r - 1u) / v->n_tiles_r + 3u, ring = 1u;
         while (ring < need) ring <<= 1;
         v->status_ring = ring;
         v->status_words = (uint64_t)ring * v->n_tiles_r;
@@ -1530,7 +1510,18 @@ int adder_b200_video_read_px(adder_b200_video* v, size_t index, adder_b200_px_st
       } else if (k + 1u >= out->length) {
         n = make_uint4(0u, 0u, 0u, 0u); /* the tail is always a node that has not integrated yet, and is not stored */
       } else {
-        CU(cudaMemcpy(&n, v->d_nodes + 2ull * index + (size_t)k * 2ull * v->Ppad, sizeof(n), cudaMemcpyDeviceToHost));
+        if (!out->popped_dtm && k + 2u == out->length) { /* the top level lives in the second half of record 0 */
+          uint4 t;
+          CU(cudaMemcpy(&t, v->d_nodes + 2ull * index + 1ull, sizeof(t), cudaMemcpyDeviceToHost));
+          adder::OffTop top;
+          top.a = t.x, top.b = t.y, top.pmin = t.w;
+          memcpy(&top.best_dt, &t.z, 4);
+          const adder::OffRec q = adder::top_unpack(top);
+          n.x = q.oi, n.y = q.od, n.w = q.w;
+          memcpy(&n.z, &q.best_dt, 4);
+        } else {
+          CU(cudaMemcpy(&n, v->d_nodes + 2ull * index + (size_t)k * 2ull * v->Ppad, sizeof(n), cudaMemcpyDeviceToHost));
+        }
         if (!out->popped_dtm) {
           float rx, rdt;
           memcpy(&rx, &root.x, 4);

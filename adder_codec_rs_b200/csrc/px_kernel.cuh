@@ -50,13 +50,10 @@
                          * row loop's own row-ahead loads already hide that latency.  A separate pass over the next tile that asked
                          * for the level records its pixels would read cost 15-30 % (same file) and was removed. */
 #endif
-#ifndef ADDER_PAIR_STORE
-#define ADDER_PAIR_STORE 0 /* 1 (experiment): a level record leaves as two 128-bit halves stored by a pair of lanes in ONE instruction,
-                            * so that the sector arrives at L2 whole */
-#endif
 #ifndef ADDER_ROW_PF
-#define ADDER_ROW_PF 1 /* offset form: at the end of a row, the level records the NEXT row's pixels will read are requested
-                        * (1: towards L2, 2: into L1) — by then that row's header and first record have arrived */
+#define ADDER_ROW_PF 0 /* 1: offset form, at the end of a row the level records the NEXT row's pixels will read are requested towards
+                        * L2 (by then that row's header and first record have arrived): within +-1.5 % on deep stacks, -3 % on
+                        * noise (profiles/r02r_ab_rowpf.txt, r02r_ab_top.txt): off */
 #endif
 #ifndef ADDER_DEEP_PF
 #define ADDER_DEEP_PF 2 /* px_step entry: pull levels 2..length-1 towards L1 (1) or L2 (2); 0 = off */
@@ -72,8 +69,6 @@ struct FrameArgs {
   uint32_t status_ring;    /* frames of status words kept (a power of two) */
   const float* running_t;  /* n_frames + 1 entries: PixelArena.running_t before frame f and after it (event_pixel_tree.rs:337) */
   unsigned long long tiles_magic; /* ceil(2^64 / n_tiles), 0 for n_tiles == 1 */
-  uint32_t tblock;                 /* T: a CTA takes a tile for T consecutive frames before it draws the next one (see tile_of) */
-  unsigned long long tblock_magic; /* ceil(2^64 / T), 0 for T == 1 */
   uint2* hdr;
   uint4* nodes;
   uint2* park_arena;               /* events beyond the shared-memory slots: [CTA][park buffer][slot][pixel-in-tile] */
@@ -464,35 +459,12 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   const uint32_t my_rows = duty ? (uint32_t)R - ADDER_DUTY_LESS : (uint32_t)R;
   const bool frame_aligned = ((reinterpret_cast<uintptr_t>(a.frame) | a.frame_stride) & 15u) == 0;
   const uint32_t n_frames = kMulti ? a.n_frames : 1u; /* kMulti = false: the single-frame form without the cross-frame machinery */
-  /* Work is handed out as ITEMS: item = (block of T frames, tile), drawn by ticket in the order block-major, tile-minor;
-   * the CTA that draws an item runs its T frames one after the other (virtual tickets item * T + j, one per pipeline
-   * iteration).  A tile's state, written for frame f, is read again for frame f + 1 one iteration later by the same CTA,
-   * while it is still in L2, and the level records of a stack — scattered 32-byte stores that DRAM serves at a fraction
-   * of its bandwidth (profiles/r02r_exp_debug.txt: 52 % of the time on aged 8K stacks) — are merged in L2 over the T
-   * frames before they are written back.  T = 1 is the frame-major order of round 1.  Frames beyond n_frames in the last
-   * block are never issued.  Tickets are still drawn in order and a tile's predecessors (same frame: items drawn
-   * earlier; previous frame: this CTA's own previous iteration or an item of the previous block) are always held by
-   * running CTAs or done, so neither the look-back nor the frame dependency can wait for a CTA that has not started. */
-  const uint32_t T = kMulti ? a.tblock : 1u;
-  const uint32_t n_blocks = (n_frames + T - 1u) / T;
-  const uint32_t n_items = n_blocks * a.n_tiles;
-  const uint32_t n_total = n_items * T; /* virtual tickets of this launch */
-  auto item_of = [&](uint32_t k) { return (kMulti && a.tblock_magic) ? mulhi_u32_u64(k, a.tblock_magic) : k; };
-  auto block_of = [&](uint32_t item) { return !kMulti ? 0u : a.tiles_magic ? mulhi_u32_u64(item, a.tiles_magic) : item; };
-  /* virtual ticket -> frame and tile */
-  auto tile_of = [&](uint32_t k, uint32_t& fi, uint32_t& tl) {
-    const uint32_t item = item_of(k), blk = block_of(item);
-    tl = item - blk * a.n_tiles;
-    fi = blk * T + (k - item * T);
-  };
-  /* the virtual ticket after k for this CTA (thread 0): the item's next frame, or a new item */
-  auto next_ticket = [&](uint32_t k) -> uint32_t {
-    if (k >= n_total) return kNone; /* this CTA has drawn its one item past the end */
-    const uint32_t item = item_of(k), blk = block_of(item), j = k - item * T;
-    const uint32_t tb = n_frames - blk * T < T ? n_frames - blk * T : T;
-    if (j + 1u < tb) return k + 1u;
-    return (atomicAdd(a.ticket, 1u) - a.ticket_base) * T;
-  };
+  const uint32_t n_total = n_frames * a.n_tiles; /* tickets of this launch */
+  /* ticket -> frame (tile = ticket - frame * n_tiles); the frame's row of status words.
+   * (Handing a tile to one CTA for T consecutive frames, so that its state would come back from L2, was built and measured:
+   * DRAM bytes and time unchanged for T = 8 and 16 — one generation of 592 tiles of 1984 pixels does not stay in L2 —
+   * profiles/r02r_dram_tblock.txt; removed again, its ticket arithmetic cost 2-3 % on every workload.) */
+  auto frame_of = [&](uint32_t k) { return !kMulti ? 0u : a.tiles_magic ? mulhi_u32_u64(k, a.tiles_magic) : k; };
   auto status_row = [&](uint32_t fi) { return !kMulti ? a.tile_status : a.tile_status + (unsigned long long)(fi & (a.status_ring - 1u)) * a.n_tiles; };
   /* this warp's row of round r, and the tile-relative index of this thread's pixel in it */
 #if ADDER_ROW_RUNS
@@ -507,9 +479,9 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
   /* tiles are handed out in ticket order so that a tile's predecessors are always held by CTAs that
    * are already running: the look-back can then never wait on a CTA that has not been scheduled. */
   if (tid == 0) {
-    const uint32_t t0 = (atomicAdd(a.ticket, 1u) - a.ticket_base) * T;
+    const uint32_t t0 = atomicAdd(a.ticket, 1u) - a.ticket_base;
     s_ticket[0] = t0;
-    s_ticket[1] = next_ticket(t0);
+    s_ticket[1] = t0 < n_total ? atomicAdd(a.ticket, 1u) - a.ticket_base : kNone;
     mbar_init(&s_bar_a, kWarps);
     mbar_init(&s_bar_b, 2u);
   }
@@ -529,9 +501,8 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
 
   /* samples of tile t -> this warp's staging area fb (asynchronously when whole and aligned) */
   auto fetch_frame = [&](uint32_t t, uint32_t fb) {
-    uint32_t fi, tl0;
-    tile_of(t, fi, tl0);
-    const uint32_t start = tl0 * TILE;
+    const uint32_t fi = frame_of(t);
+    const uint32_t start = (t - fi * a.n_tiles) * TILE;
     const uint8_t* src = a.frame + (unsigned long long)fi * a.frame_stride;
     uint8_t* dst = s_frame + fb * (kThreads * R) + warp * (R * 32u);
     if (start + TILE <= a.P && frame_aligned) {
@@ -560,8 +531,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
    * warp has arrived at the rendezvous of the current iteration, so a CTA can wait for its own publication.
    * Frame 0 of a launch follows the previous launch in stream order. */
   auto fetch_tile_head = [&](uint32_t t) {
-    uint32_t fi, tl;
-    tile_of(t, fi, tl);
+    const uint32_t fi = frame_of(t), tl = t - fi * a.n_tiles;
     if (kMulti && fi != 0u) {
       const unsigned long long* dep = status_row(fi - 1u) + tl;
       const uint32_t want = a.epoch + fi - 1u;
@@ -583,13 +553,12 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
      * the previous one was a tile: every CTA draws exactly one ticket past the end, which is what the
      * host advances ticket_base by) */
     uint32_t t_next2 = kNone;
-    if (tid == 0) t_next2 = next_ticket(s_ticket[(n + 1u) & 1u]);
+    if (tid == 0 && s_ticket[(n + 1u) & 1u] < n_total) t_next2 = atomicAdd(a.ticket, 1u) - a.ticket_base;
 
     /* ---- stage 1: the state machines of tile n --------------------------------------------------- */
     if (have_tile) {
-      uint32_t fi_cur, tl_cur;
-      tile_of(t_cur, fi_cur, tl_cur);
-      const uint32_t tile_start = tl_cur * TILE;
+      const uint32_t fi_cur = frame_of(t_cur);
+      const uint32_t tile_start = (t_cur - fi_cur * a.n_tiles) * TILE;
       px.running_t_prev = s_running_t[fi_cur];
       px.running_t = s_running_t[fi_cur + 1u];
       px.display = fi_cur == 0u ? a.px.display : (a.px.display ? 1u : 0u); /* only the launch's first frame can be a forced one */
@@ -614,25 +583,16 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         PxHeader h{__uint_as_float(hraw.x), hraw.y};
         bool deferred = false; /* kDeep: the walk below level 1 is still to be done */
         const uint32_t sample = samples[r * 32u + lane];
-#if ADDER_PAIR_STORE
-        uint32_t pend_k = 0;
-        OffRec pend_q{0u, 0u, 0.0f, 0u, 0u, 0u};
-#endif
         if constexpr (kOff) if (i < a.P) {
           OffNodes<kMulti> mem{a.nodes + 2ull * i, a.pair_stride, 0u, 0u};
           EventPark<S> park{slot_t + q, slot_d + q, arena + (unsigned long long)b * a.arena_slots * TILE + q, TILE, a.arena_slots, 0u, 0u};
           Node n0{__uint_as_float(n0raw.x), __uint_as_float(n0raw.y), __uint_as_float(n0raw.z), n0raw.w};
-          OffMeta meta{n1raw.x, n1raw.y, n1raw.z, n1raw.w};
+          OffTop top{n1raw.x, n1raw.y, __uint_as_float(n1raw.z), n1raw.w};
           uint8_t disp;
-#if ADDER_PAIR_STORE
-          const bool show = px_offset<kPlain, true>(px, sample, h, n0, meta, mem, park, errbits, &disp, &pend_k, &pend_q);
-          if (kCount && pend_k) mem.n_stores++;
-#else
-          const bool show = px_offset<kPlain>(px, sample, h, n0, meta, mem, park, errbits, &disp);
-#endif
+          const bool show = px_offset<kPlain>(px, sample, h, n0, top, mem, park, errbits, &disp);
           a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
           st_state256(a.nodes + 2ull * i, make_uint4(__float_as_uint(n0.integ), __float_as_uint(n0.dt), __float_as_uint(n0.best_dt), n0.w),
-                      make_uint4(meta.tmin, meta.od, meta.pmin, meta.info));
+                      make_uint4(top.a, top.b, __float_as_uint(top.best_dt), top.pmin));
           if (show) a.running[i] = disp;
           if (park.overflow) errbits |= ADDER_DEVERR_DEPTH;
           nev = park.n;
@@ -644,24 +604,6 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             c_len_out += HDR_LENGTH(h.y);
           }
         }
-#if ADDER_PAIR_STORE
-        if constexpr (kOff) {
-          /* round p: the records of the lanes with (lane & 1) == p; lane pair (2j, 2j+1) stores the two halves of one record */
-          const unsigned long long my_rec = (unsigned long long)reinterpret_cast<uintptr_t>(a.nodes + 2ull * i + (unsigned long long)pend_k * a.pair_stride);
-          const bool hi = (lane & 1u) != 0u;
-#pragma unroll
-          for (uint32_t p = 0; p < 2u; p++) {
-            const uint32_t src = (lane & ~1u) | p;
-            const uint32_t k_s = __shfl_sync(kFull, pend_k, src);
-            const unsigned long long addr = __shfl_sync(kFull, my_rec, src);
-            const uint32_t w0 = __shfl_sync(kFull, pend_q.oi, src), w1 = __shfl_sync(kFull, pend_q.od, src);
-            const uint32_t w2 = __shfl_sync(kFull, __float_as_uint(pend_q.best_dt), src), w3 = __shfl_sync(kFull, pend_q.w, src);
-            const uint32_t w4 = __shfl_sync(kFull, pend_q.pmin, src), w5 = __shfl_sync(kFull, pend_q.pk, src);
-            const uint4 v4 = hi ? make_uint4(w4, w5, 0u, 0u) : make_uint4(w0, w1, w2, w3);
-            if (k_s) reinterpret_cast<uint4*>(addr)[hi ? 1 : 0] = v4;
-          }
-        }
-#endif
         if constexpr (!kOff) if (i < a.P) {
           GlobalNodes<kMulti> mem{a.nodes + 2ull * i, a.pair_stride, 1u, 0u};
           EventPark<S> park{slot_t + q, slot_d + q, arena + (unsigned long long)b * a.arena_slots * TILE + q, TILE, a.arena_slots, 0u, 0u};
@@ -747,19 +689,18 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
 #if ADDER_ROW_PF
         if constexpr (kOff) {
           /* Which level records will the next row's pixels read?  A pixel that changed pops its stored levels; an unchanged
-           * one reads a record only when the level that fires is not the one its meta word caches (px_offset.cuh).  Both
-           * follow from what fetch_px brought for that row a row ago.  Hints only. */
+           * one reads a record only when a level above its top fires (px_offset.cuh).  Both follow from what fetch_px brought
+           * for that row a row ago.  Hints only. */
           if (r + 1u < my_rows) {
             const uint32_t y1 = h_next.y, len1 = HDR_LENGTH(y1);
-            if (len1 > 2u && !HDR_POPPED(y1)) {
+            if (len1 > 3u && !HDR_POPPED(y1)) {
               const uint4* const rec0 = a.nodes + 2ull * (tile_start + 32u * row_of(r + 1u) + lane);
               const uint32_t v1 = samples[(r + 1u) * 32u + lane], base1 = HDR_BASE(y1), cth1 = HDR_CTHRESH(y1);
               if (v1 + cth1 < base1 || v1 > base1 + cth1) {
 #pragma unroll 1
-                for (uint32_t k = 1; k + 1u < len1; k++) prefetch_state(rec0 + (unsigned long long)k * a.pair_stride);
-              } else {
-                const uint32_t x1 = __float2uint_rz(__uint_as_float(n0_next.x)) + v1;
-                if (x1 >= n1_next.x && (!(n1_next.w >> 31) || n1_next.z <= x1)) prefetch_state(rec0 + (unsigned long long)(n1_next.w & 0xFFu) * a.pair_stride);
+                for (uint32_t k = 1; k + 2u < len1; k++) prefetch_state(rec0 + (unsigned long long)k * a.pair_stride);
+              } else if (__float2uint_rz(__uint_as_float(n0_next.x)) + v1 >= n1_next.w) {
+                prefetch_state(rec0 + (unsigned long long)(n1_next.y >> 24) * a.pair_stride);
               }
             }
           }
@@ -844,8 +785,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           if (lane == 0) {
             /* tile 0 knows its prefix (0) at once; the others publish their aggregate now and their
              * inclusive prefix after their look-back, one iteration later */
-            uint32_t fi, tl;
-            tile_of(t_cur, fi, tl);
+            const uint32_t fi = frame_of(t_cur), tl = t_cur - fi * a.n_tiles;
             const unsigned long long tag = (unsigned long long)(a.epoch + fi) << 2;
             st_status(status_row(fi) + tl, ((tag | (tl == 0u ? kFlagPrefix : kFlagAggregate)) << 32) | tot, kMulti && n_frames > 1u);
             s_tot[b] = tot;
@@ -854,8 +794,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         }
         if (lane == 0) s_ticket[n & 1u] = t_next2; /* slot (n+2) & 1 */
       } else if (t_m1 < n_total) {
-        uint32_t fi, tl;
-        tile_of(t_m1, fi, tl);
+        const uint32_t fi = frame_of(t_m1), tl = t_m1 - fi * a.n_tiles;
         unsigned long long* const row = status_row(fi);
         const uint32_t excl = tl != 0u ? look_back(row, a.epoch + fi, tl, lane) : 0u;
         if (lane == 0) {
@@ -902,9 +841,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
       { /* the whole next tile's headers and first records towards L2 now (a tile's headers are TILE / 16 lines of 128 bytes,
          * its first records TILE / 4): the row loop's loads then find them there instead of in DRAM a row ahead.  Harmless
          * before the previous frame's tile has stored them: L2 is where those stores land. */
-        uint32_t fi_n, tl_n;
-        tile_of(t_next, fi_n, tl_n);
-        const uint32_t i0 = tl_n * TILE;
+        const uint32_t i0 = (t_next - frame_of(t_next) * a.n_tiles) * TILE;
 #pragma unroll 1
         for (uint32_t j = tid; j < TILE / 4u; j += kThreads) {
           const uint32_t i = i0 + 4u * j;
@@ -915,9 +852,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
         }
       }
 #else
-      uint32_t fi_n, tl_n;
-      tile_of(t_next, fi_n, tl_n);
-      const uint32_t i = tl_n * TILE + 32u * row_of(0u) + lane;
+      const uint32_t i = (t_next - frame_of(t_next) * a.n_tiles) * TILE + 32u * row_of(0u) + lane;
       if (my_rows && i < a.P) { /* towards L2 now, into registers after the write-out */
         if ((lane & 15u) == 0u) prefetch_l2(a.hdr + i);
         if ((lane & 3u) == 0u) prefetch_l2(a.nodes + 2ull * i); /* 128-byte lines: four 32-byte records each */
@@ -929,9 +864,8 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
     if (t_m2 < n_total) {
       const uint32_t pb = b == 2u ? 0u : b + 1u; /* (n-2) % 3 */
       const uint32_t prefix = s_prefix[n & 1u];  /* slot (n-2) & 1 */
-      uint32_t pfi, ptl;
-      tile_of(t_m2, pfi, ptl);
-      const uint32_t pstart = ptl * TILE;
+      const uint32_t pfi = frame_of(t_m2);
+      const uint32_t pstart = (t_m2 - pfi * a.n_tiles) * TILE;
       uint32_t* const ev_out = a.ev_words + (unsigned long long)pfi * a.ev_cap * 3ull;
       uint32_t* const chunk_out = a.chunk_off ? a.chunk_off + (unsigned long long)pfi * (a.n_chunks + 1u) : nullptr;
       const uint32_t* const pslot_t = s_slot_t + pb * (S * TILE);
@@ -1075,10 +1009,17 @@ __global__ void offset_to_eager_kernel(const uint2* hdr, uint4* nodes, uint32_t 
   uint4* const p = nodes + 2ull * i;
   const uint4 root = p[0];
   const uint32_t x = __float2uint_rz(__uint_as_float(root.x)), dt = __float2uint_rz(__uint_as_float(root.y));
+  const uint4 topw = p[1];
   auto level = [&](uint32_t k) -> uint4 {
     if (k == 0u) return root;
     if (k + 1u >= len) return make_uint4(0u, 0u, 0u, 0u); /* the implicit fresh tail, and everything beyond the stack */
-    uint4 r = p[(unsigned long long)k * stride];
+    uint4 r;
+    if (!frozen && k + 2u == len) { /* the top level lives in record 0 */
+      const OffRec q = top_unpack(OffTop{topw.x, topw.y, __uint_as_float(topw.z), topw.w});
+      r = make_uint4(q.oi, q.od, __float_as_uint(q.best_dt), q.w);
+    } else {
+      r = p[(unsigned long long)k * stride];
+    }
     if (!frozen) {
       r.x = __float_as_uint(__uint2float_rn(x - r.x));
       r.y = __float_as_uint(__uint2float_rn(dt - r.y));

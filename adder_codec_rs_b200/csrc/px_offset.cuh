@@ -15,14 +15,20 @@
  * and the offsets (oi_k, od_k) are constants of the level.  Level k fires in the frame in which the root's new
  * integration X reaches  thr_k = oi_k + 2^d_k  (integrate_main's test `integration + intensity >= D_SHIFT[d]`,
  * :423, on exact integers).  The shallowest such level is what the reference's walk finds (:344-366): it gets its best
- * event and a fresh child, everything deeper is dropped.  With
+ * event and a fresh child, everything deeper is dropped.  Every level record carries
  *
- *     meta  = (tmin, kmin)    the smallest threshold among the pixel's stored levels and the shallowest level that has it
- *     pmin_k, pk_k            the same over the levels ABOVE level k, kept in level k's record
+ *     pmin_k, pk_k      the smallest threshold among the levels ABOVE level k and the shallowest level that has it,
  *
- * a frame of an unchanged pixel touches the root and ONE level record, whatever the depth: if X < tmin no stored level
- * fires, so the walk reaches the tail, which is always a fresh node (see below) and always fires on its first
- * integration; otherwise start at kmin and hop to pk while pmin <= X — the hop ends at the shallowest firing level.
+ * so the shallowest firing level is found from the deepest stored level (the TOP, level length-2) by hopping to pk while
+ * pmin <= X, without looking at the levels that do not fire.
+ *
+ * The top lives in the second half of the pixel's record 0, next to the root, packed into 16 bytes (a fired level's d
+ * determines its best_event.d, so `w` need not be stored).  The stack of a pixel that does not change behaves like a
+ * binary counter: every frame exactly one level fires — the tail (a push: the stack grows by one), the top (in place),
+ * or a level above it (the stack is cut back to that level, which becomes the top).  On aged 8K stacks these are 39 %,
+ * 36 % and 19 % of the pixel-frames.  Only a push writes a level record (the previous top is spilled) and only a cut
+ * reads one; a lone 32-byte record store costs DRAM 64 bytes (the sector's partner is read first, profiles/r02r_*), so the
+ * first version of this form, which rewrote the firing level's record every frame, was bound by those stores.
  *
  * What makes this exact (bit-identical to the reference's f32 arithmetic):
  *  - a u8 source gives integer intensities, `time` is an integer number of ticks, and every integration / delta_t is a
@@ -50,8 +56,10 @@
  * ptxas 12.9).  The host simulation runs every shared case and the long runs of tests/test_px_offset_host.py through
  * this very function and checks that the flag stays clear.
  *
- * Layout (state_layout.h): record 0 of a pixel = root node (16 B, eager, as in the eager form) + meta (16 B);
- * record k >= 1 = level k: { oi, od, best_event.delta_t, w, pmin, pk, -, - } (32 B = one DRAM sector, one 256-bit access).
+ * Layout (state_layout.h): record 0 of a pixel = root node (16 B, eager, as in the eager form) + the top level (16 B:
+ * oi | d << 24, od | pk << 24, best_event.delta_t, pmin; meaningful when length >= 3 and the pixel is not frozen);
+ * record k >= 1 = level k: { oi, od, best_event.delta_t, w, pmin, pk, -, - } (32 B = one DRAM sector, one 256-bit access);
+ * the record of the top level itself is stale while the level is the top.
  */
 #pragma once
 #include "px_machine.cuh"
@@ -60,34 +68,41 @@ namespace adder {
 
 constexpr uint32_t kThrNever = 0xFFFFFFFFu;
 
-/* The meta half of record 0.  Besides (tmin, kmin) it caches what is needed to FIRE level kmin without reading its record:
- * its delta_t offset, its d (its integration offset is then tmin - 2^d), and its own (pmin, pk).  The level that fires is
- * written as a whole record afterwards, so the common frames of an unchanged pixel read no level record at all:
- *   - the tail fires (no stored level has reached its threshold): a new record is written;
- *   - level kmin fires from the cache: its record is rewritten.
- * A record is read only when the cache does not describe level kmin (valid = 0: it was left behind when kmin changed to a
- * shallower level, and is filled when that level actually fires), when a shallower level fires in the same frame (the
- * hop), when a changed pixel pops its stack, or in the one frame per delta_t_max in which the stack moves up a level. */
-struct OffMeta {
-  uint32_t tmin;  /* smallest threshold among the stored levels (kThrNever: none) */
-  uint32_t od;    /* cached: level kmin's delta_t offset */
-  uint32_t pmin;  /* cached: level kmin's pmin */
-  uint32_t info;  /* kmin | d << 8 | pk << 16 | valid << 31 */
-};
-ADDER_HD uint32_t meta_kmin(const OffMeta& m) { return m.info & 0xFFu; }
-ADDER_HD uint32_t meta_d(const OffMeta& m) { return (m.info >> 8) & 0xFFu; }
-ADDER_HD uint32_t meta_pk(const OffMeta& m) { return (m.info >> 16) & 0xFFu; }
-ADDER_HD bool meta_valid(const OffMeta& m) { return (m.info >> 31) != 0u; }
-/* the cache can stand for a level only if its integration offset follows from its threshold: d < 31 */
-ADDER_HD uint32_t meta_info(uint32_t k, uint32_t d, uint32_t pk) { return k | (d << 8) | (pk << 16) | (d < 31u ? 0x80000000u : 0u); }
-ADDER_HD void meta_clear(OffMeta& m) { m.tmin = kThrNever, m.od = 0u, m.pmin = kThrNever, m.info = 0u; }
-
 struct OffRec {
   uint32_t oi, od; /* offsets (or, frozen: the f32 bits of integration and delta_t) */
   float best_dt;
   uint32_t w;
   uint32_t pmin, pk;
 };
+
+/* the top level as it lies in record 0: a = oi | d << 24, b = od | pk << 24 */
+struct OffTop {
+  uint32_t a, b;
+  float best_dt;
+  uint32_t pmin;
+};
+/* `w` of a level that has fired: integrate_main leaves d = best_event.d + 1 (:449-461), or d = best_event.d = 128 for a
+ * zero-integration node (d = D_MAX = 127 would need an integration of 2^126) */
+ADDER_HD uint32_t w_of_d(uint32_t d) { return d >= 128u ? NODE_PACK(d, d, 1) : NODE_PACK(d, d - 1u, 1); }
+ADDER_HD OffRec top_unpack(const OffTop& t) {
+  OffRec q;
+  q.oi = t.a & 0xFFFFFFu;
+  q.od = t.b & 0xFFFFFFu;
+  q.best_dt = t.best_dt;
+  q.w = w_of_d(t.a >> 24);
+  q.pmin = t.pmin;
+  q.pk = t.b >> 24;
+  return q;
+}
+ADDER_HD OffTop top_pack(const OffRec& q, uint32_t& errbits) {
+  if (((q.oi | q.od) >> 24) || q.w != w_of_d(NODE_D(q.w))) errbits |= ADDER_DEVERR_INTERNAL; /* outside what the form admits */
+  OffTop t;
+  t.a = q.oi | (NODE_D(q.w) << 24);
+  t.b = q.od | (q.pk << 24);
+  t.best_dt = q.best_dt;
+  t.pmin = q.pmin;
+  return t;
+}
 
 /* the root integration at which a level with offset oi and decimation d (in w) fires */
 ADDER_HD uint32_t off_thr(uint32_t oi, uint32_t w) {
@@ -121,13 +136,11 @@ ADDER_HD Node off_node(const OffRec& q, uint32_t x, uint32_t dt) {
 
 /*
  * One pixel, one frame, offset form (PixelMultiMode::Collapse: offset_form_eligible).  n0 = the root (in: as loaded, out:
- * as to be stored), meta likewise; the caller stores header and record 0 afterwards.  Same contract as px_step otherwise.
+ * as to be stored), top likewise; the caller stores header and record 0 afterwards.  Same contract as px_step otherwise.
  */
-/* kDefer: the one level record a common frame writes is handed back (*st_k = its level, 0 = none; *st_q) instead of being
- * stored, so that the kernel can store the records of a row's pixels together once the warp has reconverged. */
-template <bool kPlain = false, bool kDefer = false, class Mem, class Sink>
-ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, OffMeta& meta, Mem& mem, Sink& sink, uint32_t& errbits,
-                        uint8_t* disp, uint32_t* st_k = nullptr, OffRec* st_q = nullptr) {
+template <bool kPlain = false, class Mem, class Sink>
+ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, OffTop& top, Mem& mem, Sink& sink, uint32_t& errbits,
+                        uint8_t* disp) {
   const float intensity = (float)v;
   const float time = a.time;
   float lf = h.lf;
@@ -152,16 +165,20 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
         errbits |= ADDER_DEVERR_INTERNAL; /* (see the header: only a root that has never integrated has nothing to give,
                                            * and such a root — put there by a Δt_max pop in the frame it fired — has no child) */
       }
-    } else if (len > 2u) { /* the stored levels; the tail is fresh and has nothing to give (:223-247) */
-      OffRec q = mem.load_rec(1u);
-      for (uint32_t k = 1;;) { /* record k+1 is requested before record k is worked on */
-        OffRec nxt = q;
-        if (k + 2u < len) nxt = mem.load_rec(k + 1u);
-        Node nk = off_node(q, x0, dt0);
-        pop_node<kPlain>(a, sink, lf, nk);
-        if (++k + 1u >= len) break;
-        q = nxt;
+    } else if (len > 2u) { /* the stored levels in order, the top last; the tail is fresh and has nothing to give (:223-247) */
+      if (len > 3u) {
+        OffRec q = mem.load_rec(1u);
+        for (uint32_t k = 1;;) { /* record k+1 is requested before record k is worked on */
+          OffRec nxt = q;
+          if (k + 3u < len) nxt = mem.load_rec(k + 1u);
+          Node nk = off_node(q, x0, dt0);
+          pop_node<kPlain>(a, sink, lf, nk);
+          if (++k + 2u >= len) break;
+          q = nxt;
+        }
       }
+      Node nk = off_node(top_unpack(top), x0, dt0);
+      pop_node<kPlain>(a, sink, lf, nk);
     }
     if (fresh_root) r.integ = 0.0f, r.dt = 0.0f, r.best_dt = 0.0f, r.w = 0u;
     len = 1;
@@ -184,7 +201,6 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
     emit_abs<kPlain>(a, sink, lf, NODE_BEST_D(r.w), r.best_dt);
     popped = 1;
     root_new = true;
-    meta_clear(meta);
     if (fired0 || len < 2u) { /* the root fired this very frame: it is replaced by a fresh node (:164-193 -> :195-199) */
       if (!fired0) errbits |= ADDER_DEVERR_INTERNAL; /* a root with a best event that did not fire has a child */
       r.integ = 0.0f, r.dt = 0.0f, r.best_dt = 0.0f;
@@ -192,19 +208,18 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
       new_len = 1;
     } else {
       /* the stack moves up a level (:201-204) while every level integrates this frame (:340-390) up to the first one
-       * that fires.  What is stored below the new root is never integrated again under Collapse: frozen values. */
+       * that fires.  What is stored below the new root is never integrated again under Collapse: frozen values, all of
+       * them in level records (a frozen pixel keeps no top in record 0). */
       const uint32_t last = len - 1u;
-      OffRec q{0u, 0u, 0.0f, 0u, 0u, 0u};
-      if (last > 1u) q = mem.load_rec(1u);
       for (uint32_t k = 1;; k++) {
-        OffRec nxt = q;
-        if (k + 1u < last) nxt = mem.load_rec(k + 1u);
         Node nk;
         if (k == last) { /* the fresh tail */
           nk.integ = 0.0f, nk.dt = 0.0f, nk.best_dt = 0.0f;
           nk.w = get_d_from_intensity(intensity);
+        } else if (k + 1u == last) {
+          nk = off_node(top_unpack(top), x_in, dt_in);
         } else {
-          nk = off_node(q, x_in, dt_in);
+          nk = off_node(mem.load_rec(k), x_in, dt_in);
         }
         const bool fired = integrate_main(nk, intensity, time);
         if (k == 1u) {
@@ -219,67 +234,64 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
           new_len = k + 1u; /* levels 0 .. k-1 and a fresh tail */
           break;
         }
-        q = nxt;
       }
     }
   } else if (fired0) { /* :344-355: a fresh child, deeper nodes dropped */
     if (a.depth > 1u) new_len = 2; else errbits |= ADDER_DEVERR_DEPTH;
-    meta_clear(meta);
     root_new = true;
   } else if (!popped && len > 1u) {
-    /* ---- the walk below the root (:340-390) in one step: the shallowest stored level whose threshold the root's
-     * integration has reached, else the fresh tail ------------------------------------------------------------------- */
+    /* ---- the walk below the root (:340-390) in one step: the shallowest level whose threshold the root's integration
+     * has reached, else the fresh tail ------------------------------------------------------------------------------- */
     const uint32_t x = f2u(r.integ), dt = f2u(r.dt);
     if ((x | dt) >> 24) errbits |= ADDER_DEVERR_INTERNAL; /* beyond what offset_form_eligible admits */
     uint32_t k;
     OffRec q;
     Node nk;
-    if (x >= meta.tmin) {
-      k = meta_kmin(meta);
-      if (meta_valid(meta) && meta.pmin > x) { /* level kmin fires, and everything about it is in the cache */
-        q.oi = meta.tmin - (1u << meta_d(meta));
-        q.od = meta.od;
-        q.best_dt = 0.0f; /* replaced by the firing */
-        q.w = meta_d(meta);
-        q.pmin = meta.pmin;
-        q.pk = meta_pk(meta);
-      } else {
+    bool from_tail = true;
+    if (len > 2u) {
+      const OffRec t = top_unpack(top);
+      const uint32_t thr_t = off_thr(t.oi, t.w);
+      if (t.pmin <= x) { /* a level above the top has reached its threshold: the walk stops at the shallowest (:344-366),
+                          * which becomes the top (everything below it is dropped, its own record goes stale) */
+        k = t.pk;
         q = mem.load_rec(k);
-        while (q.pmin <= x) { /* a shallower level has reached its threshold too: the walk stops there (:344-366) */
+        while (q.pmin <= x) {
           k = q.pk;
           q = mem.load_rec(k);
         }
+        from_tail = false;
+      } else if (thr_t <= x) { /* the top fires where it is */
+        k = len - 2u;
+        q = t;
+        from_tail = false;
+      } else { /* nothing stored fires: the tail does, and the top is spilled to its record */
+        k = len - 1u;
+        mem.store_rec(len - 2u, t);
+        if (t.pmin <= thr_t) { /* ties go to the shallower level, like the walk */
+          q.pmin = t.pmin;
+          q.pk = t.pk;
+        } else {
+          q.pmin = thr_t;
+          q.pk = len - 2u;
+        }
       }
-      nk = off_node(q, x_in, dt_in);
-    } else { /* the tail: PixelNode::new with its d from this intensity (:332-335) */
-      k = len - 1u;
-      q.pmin = meta.tmin;
-      q.pk = meta_kmin(meta);
+    } else { /* root and tail only */
+      k = 1u;
+      q.pmin = kThrNever;
+      q.pk = 0u;
+    }
+    if (from_tail) { /* PixelNode::new with its d from this intensity (:332-335) */
       nk.integ = 0.0f, nk.dt = 0.0f, nk.best_dt = 0.0f;
       nk.w = get_d_from_intensity(intensity);
+    } else {
+      nk = off_node(q, x_in, dt_in);
     }
     if (!integrate_main(nk, intensity, time)) errbits |= ADDER_DEVERR_INTERNAL;
     q.oi = x - f2u(nk.integ);
     q.od = dt - f2u(nk.dt);
     q.best_dt = nk.best_dt;
     q.w = nk.w;
-    if (kDefer) {
-      *st_k = k;
-      *st_q = q;
-    } else {
-      mem.store_rec(k, q);
-    }
-    const uint32_t thr = off_thr(q.oi, q.w);
-    if (thr < q.pmin) { /* this level is the next to fire (ties go to the shallower level, like the walk) */
-      meta.tmin = thr;
-      meta.od = q.od;
-      meta.pmin = q.pmin;
-      meta.info = meta_info(k, NODE_D(q.w), q.pk);
-    } else if (x >= meta.tmin) { /* a stored level fired and a level above it holds the minimum now; the cache is filled
-                                  * when that level fires (the tail leaves tmin / kmin and the cache as they are) */
-      meta.tmin = q.pmin;
-      meta.info = q.pk;
-    }
+    top = top_pack(q, errbits);
     if (k + 1u >= a.depth) errbits |= ADDER_DEVERR_DEPTH;
     new_len = k + 2u > a.depth ? a.depth : k + 2u;
   }

@@ -68,7 +68,7 @@ struct sim_video {
   std::vector<uint8_t> running;
   /* offset form (g_entry == 4): root nodes stay in nodes[0 * P + i] */
   std::vector<adder::OffRec> recs;
-  std::vector<adder::OffMeta> meta;
+  std::vector<adder::OffTop> meta; /* the top level, second half of record 0 */
   int form = -1; /* -1 undecided, 0 eager, 1 offset */
   uint64_t rec_loads = 0, rec_stores = 0, px_frames = 0;
   std::vector<adder_event_t> events;
@@ -133,7 +133,7 @@ size_t sim_integrate(sim_video* v, const uint8_t* frame, float time, uint32_t re
       v->form = ok ? 1 : 0;
       if (ok) {
         v->recs.assign(v->P * v->depth, adder::OffRec{0, 0, 0.0f, 0, 0, 0});
-        v->meta.assign(v->P, adder::OffMeta{0, 0, 0, 0});
+        v->meta.assign(v->P, adder::OffTop{0, 0, 0.0f, 0});
       }
     } else if (v->form == 1 && !ok) {
       v->err |= 0x80000000u; /* the test cases never change eligibility mid-stream (the library converts the state) */
@@ -238,9 +238,10 @@ void sim_node(const sim_video* v, size_t i, uint32_t k, float* integ, float* dt,
   if (v->form == 1 && k > 0) { /* offset form -> the reference's node (what adder_b200_video_read_px does in the library) */
     const uint32_t len = HDR_LENGTH(v->hdr[i].y);
     if (k + 1u >= len) { *integ = 0.0f; *dt = 0.0f; *best_dt = 0.0f; *w = 0u; return; }
-    const adder::OffRec& r = v->recs[(size_t)k * v->P + i];
+    const bool frozen = HDR_POPPED(v->hdr[i].y) != 0u;
+    const adder::OffRec r = (!frozen && k + 2u == len) ? adder::top_unpack(v->meta[i]) : v->recs[(size_t)k * v->P + i];
     const adder::Node& root = v->nodes[i];
-    if (HDR_POPPED(v->hdr[i].y)) { *integ = adder::bits_f(r.oi); *dt = adder::bits_f(r.od); }
+    if (frozen) { *integ = adder::bits_f(r.oi); *dt = adder::bits_f(r.od); }
     else { *integ = adder::u2f(adder::f2u(root.integ) - r.oi); *dt = adder::u2f(adder::f2u(root.dt) - r.od); }
     *best_dt = r.best_dt; *w = r.w;
     return;
