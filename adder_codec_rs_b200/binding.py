@@ -68,7 +68,7 @@ class CrfParameters(C.Structure):
 class VideoInfo(C.Structure):
     _fields_ = [("width", C.c_uint16), ("height", C.c_uint16), ("channels", C.c_uint8), ("pixel_tree_mode", C.c_uint8),
                 ("pixel_multi_mode", C.c_uint8), ("time_mode", C.c_uint8), ("view_mode", C.c_uint8),
-                ("reserved", C.c_uint8 * 3), ("chunk_rows", C.c_uint32), ("n_chunks", C.c_uint32),
+                ("state_form", C.c_uint8), ("reserved", C.c_uint8 * 2), ("chunk_rows", C.c_uint32), ("n_chunks", C.c_uint32),
                 ("in_interval_count", C.c_uint32), ("tps", C.c_uint32), ("ref_time", C.c_uint32),
                 ("delta_t_max", C.c_uint32), ("crf", CrfParameters), ("max_depth", C.c_uint32), ("device", C.c_uint32),
                 ("state_bytes", C.c_uint64), ("events_capacity", C.c_uint64)]
@@ -413,6 +413,11 @@ class Video:
         out = VideoInfo()
         _check(self.L.adder_b200_video_get_info(self.v, C.byref(out)))
         return out
+
+    @property
+    def state_form(self):
+        """0: every level of a node stack holds its own values; 1: offset form (csrc/px_offset.cuh)."""
+        return self.info().state_form
 
     @property
     def in_interval_count(self):

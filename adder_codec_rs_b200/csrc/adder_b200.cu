@@ -1017,6 +1017,7 @@ int adder_b200_video_get_info(const adder_b200_video* v, adder_b200_video_info_t
   out->pixel_multi_mode = (uint8_t)v->multi_mode;
   out->time_mode = (uint8_t)v->time_mode;
   out->view_mode = (uint8_t)v->view_mode;
+  out->state_form = (uint8_t)v->form;
   out->chunk_rows = v->chunk_rows;
   out->n_chunks = v->n_chunks;
   out->in_interval_count = v->in_interval_count;

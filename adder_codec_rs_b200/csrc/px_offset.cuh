@@ -166,16 +166,9 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
                                            * and such a root — put there by a Δt_max pop in the frame it fired — has no child) */
       }
     } else if (len > 2u) { /* the stored levels in order, the top last; the tail is fresh and has nothing to give (:223-247) */
-      if (len > 3u) {
-        OffRec q = mem.load_rec(1u);
-        for (uint32_t k = 1;;) { /* record k+1 is requested before record k is worked on */
-          OffRec nxt = q;
-          if (k + 3u < len) nxt = mem.load_rec(k + 1u);
-          Node nk = off_node(q, x0, dt0);
-          pop_node<kPlain>(a, sink, lf, nk);
-          if (++k + 2u >= len) break;
-          q = nxt;
-        }
+      for (uint32_t k = 1; k + 2u < len; k++) {
+        Node nk = off_node(mem.load_rec(k), x0, dt0);
+        pop_node<kPlain>(a, sink, lf, nk);
       }
       Node nk = off_node(top_unpack(top), x0, dt0);
       pop_node<kPlain>(a, sink, lf, nk);
@@ -189,7 +182,6 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
 
   /* ---- integrate (:317-413): the root ------------------------------------------------------------------------------ */
   if (len == 1u && r.dt == 0.0f && r.integ == 0.0f) r.w = (r.w & ~0xFFu) | get_d_from_intensity(intensity); /* :332-335 */
-  const uint32_t x_in = f2u(r.integ), dt_in = f2u(r.dt);
   const bool fired0 = integrate_main(r, intensity, time);
   const uint32_t dtm_reached = r.dt >= a.dtm_f ? 1u : 0u; /* :394 */
   if (NODE_D(r.w) == ADDER_D_MAX) errbits |= ADDER_DEVERR_INTERNAL; /* needs an integration of 2^126 */
@@ -211,6 +203,7 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
        * that fires.  What is stored below the new root is never integrated again under Collapse: frozen values, all of
        * them in level records (a frozen pixel keeps no top in record 0). */
       const uint32_t last = len - 1u;
+      const uint32_t x_in = f2u(r.integ) - v, dt_in = f2u(r.dt) - f2u(time); /* the root did not fire: it accumulated (:468-470) */
       for (uint32_t k = 1;; k++) {
         Node nk;
         if (k == last) { /* the fresh tail */
@@ -243,6 +236,7 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
     /* ---- the walk below the root (:340-390) in one step: the shallowest level whose threshold the root's integration
      * has reached, else the fresh tail ------------------------------------------------------------------------------- */
     const uint32_t x = f2u(r.integ), dt = f2u(r.dt);
+    const uint32_t x_in = x - v, dt_in = dt - f2u(time); /* the root did not fire: it accumulated (:468-470) */
     if ((x | dt) >> 24) errbits |= ADDER_DEVERR_INTERNAL; /* beyond what offset_form_eligible admits */
     uint32_t k;
     OffRec q;

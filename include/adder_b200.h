@@ -156,7 +156,12 @@ typedef struct adder_b200_video_info {
   uint16_t width, height;
   uint8_t channels;
   uint8_t pixel_tree_mode, pixel_multi_mode, time_mode, view_mode;
-  uint8_t reserved[3];
+  uint8_t state_form;        /* how the node stacks are held at the moment: 0 = one record per two levels, every level with its own
+                              * integration / delta_t (the reference's PixelNode); 1 = offset form (levels below the root hold
+                              * offsets against the root and are touched only when they fire; chosen by the library when
+                              * PixelMultiMode::Collapse, an integral time_spanned and delta_t_max < 2^23 make it exact).
+                              * Events, display bytes and adder_b200_video_read_px are the same in both. */
+  uint8_t reserved[2];
   uint32_t chunk_rows, n_chunks;
   uint32_t in_interval_count, tps, ref_time, delta_t_max;
   adder_crf_parameters_t crf;

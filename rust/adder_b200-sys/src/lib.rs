@@ -68,7 +68,9 @@ pub struct adder_b200_video_info_t {
     pub pixel_multi_mode: u8,
     pub time_mode: u8,
     pub view_mode: u8,
-    pub reserved: [u8; 3],
+    /// 0 = every level holds its own integration / delta_t, 1 = offset form (see include/adder_b200.h)
+    pub state_form: u8,
+    pub reserved: [u8; 2],
     pub chunk_rows: u32,
     pub n_chunks: u32,
     pub in_interval_count: u32,
