@@ -1515,8 +1515,8 @@ int adder_b200_video_read_px(adder_b200_video* v, size_t index, adder_b200_px_st
           uint4 t;
           CU(cudaMemcpy(&t, v->d_nodes + 2ull * index + 1ull, sizeof(t), cudaMemcpyDeviceToHost));
           adder::OffTop top;
-          top.a = t.x, top.b = t.y, top.pmin = t.w;
-          memcpy(&top.best_dt, &t.z, 4);
+          top.a = t.x, top.b = t.z, top.pmin = t.w; /* in memory: a, best_dt, b, pmin */
+          memcpy(&top.best_dt, &t.y, 4);
           const adder::OffRec q = adder::top_unpack(top);
           n.x = q.oi, n.y = q.od, n.w = q.w;
           memcpy(&n.z, &q.best_dt, 4);

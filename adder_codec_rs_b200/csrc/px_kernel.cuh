@@ -50,11 +50,6 @@
                          * row loop's own row-ahead loads already hide that latency.  A separate pass over the next tile that asked
                          * for the level records its pixels would read cost 15-30 % (same file) and was removed. */
 #endif
-#ifndef ADDER_ROW_PF
-#define ADDER_ROW_PF 0 /* 1: offset form, at the end of a row the level records the NEXT row's pixels will read are requested towards
-                        * L2 (by then that row's header and first record have arrived): within +-1.5 % on deep stacks, -3 % on
-                        * noise (profiles/r02r_ab_rowpf.txt, r02r_ab_top.txt): off */
-#endif
 #ifndef ADDER_DEEP_PF
 #define ADDER_DEEP_PF 2 /* px_step entry: pull levels 2..length-1 towards L1 (1) or L2 (2); 0 = off */
 #endif
@@ -205,7 +200,12 @@ struct GlobalNodes {
 };
 
 /* The level records of a pixel in OFFSET FORM (px_offset.cuh): record k >= 1 = level k, 32 bytes, one 256-bit access; record 0
- * (root + meta) is loaded and stored by the kernel's row loop.  Counts are in records. */
+ * (root + top level) is loaded and stored by the kernel's row loop.  Counts are in records.
+ * What these scattered accesses cost, measured on aged 8K stacks (profiles/r02r_*): a record LOAD brings a whole 128-byte
+ * line from DRAM (~113 bytes of reads per load), a record store ~44 bytes of traffic; asking for the records a row or two
+ * ahead (prefetch.global.L2 from the row loop, three variants) never paid for its instructions, 64-byte record slots
+ * written whole changed nothing but the bytes written, and storing a record as two 128-bit halves from a lane pair
+ * neither.  What did pay was needing fewer of them: the top level in record 0 (px_offset.cuh). */
 template <bool kCoherent>
 struct OffNodes {
   uint4* p; /* the pixel's record 0 */
@@ -358,14 +358,6 @@ constexpr uint32_t kMaxLaunchFrames = 512; /* frames one launch may span (FrameA
 
 /* pull the line holding *p towards L2 (no register, no scoreboard) */
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-__device__ __forceinline__ void prefetch_state(const void* p) {
-#if ADDER_ROW_PF == 2
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
@@ -587,12 +579,12 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           OffNodes<kMulti> mem{a.nodes + 2ull * i, a.pair_stride, 0u, 0u};
           EventPark<S> park{slot_t + q, slot_d + q, arena + (unsigned long long)b * a.arena_slots * TILE + q, TILE, a.arena_slots, 0u, 0u};
           Node n0{__uint_as_float(n0raw.x), __uint_as_float(n0raw.y), __uint_as_float(n0raw.z), n0raw.w};
-          OffTop top{n1raw.x, n1raw.y, __uint_as_float(n1raw.z), n1raw.w};
+          OffTop top{n1raw.x, n1raw.z, __uint_as_float(n1raw.y), n1raw.w}; /* in memory: a, best_dt, b, pmin */
           uint8_t disp;
           const bool show = px_offset<kPlain>(px, sample, h, n0, top, mem, park, errbits, &disp);
           a.hdr[i] = make_uint2(__float_as_uint(h.lf), h.y);
           st_state256(a.nodes + 2ull * i, make_uint4(__float_as_uint(n0.integ), __float_as_uint(n0.dt), __float_as_uint(n0.best_dt), n0.w),
-                      make_uint4(top.a, top.b, __float_as_uint(top.best_dt), top.pmin));
+                      make_uint4(top.a, __float_as_uint(top.best_dt), top.b, top.pmin));
           if (show) a.running[i] = disp;
           if (park.overflow) errbits |= ADDER_DEVERR_DEPTH;
           nev = park.n;
@@ -686,26 +678,6 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
             if (kCount) c_len_out += HDR_LENGTH(h.y);
           }
         }
-#if ADDER_ROW_PF
-        if constexpr (kOff) {
-          /* Which level records will the next row's pixels read?  A pixel that changed pops its stored levels; an unchanged
-           * one reads a record only when a level above its top fires (px_offset.cuh).  Both follow from what fetch_px brought
-           * for that row a row ago.  Hints only. */
-          if (r + 1u < my_rows) {
-            const uint32_t y1 = h_next.y, len1 = HDR_LENGTH(y1);
-            if (len1 > 3u && !HDR_POPPED(y1)) {
-              const uint4* const rec0 = a.nodes + 2ull * (tile_start + 32u * row_of(r + 1u) + lane);
-              const uint32_t v1 = samples[(r + 1u) * 32u + lane], base1 = HDR_BASE(y1), cth1 = HDR_CTHRESH(y1);
-              if (v1 + cth1 < base1 || v1 > base1 + cth1) {
-#pragma unroll 1
-                for (uint32_t k = 1; k + 2u < len1; k++) prefetch_state(rec0 + (unsigned long long)k * a.pair_stride);
-              } else if (__float2uint_rz(__uint_as_float(n0_next.x)) + v1 >= n1_next.w) {
-                prefetch_state(rec0 + (unsigned long long)(n1_next.y >> 24) * a.pair_stride);
-              }
-            }
-          }
-        }
-#endif
         /* place of this pixel's records inside its row's run: two ballots cover 0..2 events per
          * pixel, the shuffle scan is only taken when some pixel of the row emitted more */
         const uint32_t le = 0xFFFFFFFFu >> (31u - lane);
@@ -1015,7 +987,7 @@ __global__ void offset_to_eager_kernel(const uint2* hdr, uint4* nodes, uint32_t 
     if (k + 1u >= len) return make_uint4(0u, 0u, 0u, 0u); /* the implicit fresh tail, and everything beyond the stack */
     uint4 r;
     if (!frozen && k + 2u == len) { /* the top level lives in record 0 */
-      const OffRec q = top_unpack(OffTop{topw.x, topw.y, __uint_as_float(topw.z), topw.w});
+      const OffRec q = top_unpack(OffTop{topw.x, topw.z, __uint_as_float(topw.y), topw.w});
       r = make_uint4(q.oi, q.od, __float_as_uint(q.best_dt), q.w);
     } else {
       r = p[(unsigned long long)k * stride];

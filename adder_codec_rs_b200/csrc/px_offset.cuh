@@ -27,8 +27,9 @@
  * binary counter: every frame exactly one level fires — the tail (a push: the stack grows by one), the top (in place),
  * or a level above it (the stack is cut back to that level, which becomes the top).  On aged 8K stacks these are 39 %,
  * 36 % and 19 % of the pixel-frames.  Only a push writes a level record (the previous top is spilled) and only a cut
- * reads one; a lone 32-byte record store costs DRAM 64 bytes (the sector's partner is read first, profiles/r02r_*), so the
- * first version of this form, which rewrote the firing level's record every frame, was bound by those stores.
+ * reads one.  These scattered 32-byte accesses are what DRAM serves worst (a record load brings a whole 128-byte line,
+ * profiles/r02r_*): the first version of this form, which rewrote the firing level's record every frame, was bound by
+ * them and no faster than the eager form although it executed half the instructions.
  *
  * What makes this exact (bit-identical to the reference's f32 arithmetic):
  *  - a u8 source gives integer intensities, `time` is an integer number of ticks, and every integration / delta_t is a

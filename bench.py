@@ -626,7 +626,9 @@ def run_ours(args):
         b_survey, L_mean, E_mean = survey_formula(cnt, pxf)
         n_launch = (nf + wl.batch - 1) // wl.batch
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "integrate_frame_kernel<8,false,true>",
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "integrate_frame_kernel<8,false,true,false,true,true> (offset-form node stacks)" if wl.v.state_form == 1 else "integrate_frame_kernel<8,false,true,false,true>",
+                "state_form": "offset" if wl.v.state_form == 1 else "eager",
                 "frames_per_launch": wl.batch, "launches_per_step": n_launch,
                 "algorithmic_bytes_per_launch": alg_bytes_step / n_launch, "algorithmic_bytes_per_px_frame": alg_bytes_step / pxf,
                 "node_loads_per_px_frame": cnt["node_loads"] / pxf, "node_stores_per_px_frame": cnt["node_stores"] / pxf,
