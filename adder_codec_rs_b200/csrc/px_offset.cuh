@@ -181,12 +181,75 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
     root_new = true;
   }
 
-  /* ---- integrate (:317-413): the root ------------------------------------------------------------------------------ */
+  /* ---- integrate (:317-413) -------------------------------------------------------------------------------------------
+   * Exactly one node of a pixel fires in a frame (the root, or the shallowest level below it that reaches its threshold —
+   * the tail if no other does), or none (a root that integrates alone).  The firing arm of integrate_main, with its
+   * division, is therefore written ONCE, after the node has been chosen: the pixels of a warp's row choose differently,
+   * and a warp runs every arm one of its lanes takes. */
   if (len == 1u && r.dt == 0.0f && r.integ == 0.0f) r.w = (r.w & ~0xFFu) | get_d_from_intensity(intensity); /* :332-335 */
-  const bool fired0 = integrate_main(r, intensity, time);
-  const uint32_t dtm_reached = r.dt >= a.dtm_f ? 1u : 0u; /* :394 */
-  if (NODE_D(r.w) == ADDER_D_MAX) errbits |= ADDER_DEVERR_INTERNAL; /* needs an integration of 2^126 */
+  const float sum0 = rn_add(r.integ, intensity);
+  const bool fired0 = sum0 >= d_shift_f32(NODE_D(r.w)); /* :423 */
   uint32_t new_len = len;
+  uint32_t x = 0, dt = 0;          /* the root's integration / delta_t after this frame, when a level below it fires */
+  uint32_t k = 0;                  /* that level */
+  OffRec q{0u, 0u, 0.0f, 0u, kThrNever, 0u};
+  Node fn = r;                     /* the node that fires, as it is before this frame */
+  bool level_fires = false;
+  if (!fired0) {
+    r.integ = sum0; /* :468-470 */
+    r.dt = rn_add(r.dt, time);
+    if (!popped && len > 1u && !(r.dt >= a.dtm_f)) {
+      /* the walk below the root (:340-390) in one step: the shallowest level whose threshold the root's integration has
+       * reached, else the fresh tail */
+      x = f2u(r.integ), dt = f2u(r.dt);
+      if ((x | dt) >> 24) errbits |= ADDER_DEVERR_INTERNAL; /* beyond what offset_form_eligible admits */
+      bool from_tail = true;
+      if (len > 2u) {
+        const OffRec t = top_unpack(top);
+        const uint32_t thr_t = off_thr(t.oi, t.w);
+        if (t.pmin <= x) { /* a level above the top has reached its threshold: the walk stops at the shallowest (:344-366),
+                            * which becomes the top (everything below it is dropped, its own record goes stale) */
+          k = t.pk;
+          q = mem.load_rec(k);
+          while (q.pmin <= x) {
+            k = q.pk;
+            q = mem.load_rec(k);
+          }
+          from_tail = false;
+        } else if (thr_t <= x) { /* the top fires where it is */
+          k = len - 2u;
+          q = t;
+          from_tail = false;
+        } else { /* nothing stored fires: the tail does, and the top is spilled to its record */
+          k = len - 1u;
+          mem.store_rec(len - 2u, t);
+          if (t.pmin <= thr_t) { /* ties go to the shallower level, like the walk */
+            q.pmin = t.pmin;
+            q.pk = t.pk;
+          } else {
+            q.pmin = thr_t;
+            q.pk = len - 2u;
+          }
+        }
+      } else { /* root and tail only */
+        k = 1u;
+      }
+      if (from_tail) { /* PixelNode::new with its d from this intensity (:332-335) */
+        fn.integ = 0.0f, fn.dt = 0.0f, fn.best_dt = 0.0f;
+        fn.w = get_d_from_intensity(intensity);
+      } else { /* the root did not fire: before this frame it held x - v and dt - time */
+        fn = off_node(q, x - v, dt - f2u(time));
+      }
+      if (!(rn_add(fn.integ, intensity) >= d_shift_f32(NODE_D(fn.w)))) errbits |= ADDER_DEVERR_INTERNAL;
+      level_fires = true;
+    }
+  }
+  if (fired0 || level_fires) integrate_fire(fn, intensity, time); /* :424-466 */
+  if (fired0) {
+    r = fn;
+    if (NODE_D(r.w) == ADDER_D_MAX) errbits |= ADDER_DEVERR_INTERNAL; /* needs an integration of 2^126 */
+  }
+  const uint32_t dtm_reached = r.dt >= a.dtm_f ? 1u : 0u; /* :394 */
 
   if (dtm_reached && !popped) {
     /* ---- pop_top_event (video.rs:1371-1374, :139-210): the root's best event leaves ------------------------------- */
@@ -205,27 +268,27 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
        * them in level records (a frozen pixel keeps no top in record 0). */
       const uint32_t last = len - 1u;
       const uint32_t x_in = f2u(r.integ) - v, dt_in = f2u(r.dt) - f2u(time); /* the root did not fire: it accumulated (:468-470) */
-      for (uint32_t k = 1;; k++) {
+      for (uint32_t kk = 1;; kk++) {
         Node nk;
-        if (k == last) { /* the fresh tail */
+        if (kk == last) { /* the fresh tail */
           nk.integ = 0.0f, nk.dt = 0.0f, nk.best_dt = 0.0f;
           nk.w = get_d_from_intensity(intensity);
-        } else if (k + 1u == last) {
+        } else if (kk + 1u == last) {
           nk = off_node(top_unpack(top), x_in, dt_in);
         } else {
-          nk = off_node(mem.load_rec(k), x_in, dt_in);
+          nk = off_node(mem.load_rec(kk), x_in, dt_in);
         }
         const bool fired = integrate_main(nk, intensity, time);
-        if (k == 1u) {
+        if (kk == 1u) {
           r = nk;
         } else {
           OffRec f;
           f.oi = f_bits(nk.integ), f.od = f_bits(nk.dt), f.best_dt = nk.best_dt, f.w = nk.w, f.pmin = kThrNever, f.pk = 0u;
-          mem.store_rec(k - 1u, f);
+          mem.store_rec(kk - 1u, f);
         }
-        if (fired || k == last) {
+        if (fired || kk == last) {
           if (!fired) errbits |= ADDER_DEVERR_INTERNAL;
-          new_len = k + 1u; /* levels 0 .. k-1 and a fresh tail */
+          new_len = kk + 1u; /* levels 0 .. kk-1 and a fresh tail */
           break;
         }
       }
@@ -233,59 +296,11 @@ ADDER_HD bool px_offset(const PxParams& a, uint32_t v, PxHeader& h, Node& n0, Of
   } else if (fired0) { /* :344-355: a fresh child, deeper nodes dropped */
     if (a.depth > 1u) new_len = 2; else errbits |= ADDER_DEVERR_DEPTH;
     root_new = true;
-  } else if (!popped && len > 1u) {
-    /* ---- the walk below the root (:340-390) in one step: the shallowest level whose threshold the root's integration
-     * has reached, else the fresh tail ------------------------------------------------------------------------------- */
-    const uint32_t x = f2u(r.integ), dt = f2u(r.dt);
-    const uint32_t x_in = x - v, dt_in = dt - f2u(time); /* the root did not fire: it accumulated (:468-470) */
-    if ((x | dt) >> 24) errbits |= ADDER_DEVERR_INTERNAL; /* beyond what offset_form_eligible admits */
-    uint32_t k;
-    OffRec q;
-    Node nk;
-    bool from_tail = true;
-    if (len > 2u) {
-      const OffRec t = top_unpack(top);
-      const uint32_t thr_t = off_thr(t.oi, t.w);
-      if (t.pmin <= x) { /* a level above the top has reached its threshold: the walk stops at the shallowest (:344-366),
-                          * which becomes the top (everything below it is dropped, its own record goes stale) */
-        k = t.pk;
-        q = mem.load_rec(k);
-        while (q.pmin <= x) {
-          k = q.pk;
-          q = mem.load_rec(k);
-        }
-        from_tail = false;
-      } else if (thr_t <= x) { /* the top fires where it is */
-        k = len - 2u;
-        q = t;
-        from_tail = false;
-      } else { /* nothing stored fires: the tail does, and the top is spilled to its record */
-        k = len - 1u;
-        mem.store_rec(len - 2u, t);
-        if (t.pmin <= thr_t) { /* ties go to the shallower level, like the walk */
-          q.pmin = t.pmin;
-          q.pk = t.pk;
-        } else {
-          q.pmin = thr_t;
-          q.pk = len - 2u;
-        }
-      }
-    } else { /* root and tail only */
-      k = 1u;
-      q.pmin = kThrNever;
-      q.pk = 0u;
-    }
-    if (from_tail) { /* PixelNode::new with its d from this intensity (:332-335) */
-      nk.integ = 0.0f, nk.dt = 0.0f, nk.best_dt = 0.0f;
-      nk.w = get_d_from_intensity(intensity);
-    } else {
-      nk = off_node(q, x_in, dt_in);
-    }
-    if (!integrate_main(nk, intensity, time)) errbits |= ADDER_DEVERR_INTERNAL;
-    q.oi = x - f2u(nk.integ);
-    q.od = dt - f2u(nk.dt);
-    q.best_dt = nk.best_dt;
-    q.w = nk.w;
+  } else if (level_fires) { /* the level that fired is the top now, with a fresh tail below it */
+    q.oi = x - f2u(fn.integ);
+    q.od = dt - f2u(fn.dt);
+    q.best_dt = fn.best_dt;
+    q.w = fn.w;
     top = top_pack(q, errbits);
     if (k + 1u >= a.depth) errbits |= ADDER_DEVERR_DEPTH;
     new_len = k + 2u > a.depth ? a.depth : k + 2u;
