@@ -1641,6 +1641,7 @@ struct adder_b200_framer {
   uint32_t out_stage_frames = 0;
   uint32_t* h_result = nullptr; /* pinned: [0..2] predicates, [3] error word */
   uint8_t* d_exact_lut = nullptr; /* [257] build_exact_lut(ref_interval) */
+  uint32_t ingest_grid = 0;       /* CTAs of framer_ingest_kernel (resident CTAs per SM x SMs), set at the first call */
 };
 
 namespace {
@@ -1653,10 +1654,10 @@ int framer_set_device(const adder_b200_framer* f) {
 /* status of the front frame -> tracker update (mode): queued on the framer's stream, nothing waits */
 int framer_refresh_queue(adder_b200_framer* f, int mode, const uint32_t* d_chunk_off) {
   const uint64_t chunk_px = (uint64_t)f->chunk_rows * f->w * f->c;
+  /* one launch: per-chunk status, then the tracker update by the CTA that finishes last (d_result[4] counts them) */
   adder::framer_chunk_status_kernel<<<f->n_chunks, 256, 0, f->stream>>>(f->d_ring_some, f->ring_frames, f->frame_px, chunk_px, f->d_forced,
-                                                                        f->frames_written, f->d_status);
-  adder::framer_tracker_kernel<<<1, 256, 0, f->stream>>>(f->d_tracker, f->d_status, d_chunk_off, f->n_chunks, mode, f->d_offset_max,
-                                                         f->frames_written, f->buffer_limit, f->d_result);
+                                                                        f->frames_written, f->d_status, f->d_result + 4, f->d_tracker, d_chunk_off,
+                                                                        mode, f->d_offset_max, f->buffer_limit, f->d_result);
   CU(cudaGetLastError());
   return ADDER_OK;
 }
@@ -1696,6 +1697,10 @@ int framer_ingest(adder_b200_framer* f, const adder_event_t* d_events, const uin
   a.absolute_t = f->time_mode == ADDER_TIME_ABSOLUTE_T ? 1u : 0u;
   a.practical_d_max = f->practical_d_max;
   a.exact_lut = f->d_exact_lut;
+  a.tpf_magic = adder::ref_magic_of(f->tpf);
+  a.ring_magic = adder::ref_magic_of(f->ring_frames);
+  a.ref_magic = adder::ref_magic_of(f->ref_interval);
+  a.chunk_rows_magic = adder::ref_magic_of(f->chunk_rows);
   a.buffer_limit = f->buffer_limit;
   a.px_state = f->d_px_state;
   a.ring_val = f->d_ring_val;
@@ -1705,9 +1710,13 @@ int framer_ingest(adder_b200_framer* f, const adder_event_t* d_events, const uin
   a.offset_max = f->d_offset_max;
   a.forced_frame = f->d_forced;
   a.err = f->d_err;
-  int sms = 0;
-  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device));
-  adder::framer_ingest_kernel<<<sms * 8, 256, 0, f->stream>>>(a);
+  if (!f->ingest_grid) { /* a persistent grid of exactly the resident CTAs: the grid-stride loop then runs as one wave */
+    int sms = 0, per_sm = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adder::framer_ingest_kernel, 256, 0));
+    f->ingest_grid = (uint32_t)(sms * std::max(per_sm, 1));
+  }
+  adder::framer_ingest_kernel<<<f->ingest_grid, 256, 0, f->stream>>>(a);
   CU(cudaGetLastError());
   if (int rc = framer_refresh_queue(f, 0, d_chunk_off)) return rc;
   if (!wait) return ADDER_OK; /* the caller asks later (adder_b200_framer_frame_ready) */
@@ -1767,7 +1776,8 @@ int adder_b200_framer_create(uint16_t width, uint16_t height, uint8_t channels, 
       CU(cudaMalloc(&f->d_forced, f->n_chunks * sizeof(long long)));
       CU(cudaMalloc(&f->d_tracker, f->n_chunks));
       CU(cudaMalloc(&f->d_status, f->n_chunks));
-      CU(cudaMalloc(&f->d_result, 4 * sizeof(uint32_t)));
+      CU(cudaMalloc(&f->d_result, 5 * sizeof(uint32_t))); /* [0..2] predicates, [4] the refresh kernel's CTA counter */
+      CU(cudaMemsetAsync(f->d_result, 0, 5 * sizeof(uint32_t), f->stream));
       CU(cudaMalloc(&f->d_err, sizeof(uint32_t)));
       CU(cudaMalloc(&f->d_off_stage, ((size_t)f->n_chunks + 1) * sizeof(uint32_t)));
       CU(cudaHostAlloc(&f->h_result, 4 * sizeof(uint32_t), cudaHostAllocDefault));

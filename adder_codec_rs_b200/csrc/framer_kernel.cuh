@@ -50,6 +50,10 @@ struct FramerArgs {
   long long* forced_frame; /* absolute frame whose filled_count was forced to full by buffer_limit, or -1 */
   uint32_t* err;           /* bit 0: an event reaches beyond the ring (the reference would grow its VecDeque) */
   const uint8_t* exact_lut; /* [257] build_exact_lut(ref_interval): the Intensity byte of exactly integral intensities */
+  /* ceil(2^64 / d) for the four divisors of the per-event work (ref_magic_of: 0 stands for d == 1): n / d for any n < 2^32 is
+   * mulhi_u32_u64(n, magic), exact (px_machine.cuh div_ref, checked in tests/test_px_shortcuts_host.py).  The divisions were
+   * 40 % of the ingest kernel's instructions (profiles/r02t_framer_*). */
+  unsigned long long tpf_magic, ring_magic, ref_magic, chunk_rows_magic;
 };
 
 __host__ __device__ __forceinline__ unsigned long long framer_state_ts(const uint4& s) { return (unsigned long long)s.x | ((unsigned long long)s.y << 32); }
@@ -62,13 +66,15 @@ __host__ __device__ __forceinline__ uint4 framer_state_pack(unsigned long long t
   return make_uint4((uint32_t)ts, (uint32_t)(ts >> 32), (uint32_t)p, (uint32_t)(p >> 32));
 }
 
-/* n / d and n % d for a 64-bit n that almost always fits 32 bits (timestamps, frame numbers): the 64-bit division is a
- * long dependent sequence, and this kernel is bound by latency */
-__device__ __forceinline__ unsigned long long udiv_fast(unsigned long long n, uint32_t d) {
-  return (n >> 32) == 0ull ? (unsigned long long)((uint32_t)n / d) : n / d;
+/* n / d and n % d for a 64-bit n that almost always fits 32 bits (timestamps, frame numbers): a multiplication by the
+ * divisor's magic number there, the 64-bit division (a long dependent sequence) only beyond */
+__device__ __forceinline__ unsigned long long udiv_fast(unsigned long long n, uint32_t d, unsigned long long magic) {
+  return (n >> 32) == 0ull ? (unsigned long long)(magic ? mulhi_u32_u64((uint32_t)n, magic) : (uint32_t)n) : n / d;
 }
-__device__ __forceinline__ uint32_t urem_fast(unsigned long long n, uint32_t d) {
-  return (n >> 32) == 0ull ? (uint32_t)n % d : (uint32_t)(n % d);
+__device__ __forceinline__ uint32_t urem_fast(unsigned long long n, uint32_t d, unsigned long long magic) {
+  if ((n >> 32) != 0ull) return (uint32_t)(n % d);
+  const uint32_t q = magic ? mulhi_u32_u64((uint32_t)n, magic) : (uint32_t)n;
+  return (uint32_t)n - q * d;
 }
 
 /* <u8 as FrameValue>::get_frame_value, SourceType::U8 (scale_intensity.rs:58-104, :262-270).  The Intensity view is the
@@ -95,9 +101,44 @@ __device__ __forceinline__ uint8_t framer_value_u8(uint32_t view_mode, uint32_t 
   return (uint8_t)(u > 255u ? 255u : u);
 }
 
+/* frame_idx_offsets of a chunk (`offset_max`) is raised to the furthest frame any of its pixels has reached.  Every
+ * pixel of a chunk reaches about the same frame, so per-event atomics on the chunk's one word were 70 % of the kernel's
+ * time in round 1, and "look first, then atomicMax" still 36 us of 96 (profiles/r02t_framer_knockout.txt): at the start
+ * of a call every event of the chunk sees the old value.  The events of a warp are consecutive in the stream, i.e. in one
+ * or two chunks: the warp reduces per chunk and one lane per chunk looks and updates.  All 32 lanes call this. */
+__device__ __forceinline__ void framer_raise_offset_max(long long* offset_max, bool active, uint32_t chunk, long long reach) {
+  const uint32_t lane = threadIdx.x & 31u;
+  active = active && reach >= 0;
+  uint32_t remaining = __ballot_sync(0xFFFFFFFFu, active);
+  while (remaining) { /* warp-uniform */
+    const int leader = __ffs((int)remaining) - 1;
+    const uint32_t c = __shfl_sync(0xFFFFFFFFu, chunk, leader);
+    const bool in = active && chunk == c;
+    long long m = in ? reach : -1;
+#pragma unroll
+    for (uint32_t o = 16; o; o >>= 1) {
+      const long long t = __shfl_xor_sync(0xFFFFFFFFu, m, o);
+      m = t > m ? t : m;
+    }
+    if ((int)lane == leader && m > __ldcg(&offset_max[c])) atomicMax(&offset_max[c], m);
+    remaining &= ~__ballot_sync(0xFFFFFFFFu, in);
+  }
+}
+
+/* Measured on 1080p gray noise, 1.93 M events per call (tools/framer_bench.py; profiles/r02t_framer_*): 96 us per call for ingest +
+ * refresh at the start of round 2's last session, 55 us now — the chunk's offset_max raised once per warp and chunk instead of
+ * looked at by every event (-36 us), the four divisions by runtime constants as multiplications (they were 40 % of the
+ * instructions), a grid of exactly the resident CTAs, status + tracker in one launch.  Tried and dropped: 2 or 4 events per
+ * thread in flight with phased loads (64 / 100+ registers: 66 / 100 us), the is-some byte of an AbsoluteT event's frame
+ * requested together with the state (+-0), 6 CTAs per SM at 40 registers (-6 %). */
 __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) {
   const uint32_t total = a.chunk_off[a.n_chunks];
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+  for (uint32_t jw = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); jw < total; jw += gridDim.x * blockDim.x) { /* warp-uniform */
+    const uint32_t j = jw + (threadIdx.x & 31u);
+    uint32_t chunk = 0u;
+    long long reach = -1;
+    bool worked = false;
+    if (j < total) do {
     /* this record and the one before it, requested together: the kernel is bound by the latency of dependent loads.
      * A run never crosses a chunk boundary (chunks are disjoint rows), so comparing coordinates is enough to find
      * its first event and its end: the chunk offsets are not needed for that. */
@@ -108,17 +149,16 @@ __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) 
       p1 = a.ev_words[3ull * (j - 1u) + 1ull];
     }
     const uint32_t x = w0 & 0xFFFFu, y = w0 >> 16, cc = w1 & 0xFFu;
-    const uint32_t chunk = y / a.chunk_rows;
-    if (chunk >= a.n_chunks) continue;                 /* malformed event: silently ignored, driver.rs:441-444 */
-    if (p0 == w0 && (p1 & 0xFFu) == cc) continue;      /* only the first event of a run of same-pixel events works */
+    chunk = a.chunk_rows_magic ? mulhi_u32_u64(y, a.chunk_rows_magic) : y;
+    if (chunk >= a.n_chunks) break;                    /* malformed event: silently ignored, driver.rs:441-444 */
+    if (p0 == w0 && (p1 & 0xFFu) == cc) break;         /* only the first event of a run of same-pixel events works */
     const uint32_t channel = cc == ADDER_C_NONE ? 0u : cc;
-    if (x >= a.W || y >= a.H || channel >= a.C) continue;
+    if (x >= a.W || y >= a.H || channel >= a.C) break;
     const unsigned long long gi = ((unsigned long long)y * a.W + x) * a.C + channel;
     const uint4 st = a.px_state[gi];
     unsigned long long running_ts = framer_state_ts(st);
     long long last_filled = framer_state_last_filled(st);
     uint32_t intensity = framer_state_intensity(st);
-    long long reach = -1;
     bool force = false;
     uint32_t e1 = w1, e2 = w2;
     for (uint32_t e = j;; e++) {
@@ -141,7 +181,7 @@ __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) 
         running_ts += t;
       }
       if (!skip) {
-        const long long fidx = (long long)udiv_fast(running_ts ? running_ts - 1ull : 0ull, a.tpf);
+        const long long fidx = (long long)udiv_fast(running_ts ? running_ts - 1ull : 0ull, a.tpf, a.tpf_magic);
         if (fidx > last_filled) { /* :1014 */
           if (d != ADDER_D_EMPTY) {
             if (a.codec_version >= 2u && a.absolute_t && a.view_mode != 3u) {
@@ -160,7 +200,7 @@ __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) 
               atomicOr(a.err, 1u);
               break;
             }
-            const unsigned long long slot = (unsigned long long)urem_fast((unsigned long long)fa, a.ring_frames) * a.frame_px + gi;
+            const unsigned long long slot = (unsigned long long)urem_fast((unsigned long long)fa, a.ring_frames, a.ring_magic) * a.frame_px + gi;
             if (!a.ring_some[slot]) {
               a.ring_some[slot] = 1;
               a.ring_val[slot] = (uint8_t)intensity;
@@ -168,7 +208,7 @@ __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) 
           }
         }
         if (a.codec_version >= 1u && a.framed_source) { /* :1094-1113 */
-          const uint32_t over = urem_fast(running_ts, a.ref_interval);
+          const uint32_t over = urem_fast(running_ts, a.ref_interval, a.ref_magic);
           if (over) running_ts += a.ref_interval - over; /* = (running_ts / ref_interval + 1) * ref_interval */
         }
         if (a.buffer_limit >= 0 && last_filled > a.frames_written + a.buffer_limit) force = true; /* :1115-1121 */
@@ -178,49 +218,34 @@ __global__ void __launch_bounds__(256) framer_ingest_kernel(const FramerArgs a) 
       e2 = n2;
     }
     a.px_state[gi] = framer_state_pack(running_ts, last_filled, intensity);
-    /* every pixel of a chunk reaches about the same frame, so nearly all of these would be atomics that change nothing
-     * on one contended word per chunk (they were 70 % of the kernel's time): look first.  The word only grows, so a
-     * stale read can at worst cause an atomic that was not needed. */
-    if (reach >= 0 && reach > __ldcg(&a.offset_max[chunk])) atomicMax(&a.offset_max[chunk], reach);
+    worked = true;
     if (force) a.forced_frame[chunk] = a.frames_written; /* deque index 0 == absolute frame frames_written */
+    } while (false);
+    framer_raise_offset_max(a.offset_max, worked, chunk, reach);
   }
 }
 
-/* Per-chunk status of absolute frame `fa`: status[k] = 1 when every pixel of chunk k is Some, or the chunk's
- * filled_count was forced to full for that frame (driver.rs:820-848 is_frame_filled, per chunk).  One CTA per chunk. */
-__global__ void __launch_bounds__(256) framer_chunk_status_kernel(const uint8_t* __restrict__ ring_some, uint32_t ring_frames,
-                                                                  unsigned long long frame_px, unsigned long long chunk_px,
-                                                                  const long long* __restrict__ forced_frame, long long fa, uint8_t* status) {
-  const uint32_t k = blockIdx.x;
-  const unsigned long long begin = (unsigned long long)k * chunk_px;
-  const unsigned long long end = begin + chunk_px < frame_px ? begin + chunk_px : frame_px;
-  const uint8_t* some = ring_some + (unsigned long long)(fa % (long long)ring_frames) * frame_px;
-  int empty = 0;
-  for (unsigned long long i = begin + threadIdx.x; i < end; i += blockDim.x) empty |= !some[i];
-  const int any_empty = __syncthreads_or(empty);
-  if (threadIdx.x == 0) status[k] = (!any_empty || forced_frame[k] == fa) ? 1 : 0;
-}
-
-/* chunk_filled_tracker bookkeeping + the two predicates the host needs (one CTA):
+/* chunk_filled_tracker bookkeeping + the two predicates the host needs (run by one CTA of 256 threads):
  *   mode 0, after ingest_events_events (driver.rs:598 `*chunk_filled = filled`): only chunks that had events take their status;
  *   mode 1, after a pop (:923-924): every chunk takes the status of the new front frame;
  *   mode 2, flush_frame_buffer (:633-680): all true when some chunk holds more than one frame, else tracker[0] = false.
  * result[0] = is_frame_0_filled() (:851-866), result[1] = is_frame_filled(0) (:820-848), result[2] = any chunk longer than one frame */
-__global__ void __launch_bounds__(256) framer_tracker_kernel(uint8_t* tracker, const uint8_t* status, const uint32_t* chunk_off, uint32_t n_chunks,
-                                                             int mode, const long long* offset_max, long long frames_written,
-                                                             long long buffer_limit, uint32_t* result) {
+__device__ __forceinline__ void framer_tracker_update(uint8_t* tracker, const uint8_t* status, const uint32_t* chunk_off, uint32_t n_chunks, int mode,
+                                                      const long long* offset_max, long long frames_written, long long buffer_limit, uint32_t* result) {
   int not_tracked = 0, not_filled = 0, over_limit = 0, multi = 0;
   for (uint32_t k = threadIdx.x; k < n_chunks; k += blockDim.x) {
-    const long long off = offset_max[k] > frames_written ? offset_max[k] : frames_written;
+    const long long om = __ldcg(&offset_max[k]);
+    const long long off = om > frames_written ? om : frames_written;
     const long long len = off - frames_written + 1; /* frames the chunk's VecDeque holds */
     if (len > 1) multi = 1;
+    const uint8_t st = __ldcg(&status[k]); /* written by other CTAs of this launch */
     if (mode == 0) {
-      if (chunk_off[k + 1u] > chunk_off[k]) tracker[k] = status[k];
+      if (chunk_off[k + 1u] > chunk_off[k]) tracker[k] = st;
     } else if (mode == 1) {
-      tracker[k] = status[k];
+      tracker[k] = st;
     }
     if (buffer_limit >= 0 && len > buffer_limit) over_limit = 1;
-    if (!status[k]) not_filled = 1;
+    if (!st) not_filled = 1;
   }
   multi = __syncthreads_or(multi);
   if (mode == 2) {
@@ -238,6 +263,46 @@ __global__ void __launch_bounds__(256) framer_tracker_kernel(uint8_t* tracker, c
     result[0] = (over_limit || !not_tracked) ? 1u : 0u;
     result[1] = not_filled ? 0u : 1u;
     result[2] = multi ? 1u : 0u;
+  }
+}
+
+/* Per-chunk status of absolute frame `fa`: status[k] = 1 when every pixel of chunk k is Some, or the chunk's
+ * filled_count was forced to full for that frame (driver.rs:820-848 is_frame_filled, per chunk).  One CTA per chunk, 128-bit
+ * loads where the chunk allows; the CTA that finishes last (a counter in device memory, reset for the next launch) runs the
+ * tracker update above, so a refresh is one launch instead of two. */
+__global__ void __launch_bounds__(256) framer_chunk_status_kernel(const uint8_t* __restrict__ ring_some, uint32_t ring_frames,
+                                                                  unsigned long long frame_px, unsigned long long chunk_px,
+                                                                  const long long* forced_frame, long long fa, uint8_t* status,
+                                                                  uint32_t* done_count, uint8_t* tracker, const uint32_t* chunk_off, int mode,
+                                                                  const long long* offset_max, long long buffer_limit, uint32_t* result) {
+  const uint32_t k = blockIdx.x, n_chunks = gridDim.x;
+  const unsigned long long begin = (unsigned long long)k * chunk_px;
+  const unsigned long long end = begin + chunk_px < frame_px ? begin + chunk_px : frame_px;
+  const uint8_t* some = ring_some + (unsigned long long)(fa % (long long)ring_frames) * frame_px;
+  int empty = 0;
+  if ((((uintptr_t)(some + begin)) & 15u) == 0u) { /* is-some bytes are 0 or 1: a 16-byte group is full iff every byte is 1 */
+    const unsigned long long n16 = (end - begin) >> 4;
+    const uint4* p = reinterpret_cast<const uint4*>(some + begin);
+    for (unsigned long long i = threadIdx.x; i < n16; i += blockDim.x) {
+      const uint4 v = __ldcg(p + i);
+      empty |= (v.x & v.y & v.z & v.w) != 0x01010101u;
+    }
+    for (unsigned long long i = begin + (n16 << 4) + threadIdx.x; i < end; i += blockDim.x) empty |= !__ldcg(some + i);
+  } else {
+    for (unsigned long long i = begin + threadIdx.x; i < end; i += blockDim.x) empty |= !__ldcg(some + i);
+  }
+  const int any_empty = __syncthreads_or(empty);
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) {
+    status[k] = (!any_empty || forced_frame[k] == fa) ? 1 : 0;
+    __threadfence();
+    s_last = atomicAdd(done_count, 1u) == n_chunks - 1u ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) { /* CTA-uniform */
+    __threadfence();
+    if (threadIdx.x == 0) *done_count = 0u;
+    framer_tracker_update(tracker, status, chunk_off, n_chunks, mode, offset_max, fa, buffer_limit, result);
   }
 }
 

@@ -41,6 +41,10 @@
 #ifndef ADDER_WO_PIPE
 #define ADDER_WO_PIPE 1 /* write-out: the read of record e+1 overlaps the store of record e */
 #endif
+#ifndef ADDER_WO_DENSE
+#define ADDER_WO_DENSE 0 /* 1: write-out with one lane per RECORD of a row instead of one lane per pixel looping over its records: parity-green,
+                          * -7 % (4K jitter c = 10) to -12 % (noise) on every workload (profiles/r02t_ab_wodense.txt): off */
+#endif
 #ifndef ADDER_PF_ROLLED
 #define ADDER_PF_ROLLED 0 /* 1: -128 instructions of code, more spills, -2 % .. +2 % (profiles/r02p_ab_pfrolled.txt): off */
 #endif
@@ -854,6 +858,70 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           }
         }
       }
+#if ADDER_WO_DENSE
+      /* One lane per RECORD of the row instead of one lane per pixel: a changed pixel gives up its whole stack at once
+       * (3-6 records on slowly varying scenes, up to depth + 2), and a loop over a pixel's records runs as long as the
+       * longest run of the row with two or three lanes in it, every record beyond the first a dependent read-back from the
+       * arena (profiles/r02t_*: 12-20 % of the stall samples).  Record j of the row belongs to the last pixel whose
+       * exclusive offset is <= j (offsets are in pixel order; a pixel without records shares its offset with its
+       * successor): five shuffle steps.  The row's arena reads are then independent and in flight together. */
+#pragma unroll 1
+      for (uint32_t r = 0; r < my_rows; r++) {
+        const uint32_t row = row_of(r);
+        const uint32_t q = 32u * row + lane;
+        const uint32_t inf = pinfo[q];
+        const uint32_t excl = inf & 1023u;
+        const uint32_t wtotal = __shfl_sync(kFull, excl + (inf >> 10), 31);
+        if (wtotal == 0u) continue;
+#pragma unroll 1
+        for (uint32_t j = lane; j - lane < wtotal; j += 32u) {
+          uint32_t p = 0;
+#pragma unroll
+          for (uint32_t s = 16; s; s >>= 1) {
+            const uint32_t ex = __shfl_sync(kFull, excl, p + s);
+            if (ex <= j) p += s;
+          }
+          const uint32_t ex_p = __shfl_sync(kFull, excl, p);
+          if (j < wtotal) {
+            const uint32_t e = j - ex_p, qp = 32u * row + p;
+            const uint32_t i = pstart + qp;
+            const uint32_t y = a.wc_magic ? mulhi_u32_u64(i, a.wc_magic) : i;
+            const uint32_t rem = i - y * a.WC;
+            uint32_t x = rem, c_p = ADDER_C_NONE;
+            if (a.C != 1u) {
+              x = __umulhi(rem, a.c_magic);
+              c_p = rem - x * a.C;
+            }
+            const uint32_t w0_p = x | ((y + a.row0) << 16);
+            const uint32_t base = prefix + s_wtot[pb][row];
+            uint32_t dd, tt;
+            if (e < S) {
+              tt = pslot_t[e * TILE + qp];
+              dd = pslot_d[e * TILE + qp];
+            } else {
+              const uint2 v = (arena + (unsigned long long)pb * a.arena_slots * TILE)[(unsigned long long)(e - S) * TILE + qp];
+              tt = v.x;
+              dd = v.y;
+            }
+            const unsigned long long rec = (unsigned long long)base + j;
+            if (rec < a.ev_cap) {
+              uint32_t* dst = ev_out + rec * 3ull;
+#if ADDER_EV_STREAM
+              __stcs(dst, w0_p);
+              __stcs(dst + 1, c_p | (dd << 8));
+              __stcs(dst + 2, tt);
+#else
+              dst[0] = w0_p;
+              dst[1] = c_p | (dd << 8);
+              dst[2] = tt;
+#endif
+            } else {
+              capbits = ADDER_DEVERR_CAPACITY;
+            }
+          }
+        }
+      }
+#else
 #pragma unroll 1
       for (uint32_t r = 0; r < my_rows; r++) {
         const uint32_t row = row_of(r);
@@ -923,6 +991,7 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
 #endif
         }
       }
+#endif /* ADDER_WO_DENSE */
       if (capbits) atomicOr(a.err, capbits);
     }
 
