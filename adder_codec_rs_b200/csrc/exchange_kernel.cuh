@@ -21,6 +21,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef ADDER_PUSH_UNROLL
+#define ADDER_PUSH_UNROLL 8 /* 128-bit stores whose loads a thread of the push kernel keeps in flight */
+#endif
+
 namespace adder {
 
 struct ExchangeRing { /* lives in the consumer's memory; all producers see the same addresses through their mappings */
@@ -60,7 +64,8 @@ struct PushArgs {
   uint32_t* err;        /* ADDER_DEVERR_CAPACITY when a frame does not fit the slot */
 };
 
-__global__ void __launch_bounds__(256) exchange_push_kernel(const PushArgs a) {
+/* at most 64 registers: a push CTA has to fit the slot an integrate CTA (64 registers x 256 threads) leaves free (launch_grid) */
+__global__ void __launch_bounds__(256, 4) exchange_push_kernel(const PushArgs a) {
   __shared__ unsigned long long s_prefix;
   __shared__ uint32_t s_total, s_ok;
   __shared__ unsigned long long s_part[256];
@@ -126,19 +131,21 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const PushArgs a) {
       if (rank == 0u && threadIdx.x < h) dst[threadIdx.x] = src[threadIdx.x];
       uint4* dst4 = reinterpret_cast<uint4*>(dst + h);
       const uint32_t* s4 = src + h;
-      /* the source is only word-aligned relative to dst: four 32-bit loads per 128-bit store; four stores' worth of loads
-       * are in flight per thread (a lone load-then-store chain moved 200 GB/s over NVLink, profiles/r02g n2) */
+      /* the source is only word-aligned relative to dst: four 32-bit loads per 128-bit store; kPushUnroll stores' worth of
+       * loads are in flight per thread (a lone load-then-store chain moved 200 GB/s over NVLink, profiles/r02g n2; four in
+       * flight 167 GB/s from ONE band's 16 CTAs on a dense stream, profiles/r02u n2 — the copy is bound by bytes in flight) */
+      constexpr int kPushUnroll = ADDER_PUSH_UNROLL;
       const unsigned long long T = (unsigned long long)gsize * blockDim.x;
       unsigned long long i = (unsigned long long)rank * blockDim.x + threadIdx.x;
-      for (; i + 3ull * T < n_vec; i += 4ull * T) {
-        uint4 v[4];
+      for (; i + (unsigned long long)(kPushUnroll - 1) * T < n_vec; i += (unsigned long long)kPushUnroll * T) {
+        uint4 v[kPushUnroll];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < kPushUnroll; u++) {
           const uint32_t* p = s4 + 4ull * (i + u * T);
           v[u] = make_uint4(__ldcs(p), __ldcs(p + 1), __ldcs(p + 2), __ldcs(p + 3));
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) dst4[i + u * T] = v[u];
+        for (int u = 0; u < kPushUnroll; u++) dst4[i + u * T] = v[u];
       }
       for (; i < n_vec; i += T) {
         const uint32_t* p = s4 + 4ull * i;
