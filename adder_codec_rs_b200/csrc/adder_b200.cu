@@ -616,9 +616,10 @@ int launch_gray(adder_b200_video* v, cudaStream_t stream, const uint8_t* d_rgb, 
     CU(cudaMemcpyToSymbolAsync(adder::c_gray_diag, diag, sizeof(diag), 0, cudaMemcpyHostToDevice, stream)); /* pageable source: staged before the call returns */
     v->gray_diag_ready = true;
   }
-  const uint32_t n_px = v->P * n_frames; /* frames back to back on both sides */
-  const uint32_t groups = (n_px + 3u) / 4u;
-  adder::rgb_to_gray_kernel<<<(groups + 255u) / 256u, 256, 0, stream>>>(d_rgb, d_gray, n_px);
+  const uint64_t n_px = (uint64_t)v->P * n_frames; /* frames back to back on both sides */
+  const uint64_t groups = (n_px + adder::kGrayPxPerThread - 1u) / adder::kGrayPxPerThread;
+  if ((groups + 255u) / 256u > 0x7FFFFFFFull) return fail(ADDER_ERR_INTERNAL, "launch_gray: batch not split by the caller");
+  adder::rgb_to_gray_kernel<<<(uint32_t)((groups + 255u) / 256u), 256, 0, stream>>>(d_rgb, d_gray, n_px);
   v->launches++;
   CU(cudaGetLastError());
   return ADDER_OK;
@@ -1111,7 +1112,7 @@ int launch_raw_encode(adder_b200_video* v, cudaStream_t stream, const adder_even
   if (n_max == 0) return ADDER_OK;
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v->device));
-  const uint64_t want = (n_max + adder::kRawThreads - 1) / adder::kRawThreads;
+  const uint64_t want = (n_max + adder::kRawChunk - 1) / adder::kRawChunk;
   const uint32_t blocks = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 8u);
   adder::raw_encode_kernel<<<blocks, adder::kRawThreads, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_events), d_n, n_max,
                                                                       raw_event_size(v), d_out);

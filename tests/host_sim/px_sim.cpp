@@ -15,6 +15,7 @@
 #include "../../adder_codec_rs_b200/csrc/px_machine.cuh"
 #include "../../adder_codec_rs_b200/csrc/px_offset.cuh"
 #include "../../adder_codec_rs_b200/csrc/gray_math.h"
+#include "../../adder_codec_rs_b200/csrc/raw_pack.h"
 
 namespace adder {
 int g_fast_div_ulps = 0;
@@ -224,6 +225,14 @@ uint32_t sim_gray_of(uint32_t c0, uint32_t c1, uint32_t c2) {
   uint8_t diag[256];
   adder::build_gray_diag(diag);
   return adder::gray_of(c0, c1, c2, diag);
+}
+/* raw_pack.h: n records (12-byte, n a multiple of 4) -> wire bytes, four at a time like a thread of raw_encode_kernel */
+void sim_raw_pack(const uint32_t* words, size_t n, uint32_t esize, uint8_t* out) {
+  for (size_t i = 0; i + 4 <= n; i += 4) {
+    uint32_t o[11] = {0};
+    if (esize == 11u) adder::raw_pack4<11u>(words + 3 * i, o); else adder::raw_pack4<9u>(words + 3 * i, o);
+    memcpy(out + i * esize, o, 4 * esize);
+  }
 }
 void sim_force_display(sim_video* v) { v->force_display = 1; }
 const adder_event_t* sim_events(const sim_video* v) { return v->events.data(); }

@@ -14,7 +14,8 @@ _DEPS = [os.path.join(_HERE, "px_sim.cpp"),
          os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "px_machine.cuh"),
          os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "px_offset.cuh"),
          os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "state_layout.h"),
-         os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "gray_math.h")]
+         os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "gray_math.h"),
+         os.path.join(_ROOT, "adder_codec_rs_b200", "csrc", "raw_pack.h")]
 _lib = None
 
 
@@ -43,6 +44,7 @@ def lib():
         L.sim_gray_check.argtypes = [C.POINTER(C.c_uint64)]
         L.sim_gray_of.restype = u32
         L.sim_gray_of.argtypes = [u32, u32, u32]
+        L.sim_raw_pack.argtypes = [vp, sz, u32, vp]
         L.sim_div_ref.restype = u32
         L.sim_div_ref.argtypes = [u32, u32]
         L.sim_frame_value_intensity.restype = u32

@@ -145,3 +145,27 @@ def test_gray_conversion_shortcut_is_exact_for_every_colour():
     want = O.handle_color(cols.reshape(1, -1, 3)).reshape(-1)
     got = np.array([L.sim_gray_of(int(a), int(b), int(c)) for a, b, c in cols], dtype=np.uint8)
     assert np.array_equal(got, want)
+
+
+def test_raw_pack4_matches_the_oracle_encoder():
+    """raw_pack.h (what a thread of raw_encode_kernel runs: four records -> 36 / 44 wire bytes on registers) against the oracle's
+    serialiser (RawOutput::ingest_event, raw/stream.rs:100-120), both record sizes, extreme field values included."""
+    L = sim_lib()
+    rng = np.random.default_rng(11)
+    n = 4096
+    ev = np.zeros(n, dtype=O.EVENT_DTYPE)
+    ev["x"] = rng.integers(0, 65536, n)
+    ev["y"] = rng.integers(0, 65536, n)
+    ev["c"] = rng.integers(0, 3, n)
+    ev["d"] = rng.integers(0, 256, n)
+    ev["t"] = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    ev[:4] = [(0x0102, 0x0304, 2, 7, 0, 0x0A0B0C0D), (65535, 0, 0, 255, 0, 0xFFFFFFFF), (0, 65535, 1, 0, 0, 0), (1, 2, 2, 0xFE, 0, 0x80000001)]
+    words = np.frombuffer(ev.tobytes(), dtype=np.uint32).copy()
+    for channels, esize in ((3, 11), (1, 9)):
+        e = ev.copy()
+        if channels == 1:
+            e["c"] = O.C_NONE
+            words = np.frombuffer(e.tobytes(), dtype=np.uint32).copy()
+        out = np.zeros(n * esize, dtype=np.uint8)
+        L.sim_raw_pack(words.ctypes.data, n, esize, out.ctypes.data)
+        assert out.tobytes() == O.raw_encode(e, channels), f"esize {esize}"
