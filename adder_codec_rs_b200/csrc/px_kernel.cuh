@@ -39,7 +39,7 @@
 
 /* build-time switches of the kernel (A/B builds: tools/gpu_ab.sh) */
 #ifndef ADDER_WO_PIPE
-#define ADDER_WO_PIPE 1 /* write-out: the read of record e+1 overlaps the store of record e */
+#define ADDER_WO_PIPE 1 /* write-out: the read of record e+1 overlaps the store of record e (2: e+1 and e+2 in flight, +-0: profiles/r02w_ab_wopipe2.txt) */
 #endif
 #ifndef ADDER_WO_DENSE
 #define ADDER_WO_DENSE 0 /* 1: write-out with one lane per RECORD of a row instead of one lane per pixel looping over its records: parity-green,
@@ -940,7 +940,28 @@ __global__ void __launch_bounds__(ADDER_TILE_PX, ADDER_MIN_CTAS) integrate_frame
           }
           const uint32_t w0 = x | ((y + a.row0) << 16);
           EventPark<S> park{const_cast<uint32_t*>(pslot_t) + q, const_cast<uint8_t*>(pslot_d) + q, arena + (unsigned long long)pb * a.arena_slots * TILE + q, TILE, a.arena_slots, nev, 0u};
-#if ADDER_WO_PIPE
+#if ADDER_WO_PIPE == 2
+          /* two reads in flight: records e+1 and e+2 are requested while record e is stored */
+          uint32_t dd, tt, d1 = 0, t1 = 0;
+          park.get(0u, dd, tt);
+          if (nev > 1u) park.get(1u, d1, t1);
+#pragma unroll 1
+          for (uint32_t e = 0; e < nev; e++) {
+            uint32_t d2 = 0, t2 = 0;
+            if (e + 2u < nev) park.get(e + 2u, d2, t2);
+            const unsigned long long rec = (unsigned long long)first + e;
+            if (rec < a.ev_cap) {
+              uint32_t* dst = ev_out + rec * 3ull;
+              __stcs(dst, w0);
+              __stcs(dst + 1, c | (dd << 8));
+              __stcs(dst + 2, tt);
+            } else {
+              capbits = ADDER_DEVERR_CAPACITY;
+            }
+            dd = d1, tt = t1;
+            d1 = d2, t1 = t2;
+          }
+#elif ADDER_WO_PIPE
           /* records beyond the shared-memory slot come back from global memory: the read of record
            * e+1 is in flight while record e is stored */
           uint32_t dd, tt;
