@@ -9,13 +9,18 @@
  * and times the two parts separately, so that the cost of the drop-in call behind consume() is known with the
  * vector build included (VERDICT r1 task 6).
  *
- *   usage: consumer <cfg1|cfg2|WxHxC:kind> <frames> <out.bin> [pageable]
+ * The vector build is a map over independent chunks; the reference runs that loop on its rayon pool (video.rs:677-734).  It is
+ * timed twice per frame: on one thread, and on a persistent pool of `threads` workers (chunk ci goes to worker ci % threads),
+ * which is what the Rust shim would do with the pool the reference already has.
+ *
+ *   usage: consumer <cfg1|cfg2|WxHxC:kind> <frames> <out.bin> [pageable|pinned] [threads]
  *     cfg1 = 640x480 gray gradient, Video::new defaults (c_thresh 10), dtm = ref = 255        (BASELINE configs[0])
  *     cfg2 = 1920x1080 RGB noise, crf 3, ref 255, dtm 7650                                     (BASELINE configs[1])
  *   out.bin: per frame  u32 n_chunks | u32 counts[n_chunks] | records[sum] (12 bytes each)   — compared with the oracle by
  *   tests/test_gpu_c_consumer.py.
  */
 #define _POSIX_C_SOURCE 200809L
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -41,6 +46,46 @@ typedef struct ref_event {
 _Static_assert(sizeof(ref_event) == 11, "packed Event is 11 bytes");
 
 typedef struct chunk_vec { ref_event* data; size_t len, cap; } chunk_vec;
+
+/* chunk ci of the frame: a fresh vector with_capacity(count) (the reference allocates one per chunk per frame, video.rs:693),
+ * records [first, first + count) mapped to the reference's Event */
+static void build_chunk(chunk_vec* cv, const adder_event_t* ev, size_t first, uint32_t count) {
+  free(cv->data);
+  cv->len = cv->cap = count;
+  cv->data = (ref_event*)malloc((cv->cap ? cv->cap : 1) * sizeof(ref_event));
+  for (size_t j = 0; j < cv->len; j++) {
+    const adder_event_t* r = &ev[first + j];
+    ref_event* e = &cv->data[j];
+    e->x = r->x;
+    e->y = r->y;
+    e->c_is_some = r->c != ADDER_C_NONE;
+    e->c = e->c_is_some ? r->c : 0;
+    e->d = r->d;
+    e->t = r->t;
+  }
+}
+
+/* a persistent pool (the stand-in for rayon's): the workers wait at a barrier for a frame, build their chunks, meet again */
+typedef struct pool {
+  pthread_barrier_t bar;
+  uint32_t n_threads, n_chunks;
+  chunk_vec* chunks;
+  const adder_event_t* ev;
+  const uint32_t* counts;
+  const size_t* first; /* exclusive prefix of counts */
+  int stop;
+} pool;
+typedef struct worker { pool* p; uint32_t id; } worker;
+static void* worker_main(void* arg) {
+  worker* w = (worker*)arg;
+  pool* p = w->p;
+  for (;;) {
+    pthread_barrier_wait(&p->bar); /* a frame is ready (or stop) */
+    if (p->stop) return NULL;
+    for (uint32_t ci = w->id; ci < p->n_chunks; ci += p->n_threads) build_chunk(&p->chunks[ci], p->ev, p->first[ci], p->counts[ci]);
+    pthread_barrier_wait(&p->bar); /* the frame's vectors are built */
+  }
+}
 
 static double now_s(void) {
   struct timespec ts;
@@ -86,6 +131,7 @@ int main(int argc, char** argv) {
   }
   const uint32_t n_frames = (uint32_t)atoi(argv[2]);
   const int pageable = argc > 4 && !strcmp(argv[4], "pageable");
+  const uint32_t n_threads = argc > 5 ? (uint32_t)atoi(argv[5]) : 0u; /* 0: no pool, the single-threaded build only */
   FILE* out = fopen(argv[3], "wb");
   if (!out) return 1;
   if (adder_b200_abi_version() != ADDER_B200_ABI_VERSION) {
@@ -115,9 +161,25 @@ int main(int argc, char** argv) {
   }
   uint32_t* counts = (uint32_t*)malloc(n_chunks * sizeof(uint32_t));
   chunk_vec* chunks = (chunk_vec*)calloc(n_chunks, sizeof(chunk_vec));
-  if (!frame || !ev || !counts || !chunks) return 2;
+  size_t* first = (size_t*)malloc(n_chunks * sizeof(size_t));
+  if (!frame || !ev || !counts || !chunks || !first) return 2;
+  pool pl;
+  pthread_t* threads = NULL;
+  worker* workers = NULL;
+  if (n_threads) {
+    memset(&pl, 0, sizeof(pl));
+    pl.n_threads = n_threads, pl.n_chunks = n_chunks, pl.chunks = chunks, pl.ev = ev, pl.counts = counts, pl.first = first;
+    if (pthread_barrier_init(&pl.bar, NULL, n_threads + 1u)) return 2;
+    threads = (pthread_t*)malloc(n_threads * sizeof(pthread_t));
+    workers = (worker*)malloc(n_threads * sizeof(worker));
+    if (!threads || !workers) return 2;
+    for (uint32_t t = 0; t < n_threads; t++) {
+      workers[t].p = &pl, workers[t].id = t;
+      if (pthread_create(&threads[t], NULL, worker_main, &workers[t])) return 2;
+    }
+  }
 
-  double t_call = 0.0, t_vec = 0.0;
+  double t_call = 0.0, t_vec = 0.0, t_vec_mt = 0.0;
   uint64_t total = 0;
   for (uint32_t f = 0; f < n_frames; f++) {
     make_frame(frame, kind, f, w, h, c); /* stands for the decoder; not timed */
@@ -128,21 +190,17 @@ int main(int argc, char** argv) {
     /* Vec<Vec<Event>>: one vector per chunk, with_capacity(count), records mapped to the reference's Event */
     size_t k = 0;
     for (uint32_t ci = 0; ci < n_chunks; ci++) {
-      chunk_vec* cv = &chunks[ci];
-      free(cv->data); /* the reference allocates a fresh Vec per chunk per frame (video.rs:693) */
-      cv->len = cv->cap = counts[ci];
-      cv->data = (ref_event*)malloc((cv->cap ? cv->cap : 1) * sizeof(ref_event));
-      for (size_t j = 0; j < cv->len; j++, k++) {
-        ref_event* e = &cv->data[j];
-        e->x = ev[k].x;
-        e->y = ev[k].y;
-        e->c_is_some = ev[k].c != ADDER_C_NONE;
-        e->c = e->c_is_some ? ev[k].c : 0;
-        e->d = ev[k].d;
-        e->t = ev[k].t;
-      }
+      first[ci] = k;
+      k += counts[ci];
     }
+    for (uint32_t ci = 0; ci < n_chunks; ci++) build_chunk(&chunks[ci], ev, first[ci], counts[ci]);
     const double t2 = now_s();
+    if (n_threads) { /* the same build on the pool (the vectors the test reads back are these) */
+      pthread_barrier_wait(&pl.bar);
+      pthread_barrier_wait(&pl.bar);
+    }
+    const double t3 = now_s();
+    t_vec_mt += t3 - t2;
     if (k != n) return 3;
     t_call += t1 - t0;
     t_vec += t2 - t1;
@@ -159,9 +217,20 @@ int main(int argc, char** argv) {
   }
   fclose(out);
   printf("{\"workload\": \"%s\", \"plane\": \"%ux%ux%u\", \"frames\": %u, \"events\": %llu, \"buffers\": \"%s\", "
-         "\"ms_per_call_integrate_matrix\": %.4f, \"ms_per_frame_vec_vec_event\": %.4f, \"ms_per_consume\": %.4f, \"mpx_per_s\": %.1f}\n",
+         "\"ms_per_call_integrate_matrix\": %.4f, \"ms_per_frame_vec_vec_event\": %.4f, \"ms_per_consume\": %.4f, \"mpx_per_s\": %.1f, "
+         "\"pool_threads\": %u, \"ms_per_frame_vec_vec_event_pool\": %.4f, \"ms_per_consume_pool\": %.4f, \"mpx_per_s_pool\": %.1f}\n",
          argv[1], w, h, c, n_frames, (unsigned long long)total, pageable ? "pageable" : "page-locked", 1e3 * t_call / n_frames,
-         1e3 * t_vec / n_frames, 1e3 * (t_call + t_vec) / n_frames, (double)P * n_frames / (t_call + t_vec) / 1e6);
+         1e3 * t_vec / n_frames, 1e3 * (t_call + t_vec) / n_frames, (double)P * n_frames / (t_call + t_vec) / 1e6, n_threads,
+         1e3 * t_vec_mt / n_frames, 1e3 * (t_call + t_vec_mt) / n_frames, n_threads ? (double)P * n_frames / (t_call + t_vec_mt) / 1e6 : 0.0);
+  if (n_threads) {
+    pl.stop = 1;
+    pthread_barrier_wait(&pl.bar);
+    for (uint32_t t = 0; t < n_threads; t++) pthread_join(threads[t], NULL);
+    pthread_barrier_destroy(&pl.bar);
+    free(threads);
+    free(workers);
+  }
+  free(first);
   for (uint32_t ci = 0; ci < n_chunks; ci++) free(chunks[ci].data);
   free(chunks);
   free(counts);

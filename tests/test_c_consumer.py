@@ -22,7 +22,7 @@ def _build(tmp_path):
     A.build()
     exe = str(tmp_path / "consumer")
     libdir = os.path.join(ROOT, "adder_codec_rs_b200")
-    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), SRC,
+    subprocess.run(["gcc", "-std=c11", "-O2", "-pthread", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), SRC,
                     "-L", libdir, "-ladder_b200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
     return exe
 
@@ -54,7 +54,7 @@ def _read_out(path, n_frames):
 def test_c_consumer_runs_cfg1_and_matches_the_oracle(tmp_path):
     exe = _build(tmp_path)
     out = str(tmp_path / "cfg1.bin")
-    r = subprocess.run([exe, "cfg1", "30", out], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, "cfg1", "30", out, "pinned", "3"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     stats = json.loads(r.stdout.strip().splitlines()[-1])
     ov = O.Video(640, 480, 1, O.MODE_FRAME_PERFECT)
@@ -75,7 +75,7 @@ def test_c_consumer_cost_of_one_consume_at_1080p_rgb(tmp_path):
     compared with the oracle as well)."""
     exe = _build(tmp_path)
     out = str(tmp_path / "cfg2.bin")
-    r = subprocess.run([exe, "cfg2", "12", out], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, "cfg2", "12", out, "pinned", str(len(os.sched_getaffinity(0)))], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     stats = json.loads(r.stdout.strip().splitlines()[-1])
     ov = O.Video(1920, 1080, 3, O.MODE_FRAME_PERFECT)
