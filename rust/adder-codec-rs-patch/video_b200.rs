@@ -9,6 +9,7 @@
 
 use adder_b200_sys as ffi;
 use adder_codec_core::{Coord, Event, PlaneSize};
+use rayon::prelude::*; // already a dependency of adder-codec-rs (video.rs:677-734)
 use std::ffi::CStr;
 
 use crate::transcoder::source::video::SourceError;
@@ -72,19 +73,24 @@ impl B200Video {
         }
         check(rc)?;
         let records = unsafe { std::slice::from_raw_parts(self.ev_buf, n as usize) };
-        // 12-byte records -> Event; the packed Option<u8> layout of Event is never aliased.
-        // (rayon over chunks here if the serial map shows up: each chunk's slice is independent.)
-        let mut out = Vec::with_capacity(self.n_chunks);
+        // 12-byte records -> Event; the packed Option<u8> layout of Event is never aliased.  One vector per chunk, built on
+        // the rayon pool the reference already runs this loop on (video.rs:677-734): the chunks' slices are independent.
+        // Measured by the C consumer at 1080p RGB (5.6 M events): 13.3 ms on one thread, 2.2 ms on a pool of 16
+        // (profiles/r02x_c_consumer_1080p.json).
+        let mut first = Vec::with_capacity(self.n_chunks);
         let mut at = 0usize;
         for &len in &self.counts {
-            let len = len as usize;
-            out.push(records[at..at + len].iter().map(|e| Event {
+            first.push(at);
+            at += len as usize;
+        }
+        let counts = &self.counts;
+        let out: Vec<Vec<Event>> = (0..self.n_chunks).into_par_iter().map(|ci| {
+            records[first[ci]..first[ci] + counts[ci] as usize].iter().map(|e| Event {
                 coord: Coord { x: e.x, y: e.y, c: if e.c == ffi::ADDER_C_NONE { None } else { Some(e.c) } },
                 d: e.d,
                 t: e.t,
-            }).collect());
-            at += len;
-        }
+            }).collect()
+        }).collect();
         Ok(out)
     }
 

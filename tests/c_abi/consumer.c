@@ -160,15 +160,16 @@ int main(int argc, char** argv) {
     CHECK(adder_b200_host_alloc(cap * sizeof(adder_event_t), (void**)&ev));
   }
   uint32_t* counts = (uint32_t*)malloc(n_chunks * sizeof(uint32_t));
-  chunk_vec* chunks = (chunk_vec*)calloc(n_chunks, sizeof(chunk_vec));
+  chunk_vec* chunks = (chunk_vec*)calloc(n_chunks, sizeof(chunk_vec));      /* built by the main thread */
+  chunk_vec* chunks_pool = (chunk_vec*)calloc(n_chunks, sizeof(chunk_vec)); /* built by the pool: every vector is allocated and freed by the same worker */
   size_t* first = (size_t*)malloc(n_chunks * sizeof(size_t));
-  if (!frame || !ev || !counts || !chunks || !first) return 2;
+  if (!frame || !ev || !counts || !chunks || !chunks_pool || !first) return 2;
   pool pl;
   pthread_t* threads = NULL;
   worker* workers = NULL;
   if (n_threads) {
     memset(&pl, 0, sizeof(pl));
-    pl.n_threads = n_threads, pl.n_chunks = n_chunks, pl.chunks = chunks, pl.ev = ev, pl.counts = counts, pl.first = first;
+    pl.n_threads = n_threads, pl.n_chunks = n_chunks, pl.chunks = chunks_pool, pl.ev = ev, pl.counts = counts, pl.first = first;
     if (pthread_barrier_init(&pl.bar, NULL, n_threads + 1u)) return 2;
     threads = (pthread_t*)malloc(n_threads * sizeof(pthread_t));
     workers = (worker*)malloc(n_threads * sizeof(worker));
@@ -195,7 +196,7 @@ int main(int argc, char** argv) {
     }
     for (uint32_t ci = 0; ci < n_chunks; ci++) build_chunk(&chunks[ci], ev, first[ci], counts[ci]);
     const double t2 = now_s();
-    if (n_threads) { /* the same build on the pool (the vectors the test reads back are these) */
+    if (n_threads) { /* the same build on the pool, into its own set of vectors (the ones the test reads back) */
       pthread_barrier_wait(&pl.bar);
       pthread_barrier_wait(&pl.bar);
     }
@@ -208,9 +209,10 @@ int main(int argc, char** argv) {
     /* what the test compares: read back from the per-chunk vectors, not from the library's buffer */
     fwrite(&n_chunks, 4, 1, out);
     fwrite(counts, 4, n_chunks, out);
+    const chunk_vec* built = n_threads ? chunks_pool : chunks;
     for (uint32_t ci = 0; ci < n_chunks; ci++)
-      for (size_t j = 0; j < chunks[ci].len; j++) {
-        const ref_event* e = &chunks[ci].data[j];
+      for (size_t j = 0; j < built[ci].len; j++) {
+        const ref_event* e = &built[ci].data[j];
         adder_event_t r = {e->x, e->y, e->c_is_some ? e->c : (uint8_t)ADDER_C_NONE, e->d, 0, e->t};
         fwrite(&r, sizeof(r), 1, out);
       }
@@ -231,8 +233,9 @@ int main(int argc, char** argv) {
     free(workers);
   }
   free(first);
-  for (uint32_t ci = 0; ci < n_chunks; ci++) free(chunks[ci].data);
+  for (uint32_t ci = 0; ci < n_chunks; ci++) free(chunks[ci].data), free(chunks_pool[ci].data);
   free(chunks);
+  free(chunks_pool);
   free(counts);
   if (pageable) {
     free(frame);
