@@ -45,6 +45,11 @@
 #define ADDER_WO_DENSE 0 /* 1: write-out with one lane per RECORD of a row instead of one lane per pixel looping over its records: parity-green,
                           * -7 % (4K jitter c = 10) to -12 % (noise) on every workload (profiles/r02t_ab_wodense.txt): off */
 #endif
+#ifndef ADDER_REC_LTC64
+#define ADDER_REC_LTC64 1 /* level-record loads of the offset form carry the L2::64B prefetch-size hint (LDG.E.ENL2.LTC64B.256): an isolated
+                           * 32-byte record no longer drags a 128-byte line out of DRAM.  Aged 8K stacks: DRAM reads 74.9 -> 63.0 GB per 32-frame
+                           * launch, 996 -> 980 us per frame; 4K jitter +-0 (profiles/r02x_ab_ltc64.txt) */
+#endif
 #ifndef ADDER_PF_ROLLED
 #define ADDER_PF_ROLLED 0 /* 1: -128 instructions of code, more spills, -2 % .. +2 % (profiles/r02p_ab_pfrolled.txt): off */
 #endif
@@ -218,7 +223,18 @@ struct OffNodes {
   __device__ __forceinline__ OffRec load_rec(uint32_t k) {
     n_loads++;
     uint4 a, b;
+#if ADDER_REC_LTC64
+    /* a level record is one isolated 32-byte sector: ask L2 to fetch 64 bytes around it instead of its default 128 */
+    const uint4* q = p + (unsigned long long)k * stride;
+    if (kCoherent && !ADDER_STATE_L1)
+      asm volatile("ld.relaxed.gpu.global.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(q) : "memory");
+    else
+      asm volatile("ld.global.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(q) : "memory");
+#else
     ld_state256<kCoherent>(p + (unsigned long long)k * stride, a, b);
+#endif
     OffRec r;
     r.oi = a.x, r.od = a.y, r.best_dt = __uint_as_float(a.z), r.w = a.w, r.pmin = b.x, r.pk = b.y;
     return r;
