@@ -50,6 +50,9 @@
                            * 32-byte record no longer drags a 128-byte line out of DRAM.  Aged 8K stacks: DRAM reads 74.9 -> 63.0 GB per 32-frame
                            * launch, 996 -> 980 us per frame; 4K jitter +-0 (profiles/r02x_ab_ltc64.txt) */
 #endif
+#ifndef ADDER_NODE_LTC64
+#define ADDER_NODE_LTC64 0 /* 1: the eager form's deep-level loads with the L2::64B hint: no change in DRAM bytes or time (prefetch_levels has pulled the lines already; profiles/r02x_ab_eager_ltc64.txt) */
+#endif
 #ifndef ADDER_PF_ROLLED
 #define ADDER_PF_ROLLED 0 /* 1: -128 instructions of code, more spills, -2 % .. +2 % (profiles/r02p_ab_pfrolled.txt): off */
 #endif
@@ -135,7 +138,17 @@ struct GlobalNodes {
   __device__ __forceinline__ uint4* at(uint32_t k) const { return p + (unsigned long long)(k >> 1) * stride + (k & 1u); }
   __device__ __forceinline__ Node load(uint32_t k) {
     n_loads++;
+#if ADDER_NODE_LTC64
+    /* levels beyond the first record are reached by some pixels of a row only: isolated sectors, fetched with the L2::64B hint
+     * like the offset form's level records (ADDER_REC_LTC64) */
+    uint4 v;
+    if (kCoherent && !ADDER_STATE_L1)
+      asm volatile("ld.relaxed.gpu.global.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(at(k)) : "memory");
+    else
+      asm volatile("ld.global.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(at(k)) : "memory");
+#else
     const uint4 v = ld_state<kCoherent>(at(k));
+#endif
     Node n;
     n.integ = __uint_as_float(v.x);
     n.dt = __uint_as_float(v.y);
