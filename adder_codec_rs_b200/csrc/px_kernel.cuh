@@ -53,6 +53,9 @@
 #ifndef ADDER_NODE_LTC64
 #define ADDER_NODE_LTC64 0 /* 1: the eager form's deep-level loads with the L2::64B hint: no change in DRAM bytes or time (prefetch_levels has pulled the lines already; profiles/r02x_ab_eager_ltc64.txt) */
 #endif
+#ifndef ADDER_ROW_LTC256
+#define ADDER_ROW_LTC256 0 /* 1: the row loop's record-0 loads with the L2::256B prefetch-size hint: +-0 on every workload (profiles/r02y_ab_ltc256.txt) */
+#endif
 #ifndef ADDER_PF_ROLLED
 #define ADDER_PF_ROLLED 0 /* 1: -128 instructions of code, more spills, -2 % .. +2 % (profiles/r02p_ab_pfrolled.txt): off */
 #endif
@@ -115,6 +118,19 @@ __device__ __forceinline__ uint2 ld_state(const uint2* p) { return (kCoherent &&
 /* root and first child of a pixel: one 32-byte record, one 256-bit access */
 template <bool kCoherent>
 __device__ __forceinline__ void ld_state256(const uint4* p, uint4& a, uint4& b) {
+#if ADDER_ROW_LTC256
+  if (kCoherent && !ADDER_STATE_L1)
+    asm volatile("ld.relaxed.gpu.global.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p)
+                 : "memory");
+  else
+    asm volatile("ld.global.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p)
+                 : "memory");
+  return;
+#endif
   if (kCoherent && !ADDER_STATE_L1)
     asm volatile("ld.relaxed.gpu.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
