@@ -1297,11 +1297,14 @@ int adder_b200_expand_compact(uint16_t width, uint16_t rows, uint8_t channels, u
     const uint64_t P = (uint64_t)width * rows * channels, WC = (uint64_t)width * channels;
     const bool dense = 4ull * n_events > P;
     const uint32_t T = std::max<uint32_t>(1u, std::min<uint32_t>(n_threads ? n_threads : 1u, 256u));
-    auto put = [&](adder_event_t& e, uint64_t idx, const uint8_t* dt) {
-      const uint64_t y = idx / WC, rem = idx - y * WC;
-      e.x = (uint16_t)(rem / channels);
+    /* P < 2^40 in principle (u16 x u16 x u8), but an index of the sparse form is a u32 and the dense form walks pixels with
+     * running coordinates, so no 64-bit division is on either path */
+    const uint32_t WC32 = (uint32_t)WC, C32 = channels;
+    auto put = [&](adder_event_t& e, uint32_t idx, const uint8_t* dt) {
+      const uint32_t y = idx / WC32, rem = idx - y * WC32, x = rem / C32;
+      e.x = (uint16_t)x;
       e.y = (uint16_t)(y + row0);
-      e.c = channels == 1 ? (uint8_t)ADDER_C_NONE : (uint8_t)(rem % channels);
+      e.c = channels == 1 ? (uint8_t)ADDER_C_NONE : (uint8_t)(rem - x * C32);
       e.d = dt[0];
       e.reserved = 0;
       memcpy(&e.t, dt + 1, 4);
@@ -1337,11 +1340,29 @@ int adder_b200_expand_compact(uint16_t width, uint16_t rows, uint8_t channels, u
       if (first[T] != n_events) return fail(ADDER_ERR_BAD_PARAMS, "compact block: the count bytes add up to %llu events, not %llu",
                                             (unsigned long long)first[T], (unsigned long long)n_events);
       const uint8_t* body = block + P;
-      auto work = [&](uint32_t t) {
+      auto work = [&](uint32_t t) { /* raster walk with running coordinates: one division per thread, none per event */
         const uint64_t a = P * t / T, b = P * (t + 1) / T;
         uint64_t k = first[t];
-        for (uint64_t i = a; i < b; i++)
-          for (uint32_t j = block[i]; j; j--, k++) put(events_out[k], i, body + 5ull * k);
+        uint32_t y = (uint32_t)(a / WC), x = (uint32_t)((a - (uint64_t)y * WC) / channels), c = (uint32_t)(a - (uint64_t)y * WC - (uint64_t)x * channels);
+        static_assert(sizeof(adder_event_t) == 12, "a record is three little-endian words: x | y << 16, c | d << 8, t");
+        for (uint64_t i = a; i < b; i++) {
+          if (const uint32_t n_here = block[i]) {
+            const uint32_t w0 = x | (((y + row0) & 0xFFFFu) << 16), cw = channels == 1 ? (uint32_t)ADDER_C_NONE : c;
+            for (uint32_t j = n_here; j; j--, k++) {
+              const uint8_t* dt = body + 5ull * k;
+              uint32_t* rec = reinterpret_cast<uint32_t*>(events_out + k); /* 4-byte aligned: three word stores */
+              uint32_t t;
+              memcpy(&t, dt + 1, 4);
+              rec[0] = w0;
+              rec[1] = cw | ((uint32_t)dt[0] << 8);
+              rec[2] = t;
+            }
+          }
+          if (++c == C32) {
+            c = 0;
+            if (++x == width) x = 0, y++;
+          }
+        }
       };
       for (uint32_t t = 1; t < T; t++) pool.emplace_back(work, t);
       work(0);
